@@ -1,0 +1,206 @@
+// ORACLE (test infrastructure, not product code): CPU restatement of the two-adic DFT / coset LDE
+// the reference obtains from Plonky3's `p3_dft::Radix2DitParallel` (type alias src/types.rs:200;
+// call sites src/prover.rs:440,650,716 and, inside `TwoAdicFriPcs::commit`, src/prover.rs:350,419,
+// src/system.rs:193). p3-dft 0.5.1 (rev e9d75614) is not vendored in the reference, so this restates
+// its published conventions:
+//   dft(f)_k = sum_j f_j w^{jk},  w = two_adic_generator(log n)
+//   coset_lde_batch(evals, added_bits, shift) = idft -> *shift^j -> zero-pad -> dft
+//   Radix2DitParallel returns a bit-reversed view; `.bit_reverse_rows()` is the raw storage in which
+//   natural index k lives at row rev(k).
+// Field arithmetic is exact, so any correct DFT is bit-identical to the reference's; only the
+// storage order is a convention, and it is pinned by the reference's own relational test
+// (src/prover.rs:975-999), mirrored in tests/test_oracle_dft.py.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may use this file.
+#pragma once
+#include "../multi_stark_b200/host/goldilocks.hpp"
+#include <map>
+#include <mutex>
+#include <memory>
+#include <algorithm>
+
+namespace orc {
+using namespace msh;
+
+// Twiddle table w_N^i, i < N/2, cached per log N.
+inline const std::vector<Fp>& twiddles(unsigned log_n) {
+    static std::mutex mu;
+    static std::map<unsigned, std::unique_ptr<std::vector<Fp>>> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto& slot = cache[log_n];
+    if (!slot) {
+        size_t half = log_n == 0 ? 0 : (size_t(1) << (log_n - 1));
+        slot = std::make_unique<std::vector<Fp>>(half);
+        Fp w = two_adic_generator(log_n), acc = Fp::one();
+        for (size_t i = 0; i < half; i++) { (*slot)[i] = acc; acc *= w; }
+    }
+    return *slot;
+}
+
+// One radix-2 decimation-in-frequency layer on rows [base, base+2*half) of a row-major matrix.
+static inline void dif_layer_block(Fp* m, size_t width, size_t base, size_t half, const Fp* tw, size_t tw_stride) {
+    for (size_t j = 0; j < half; j++) {
+        Fp t = tw[j * tw_stride];
+        Fp* a = m + (base + j) * width;
+        Fp* b = m + (base + j + half) * width;
+        for (size_t c = 0; c < width; c++) {
+            Fp x = a[c], y = b[c];
+            a[c] = x + y;
+            b[c] = (x - y) * t;
+        }
+    }
+}
+
+// In-place forward DFT of every column; output left in BIT-REVERSED row order
+// (row rev(k) holds dft_k) -- i.e. `dft.dft_batch(m).bit_reverse_rows()` (src/prover.rs:650,716).
+inline void dft_batch_bitrev_inplace(Fp* m, size_t n, size_t width) {
+    if (n <= 1) return;
+    unsigned log_n = log2_strict(n);
+    const std::vector<Fp>& tw = twiddles(log_n);
+    // Layers whose blocks exceed the cache-sized chunk are streamed over the whole matrix; the
+    // remaining layers are finished chunk by chunk so each chunk stays cache resident.
+    size_t chunk_rows = 1;
+    while (chunk_rows < n && chunk_rows * 2 * width * sizeof(Fp) <= (size_t(1) << 18)) chunk_rows *= 2;
+    size_t block = n;
+    for (; block > chunk_rows; block >>= 1) {
+        size_t half = block >> 1, stride = n / block;
+        long long nbf = (long long)(n / 2);
+#pragma omp parallel for schedule(static)
+        for (long long b = 0; b < nbf; b++) {
+            size_t blk = (size_t)b / half, j = (size_t)b % half;
+            Fp t = tw[j * stride];
+            Fp* a = m + (blk * block + j) * width;
+            Fp* bb = a + half * width;
+            for (size_t c = 0; c < width; c++) {
+                Fp x = a[c], y = bb[c];
+                a[c] = x + y;
+                bb[c] = (x - y) * t;
+            }
+        }
+    }
+    long long nchunks = (long long)(n / block);
+    size_t top = block;
+#pragma omp parallel for schedule(static)
+    for (long long ch = 0; ch < nchunks; ch++) {
+        for (size_t blk = top; blk >= 2; blk >>= 1) {
+            size_t half = blk >> 1, stride = n / blk;
+            for (size_t base = (size_t)ch * top; base < (size_t)(ch + 1) * top; base += blk)
+                dif_layer_block(m, width, base, half, tw.data(), stride);
+        }
+    }
+}
+
+// Out-of-place row permutation by bit reversal.
+inline Matrix bit_reverse_rows(const Matrix& in) {
+    size_t n = in.height(), w = in.width;
+    Matrix out(n, w);
+    if (n == 0) return out;
+    unsigned log_n = log2_strict(n);
+    long long nn = (long long)n;
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < nn; i++) {
+        size_t r = reverse_bits_len((size_t)i, log_n);
+        std::copy(in.row(i), in.row(i) + w, out.row(r));
+    }
+    return out;
+}
+
+// dft_batch in natural order.
+inline Matrix dft_batch(Matrix m) {
+    dft_batch_bitrev_inplace(m.values.data(), m.height(), m.width);
+    return bit_reverse_rows(m);
+}
+
+// idft(f)_j = n^{-1} dft(f)_{(n-j) mod n}  (stated at src/prover.rs:620-622).
+inline Matrix idft_batch(Matrix m) {
+    size_t n = m.height(), w = m.width;
+    if (n == 0) return m;
+    unsigned log_n = log2_strict(n);
+    dft_batch_bitrev_inplace(m.values.data(), n, w);
+    Matrix out(n, w);
+    Fp n_inv = Fp((u64)n).inverse();
+    long long nn = (long long)n;
+#pragma omp parallel for schedule(static)
+    for (long long j = 0; j < nn; j++) {
+        size_t src = reverse_bits_len((n - (size_t)j) & (n - 1), log_n);
+        const Fp* s = m.row(src);
+        Fp* d = out.row(j);
+        for (size_t c = 0; c < w; c++) d[c] = s[c] * n_inv;
+    }
+    return out;
+}
+
+// Multiply row j by shift^j.
+inline void scale_rows_by_powers(Matrix& m, Fp shift) {
+    size_t n = m.height(), w = m.width;
+    const size_t CH = 512;
+    long long nch = (long long)((n + CH - 1) / CH);
+#pragma omp parallel for schedule(static)
+    for (long long ch = 0; ch < nch; ch++) {
+        Fp weight = shift.pow((u64)ch * CH);
+        for (size_t r = (size_t)ch * CH; r < std::min(n, (size_t)(ch + 1) * CH); r++) {
+            Fp* row = m.row(r);
+            for (size_t c = 0; c < w; c++) row[c] *= weight;
+            weight *= shift;
+        }
+    }
+}
+
+// coset_dft_batch(coeffs, shift): evaluations at shift * w^k, natural order.
+inline Matrix coset_dft_batch(Matrix coeffs, Fp shift) {
+    scale_rows_by_powers(coeffs, shift);
+    return dft_batch(std::move(coeffs));
+}
+// coset_idft_batch(evals, shift): coefficients of the polynomial with those evaluations on shift*H.
+inline Matrix coset_idft_batch(Matrix evals, Fp shift) {
+    Matrix c = idft_batch(std::move(evals));
+    scale_rows_by_powers(c, shift.inverse());
+    return c;
+}
+
+// `lde_from_shifted_coefficients` (src/prover.rs:709-717): zero-pad to n << added_bits, one DFT,
+// raw bit-reversed storage.
+inline Matrix lde_from_shifted_coefficients(Matrix coeffs, unsigned added_bits) {
+    size_t n = coeffs.height(), w = coeffs.width;
+    coeffs.values.resize((n << added_bits) * w, Fp::zero());
+    dft_batch_bitrev_inplace(coeffs.values.data(), n << added_bits, w);
+    return coeffs;
+}
+
+// What `TwoAdicFriPcs::commit` stores per matrix (src/prover.rs:681-692):
+// coset_lde_batch(evals, log_blowup, shift).bit_reverse_rows(): stored[i] = P(shift * w_{nB}^{rev(i)}).
+inline Matrix coset_lde_batch_bitrev(Matrix evals, unsigned added_bits, Fp shift) {
+    Matrix c = idft_batch(std::move(evals));
+    scale_rows_by_powers(c, shift);
+    return lde_from_shifted_coefficients(std::move(c), added_bits);
+}
+
+// `shifted_quotient_slices` (src/prover.rs:631-679): from the quotient's evaluations on the coset
+// GENERATOR*H_{nq} (nq rows, d columns, natural order) to the n x (q*d) matrix of slice coefficients
+// with the committed LDE's GENERATOR^r row pre-scale folded in:
+//   out[r][k*d+c] = S[rev((N-(k*n+r)) mod N)][c] * N^{-1} * GENERATOR^{-k*n},  S = raw DFT storage.
+inline Matrix shifted_quotient_slices(Matrix quotient_evals, size_t quotient_degree) {
+    size_t d = quotient_evals.width, big = quotient_evals.height();
+    unsigned log_big = log2_strict(big);
+    size_t n = big / quotient_degree, width = quotient_degree * d;
+    dft_batch_bitrev_inplace(quotient_evals.values.data(), big, d);
+    const Matrix& storage = quotient_evals;
+    Fp n_inv = Fp((u64)big).inverse();
+    Fp step = Fp(GL_GENERATOR).pow((u64)n).inverse();
+    std::vector<Fp> weights(quotient_degree);
+    Fp acc = Fp::one();
+    for (size_t k = 0; k < quotient_degree; k++) { weights[k] = acc * n_inv; acc *= step; }
+    Matrix out(n, width);
+    long long nn = (long long)n;
+#pragma omp parallel for schedule(static)
+    for (long long row = 0; row < nn; row++) {
+        for (size_t k = 0; k < quotient_degree; k++) {
+            size_t j = k * n + (size_t)row;
+            size_t src = reverse_bits_len((big - j) & (big - 1), log_big);
+            for (size_t c = 0; c < d; c++) out.row(row)[k * d + c] = storage.row(src)[c] * weights[k];
+        }
+    }
+    return out;
+}
+
+}  // namespace orc

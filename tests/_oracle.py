@@ -1,0 +1,120 @@
+"""ctypes loader for the CPU oracle (oracle/liboracle.so). Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+
+u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(ROOT, "oracle", "liboracle.so")
+    build()  # make is a no-op when liboracle.so is newer than its sources
+    L = C.CDLL(path)
+    sig = {
+        "orc_num_threads": (C.c_int, []),
+        "orc_set_num_threads": (None, [C.c_int]),
+        "orc_fp_mul": (C.c_uint64, [C.c_uint64, C.c_uint64]),
+        "orc_fp_inv": (C.c_uint64, [C.c_uint64]),
+        "orc_two_adic_generator": (C.c_uint64, [C.c_uint32]),
+        "orc_fp2_mul": (None, [u64p, u64p, u64p]),
+        "orc_fp2_inv": (None, [u64p, u64p]),
+        "orc_dft_batch": (None, [u64p, C.c_uint64, C.c_uint64, u64p]),
+        "orc_dft_batch_bitrev": (None, [u64p, C.c_uint64, C.c_uint64, u64p]),
+        "orc_idft_batch": (None, [u64p, C.c_uint64, C.c_uint64, u64p]),
+        "orc_coset_dft_batch": (None, [u64p, C.c_uint64, C.c_uint64, C.c_uint64, u64p]),
+        "orc_coset_idft_batch": (None, [u64p, C.c_uint64, C.c_uint64, C.c_uint64, u64p]),
+        "orc_coset_lde_batch_bitrev": (None, [u64p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, u64p]),
+        "orc_lde_from_shifted_coefficients": (None, [u64p, C.c_uint64, C.c_uint64, C.c_uint32, u64p]),
+        "orc_shifted_quotient_slices": (None, [u64p, C.c_uint64, C.c_uint64, C.c_uint64, u64p]),
+        "orc_blake3": (None, [u8p, C.c_uint64, u8p]),
+        "orc_blake3_compress_raw": (None, [u32p, u32p, u32p]),
+        "orc_hash_row": (None, [u64p, C.c_uint64, u8p]),
+        "orc_compress": (None, [u8p, u8p, u8p]),
+        "orc_mmcs_commit": (C.c_void_p, [C.POINTER(C.c_void_p), u64p, u64p, C.c_uint64, u8p]),
+        "orc_mmcs_num_layers": (C.c_uint64, [C.c_void_p]),
+        "orc_mmcs_layer_len": (C.c_uint64, [C.c_void_p, C.c_uint64]),
+        "orc_mmcs_layer": (None, [C.c_void_p, C.c_uint64, u8p]),
+        "orc_mmcs_open": (None, [C.c_void_p, C.c_uint64, u64p, u8p]),
+        "orc_mmcs_verify": (C.c_int, [u8p, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u8p, C.c_uint64]),
+        "orc_mmcs_free": (None, [C.c_void_p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = L
+    return L
+
+
+P = 2**64 - 2**32 + 1
+
+
+def rand_matrix(rng, rows, cols):
+    return (rng.integers(0, P, size=(rows, cols), dtype=np.uint64)).astype(np.uint64)
+
+
+def coset_lde(L, m, added_bits, shift=7):
+    rows, cols = m.shape
+    out = np.empty((rows << added_bits, cols), dtype=np.uint64)
+    L.orc_coset_lde_batch_bitrev(np.ascontiguousarray(m), rows, cols, added_bits, shift, out)
+    return out
+
+
+def dft_bitrev(L, m):
+    out = np.empty_like(m)
+    L.orc_dft_batch_bitrev(np.ascontiguousarray(m), m.shape[0], m.shape[1], out)
+    return out
+
+
+class MmcsTree:
+    def __init__(self, L, mats):
+        self.L = L
+        self.mats = [np.ascontiguousarray(m, dtype=np.uint64) for m in mats]
+        n = len(mats)
+        ptrs = (C.c_void_p * n)(*[m.ctypes.data for m in self.mats])
+        self.heights = np.array([m.shape[0] for m in self.mats], dtype=np.uint64)
+        self.widths = np.array([m.shape[1] for m in self.mats], dtype=np.uint64)
+        self.root = np.zeros(32, dtype=np.uint8)
+        self.h = L.orc_mmcs_commit(ptrs, self.heights, self.widths, n, self.root)
+        assert self.h, "orc_mmcs_commit failed"
+
+    def layers(self):
+        out = []
+        for i in range(self.L.orc_mmcs_num_layers(self.h)):
+            ln = self.L.orc_mmcs_layer_len(self.h, i)
+            buf = np.zeros((ln, 32), dtype=np.uint8)
+            self.L.orc_mmcs_layer(self.h, i, buf)
+            out.append(buf)
+        return out
+
+    def open(self, index):
+        total = int(self.widths.sum())
+        opened = np.zeros(total, dtype=np.uint64)
+        depth = int(self.heights.max()).bit_length() - 1
+        proof = np.zeros((max(depth, 1), 32), dtype=np.uint8)
+        self.L.orc_mmcs_open(self.h, index, opened, proof)
+        return opened, proof[:depth]
+
+    def verify(self, index, opened, proof):
+        return bool(self.L.orc_mmcs_verify(self.root, self.heights, self.widths, len(self.mats), index,
+                                           np.ascontiguousarray(opened), np.ascontiguousarray(proof).reshape(-1),
+                                           len(proof)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_mmcs_free(self.h)
+            self.h = None
