@@ -1,0 +1,126 @@
+/* libmsgpu -- C ABI of the B200 (sm_100a) commitment hot path for multi-stark.
+ *
+ * These are the entry points a Rust `msgpu-sys` crate binds (INTEGRATION.md shows the `extern "C"`
+ * block and the `GpuDft` / `GpuFriPcs` wrappers that slot into `GoldilocksBlake3Config`,
+ * reference src/types.rs:85,200,209-223). Conventions:
+ *   - every function returns 0 on success and a negative code on failure; msgpu_last_error() gives the
+ *     message of the last failure on the calling thread. Nothing aborts or throws across the ABI.
+ *   - matrices are row-major arrays of canonical Goldilocks values (uint64_t < 2^64 - 2^32 + 1),
+ *     i.e. the memory of a p3 `RowMajorMatrix<Goldilocks>` (reference src/prover.rs:336-351).
+ *   - extension-field values (`BinomialExtensionField<Goldilocks, 2>`, X^2 = 7) are two adjacent
+ *     uint64_t (c0, c1), the layout `flatten_to_base` produces (reference src/prover.rs:494-495).
+ *   - a context owns one CUDA stream; calls on one context must come from one thread at a time
+ *     (Send, not Sync -- the reference calls `prove` from a single thread, src/prover.rs:289).
+ *   - host-pointer entry points copy their inputs to the device before returning and block until
+ *     their outputs are written; `_dev` entry points take device pointers and are stream-ordered.
+ */
+#ifndef MSGPU_H
+#define MSGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct msgpu_ctx msgpu_ctx;
+/* Device-resident `Pcs::ProverData` / `Mmcs::ProverData`: the committed (LDE) matrices in
+ * bit-reversed row order plus every digest layer of the Merkle tree. */
+typedef struct msgpu_pdata msgpu_pdata;
+
+#define MSGPU_OK 0
+#define MSGPU_ERR_INVALID (-1) /* bad argument (the reference panics/asserts on these) */
+#define MSGPU_ERR_CUDA (-2)    /* CUDA runtime failure; there is no CPU fallback */
+#define MSGPU_ERR_INTERNAL (-3)
+
+/* ---- context ---------------------------------------------------------------------------------- */
+/* `stream`: a cudaStream_t to launch on (e.g. the caller's current stream) or NULL to create one. */
+int msgpu_ctx_create(int device, void* stream, msgpu_ctx** out);
+void msgpu_ctx_destroy(msgpu_ctx* ctx);
+const char* msgpu_last_error(void);
+int msgpu_sync(msgpu_ctx* ctx);
+void* msgpu_stream(msgpu_ctx* ctx);
+/* number of kernels this library has launched on the context (bench.py `gpu_launches`) */
+uint64_t msgpu_launch_count(msgpu_ctx* ctx);
+
+/* ---- memory ----------------------------------------------------------------------------------- */
+int msgpu_malloc(msgpu_ctx* ctx, size_t bytes, void** dptr);
+int msgpu_free(msgpu_ctx* ctx, void* dptr);
+int msgpu_memcpy_h2d(msgpu_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int msgpu_memcpy_d2h(msgpu_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int msgpu_host_alloc(size_t bytes, void** hptr); /* pinned host memory */
+int msgpu_host_free(void* hptr);
+
+/* ---- TwoAdicSubgroupDft slot (reference: `type Dft = Radix2DitParallel<Val>`, src/types.rs:200;
+ *      used at src/prover.rs:440,650,716) ------------------------------------------------------- */
+/* dft_batch(m): out[k] = sum_j in[j] w^{jk}, natural order (rows x cols in, rows x cols out). */
+int msgpu_dft_batch(msgpu_ctx* ctx, const uint64_t* in, uint64_t rows, uint64_t cols, uint64_t* out);
+/* dft_batch(m).bit_reverse_rows(): the raw storage, natural index k at row rev(k)
+ * (src/prover.rs:648-650,716). */
+int msgpu_dft_batch_bitrev(msgpu_ctx* ctx, const uint64_t* in, uint64_t rows, uint64_t cols, uint64_t* out);
+/* idft_batch(m): inverse of dft_batch, natural order. */
+int msgpu_idft_batch(msgpu_ctx* ctx, const uint64_t* in, uint64_t rows, uint64_t cols, uint64_t* out);
+/* coset_lde_batch(m, added_bits, shift).bit_reverse_rows(): what `Pcs::commit` stores per matrix,
+ * out[i] = P(shift * w_{rows<<added_bits}^{rev(i)}) (src/prover.rs:681-692). */
+int msgpu_coset_lde_batch_bitrev(msgpu_ctx* ctx, const uint64_t* in, uint64_t rows, uint64_t cols, uint32_t added_bits,
+                                 uint64_t shift, uint64_t* out);
+/* `lde_from_shifted_coefficients` (src/prover.rs:709-717): zero-pad to rows << added_bits, one DFT,
+ * bit-reversed storage. */
+int msgpu_lde_from_shifted_coefficients(msgpu_ctx* ctx, const uint64_t* in, uint64_t rows, uint64_t cols,
+                                        uint32_t added_bits, uint64_t* out);
+/* device-pointer forms (in and out are device buffers; out may not alias in) */
+int msgpu_dft_batch_bitrev_dev(msgpu_ctx* ctx, const uint64_t* in, uint64_t rows, uint64_t cols, uint64_t* out);
+int msgpu_coset_lde_batch_bitrev_dev(msgpu_ctx* ctx, const uint64_t* in, uint64_t rows, uint64_t cols,
+                                     uint32_t added_bits, uint64_t shift, uint64_t* out);
+int msgpu_lde_from_shifted_coefficients_dev(msgpu_ctx* ctx, const uint64_t* in, uint64_t rows, uint64_t cols,
+                                            uint32_t added_bits, uint64_t* out);
+
+/* ---- Pcs / Mmcs slot (reference: `type Pcs = TwoAdicFriPcs<Val, Dft, Mmcs, ExtMmcs>`,
+ *      `type Mmcs = MerkleTreeMmcs<..Blake3..>`, src/types.rs:82-85,199-223) ---------------------- */
+/* Pcs::commit (src/prover.rs:350,419; src/system.rs:193): per matrix the coset LDE with shift
+ * GENERATOR = 7 in bit-reversed row order, then one MMCS over all LDEs. `mats[i]` is a HOST pointer
+ * to heights[i] x widths[i] evaluations over the natural domain. root32 receives the 32-byte root
+ * (cap_height 0). */
+int msgpu_commit(msgpu_ctx* ctx, const uint64_t* const* mats, const uint64_t* heights, const uint64_t* widths,
+                 uint64_t n_mats, uint32_t log_blowup, msgpu_pdata** out, uint8_t* root32);
+/* same with DEVICE input pointers (inputs are not modified) */
+int msgpu_commit_dev(msgpu_ctx* ctx, const uint64_t* const* mats, const uint64_t* heights, const uint64_t* widths,
+                     uint64_t n_mats, uint32_t log_blowup, msgpu_pdata** out, uint8_t* root32);
+/* Pcs::commit_ldes (src/prover.rs:526): Merkle-only commitment to LDEs that already live on the
+ * device in bit-reversed row order. The prover data BORROWS (take_ownership = 0) or adopts
+ * (take_ownership = 1; buffers must come from msgpu_malloc) the matrices. */
+int msgpu_commit_ldes_dev(msgpu_ctx* ctx, uint64_t* const* ldes, const uint64_t* heights, const uint64_t* widths,
+                          uint64_t n_mats, int take_ownership, msgpu_pdata** out, uint8_t* root32);
+/* Mmcs::commit on HOST matrices as they are (no LDE): used for the FRI layers' ExtensionMmcs rows
+ * and by the parity tests of the tree shape (cases of src/types.rs:246-282). */
+int msgpu_mmcs_commit(msgpu_ctx* ctx, const uint64_t* const* mats, const uint64_t* heights, const uint64_t* widths,
+                      uint64_t n_mats, msgpu_pdata** out, uint8_t* root32);
+
+void msgpu_pdata_free(msgpu_pdata* pd);
+uint64_t msgpu_pdata_num_matrices(const msgpu_pdata* pd);
+/* Pcs::get_evaluations_on_domain (src/prover.rs:454-468) is a view: the first rows*q stored rows of
+ * matrix `idx`. Returns the device pointer and the stored shape. */
+int msgpu_pdata_matrix(const msgpu_pdata* pd, uint64_t idx, uint64_t** dev_ptr, uint64_t* rows, uint64_t* cols);
+/* copy stored rows [row0, row0 + nrows) of matrix idx to the host */
+int msgpu_pdata_read_rows(msgpu_ctx* ctx, const msgpu_pdata* pd, uint64_t idx, uint64_t row0, uint64_t nrows,
+                          uint64_t* out);
+uint64_t msgpu_pdata_num_layers(const msgpu_pdata* pd);
+uint64_t msgpu_pdata_layer_len(const msgpu_pdata* pd, uint64_t layer);
+int msgpu_pdata_read_layer(msgpu_ctx* ctx, const msgpu_pdata* pd, uint64_t layer, uint8_t* out);
+/* Mmcs::open_batch for n_idx indices at once. For query k: the opened rows of every matrix in
+ * commit order (matrix m contributes stored row index >> (log_max_height - log_height_m)), written
+ * back to back at opened_out + k * sum(widths); then log2(max_height) sibling digests, bottom-up,
+ * at proof_out + k * 32 * log2(max_height). */
+int msgpu_open_batch(msgpu_ctx* ctx, const msgpu_pdata* pd, const uint64_t* indices, uint64_t n_idx,
+                     uint64_t* opened_out, uint8_t* proof_out);
+
+/* ---- test hooks --------------------------------------------------------------------------------- */
+/* raw 7-round BLAKE3 compression of a 16-word state and 16 message words (known-answer vector of
+ * reference src/test_circuits/blake3.rs:2646-2746); host pointers */
+int msgpu_blake3_compress_raw(msgpu_ctx* ctx, const uint32_t* state16, const uint32_t* msg16, uint32_t* out16);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSGPU_H */

@@ -1,0 +1,88 @@
+"""ctypes binding of include/msgpu.h. The signatures below are the whole ABI; tests/test_abi.py checks
+that every symbol the header declares is exported by the built library."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+c_u64p = C.POINTER(C.c_uint64)
+c_u8p = C.POINTER(C.c_uint8)
+c_u32p = C.POINTER(C.c_uint32)
+c_vpp = C.POINTER(C.c_void_p)
+
+SIGNATURES = {
+    "msgpu_ctx_create": (C.c_int, [C.c_int, C.c_void_p, c_vpp]),
+    "msgpu_ctx_destroy": (None, [C.c_void_p]),
+    "msgpu_last_error": (C.c_char_p, []),
+    "msgpu_sync": (C.c_int, [C.c_void_p]),
+    "msgpu_stream": (C.c_void_p, [C.c_void_p]),
+    "msgpu_launch_count": (C.c_uint64, [C.c_void_p]),
+    "msgpu_malloc": (C.c_int, [C.c_void_p, C.c_size_t, c_vpp]),
+    "msgpu_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "msgpu_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "msgpu_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "msgpu_host_alloc": (C.c_int, [C.c_size_t, c_vpp]),
+    "msgpu_host_free": (C.c_int, [C.c_void_p]),
+    "msgpu_dft_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "msgpu_dft_batch_bitrev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "msgpu_idft_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "msgpu_coset_lde_batch_bitrev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64,
+                                               C.c_void_p]),
+    "msgpu_lde_from_shifted_coefficients": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32,
+                                                      C.c_void_p]),
+    "msgpu_dft_batch_bitrev_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "msgpu_coset_lde_batch_bitrev_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32,
+                                                   C.c_uint64, C.c_void_p]),
+    "msgpu_lde_from_shifted_coefficients_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32,
+                                                          C.c_void_p]),
+    "msgpu_commit": (C.c_int, [C.c_void_p, c_vpp, c_u64p, c_u64p, C.c_uint64, C.c_uint32, c_vpp, C.c_void_p]),
+    "msgpu_commit_dev": (C.c_int, [C.c_void_p, c_vpp, c_u64p, c_u64p, C.c_uint64, C.c_uint32, c_vpp, C.c_void_p]),
+    "msgpu_commit_ldes_dev": (C.c_int, [C.c_void_p, c_vpp, c_u64p, c_u64p, C.c_uint64, C.c_int, c_vpp, C.c_void_p]),
+    "msgpu_mmcs_commit": (C.c_int, [C.c_void_p, c_vpp, c_u64p, c_u64p, C.c_uint64, c_vpp, C.c_void_p]),
+    "msgpu_pdata_free": (None, [C.c_void_p]),
+    "msgpu_pdata_num_matrices": (C.c_uint64, [C.c_void_p]),
+    "msgpu_pdata_matrix": (C.c_int, [C.c_void_p, C.c_uint64, c_vpp, c_u64p, c_u64p]),
+    "msgpu_pdata_read_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "msgpu_pdata_num_layers": (C.c_uint64, [C.c_void_p]),
+    "msgpu_pdata_layer_len": (C.c_uint64, [C.c_void_p, C.c_uint64]),
+    "msgpu_pdata_read_layer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "msgpu_open_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "msgpu_blake3_compress_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+
+class MsgpuError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("msgpu error %d: %s" % (code, message))
+        self.code = code
+
+
+def lib_path():
+    return _build.LIB
+
+
+def lib():
+    """Loads libmsgpu.so, building it with nvcc first if the sources are newer. Raises if that fails."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if _build.needs_build():
+        if not os.path.exists(_build.NVCC):
+            if not os.path.exists(_build.LIB):
+                raise MsgpuError(-3, "libmsgpu.so is not built and nvcc is not available")
+        else:
+            _build.build()
+    L = C.CDLL(_build.LIB)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)  # AttributeError here = the library does not export the ABI
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = L
+    return L
+
+
+def check(code):
+    if code != 0:
+        raise MsgpuError(code, (lib().msgpu_last_error() or b"").decode("utf-8", "replace"))

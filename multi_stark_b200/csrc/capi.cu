@@ -1,0 +1,362 @@
+// extern "C" surface of libmsgpu (include/msgpu.h). Every entry point catches C++ exceptions and
+// turns them into error codes + a thread-local message; nothing unwinds across the ABI.
+#include "../../include/msgpu.h"
+#include "internal.hpp"
+#include "mmcs.hpp"
+#include <cstring>
+
+struct msgpu_ctx {
+    msg::Ctx c;
+};
+
+namespace msg {
+
+static thread_local std::string g_last_error;
+
+void* Ctx::alloc(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 8;
+    MSG_CUDA(cudaMallocAsync(&p, bytes, stream));
+    return p;
+}
+void Ctx::free(void* p) {
+    if (p) MSG_CUDA(cudaFreeAsync(p, stream));
+}
+
+void b3_compress_raw_dev(Ctx& c, const u32* st, const u32* msg, u32* out);
+
+template <class F>
+static int guard(F&& f) {
+    try {
+        f();
+        return MSGPU_OK;
+    } catch (const Error& e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return MSGPU_ERR_INTERNAL;
+    } catch (...) {
+        g_last_error = "unknown error";
+        return MSGPU_ERR_INTERNAL;
+    }
+}
+
+struct DevBuf {  // RAII stream-ordered buffer
+    Ctx& c;
+    void* p = nullptr;
+    DevBuf(Ctx& c_, size_t bytes) : c(c_) { p = c.alloc(bytes); }
+    ~DevBuf() {
+        if (p) cudaFreeAsync(p, c.stream);
+    }
+    u64* u() const { return (u64*)p; }
+    void* release() { void* r = p; p = nullptr; return r; }
+};
+
+static void check_shape(u64 rows, u64 cols) {
+    MSG_REQUIRE(is_pow2(rows), "matrix height must be a power of two");
+    MSG_REQUIRE(cols == 0 || rows <= (~0ull) / 8 / cols, "matrix too large");
+}
+
+// shared body of the host-pointer DFT entry points: upload, run, download
+template <class F>
+static void host_transform(Ctx& c, const u64* in, u64 rows, u64 cols, u64 out_rows, u64* out, F&& run) {
+    check_shape(rows, cols);
+    if (rows * cols == 0) return;
+    DevBuf din(c, rows * cols * 8), dout(c, out_rows * cols * 8);
+    MSG_CUDA(cudaMemcpyAsync(din.p, in, rows * cols * 8, cudaMemcpyHostToDevice, c.stream));
+    run(din.u(), dout.u());
+    MSG_CUDA(cudaMemcpyAsync(out, dout.p, out_rows * cols * 8, cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+}
+
+static msgpu_pdata* commit_impl(Ctx& c, const u64* const* mats, const u64* heights, const u64* widths, u64 n,
+                                u32 log_blowup, bool host_inputs, bool do_lde) {
+    MSG_REQUIRE(n > 0, "commit: no matrices given");
+    msgpu_pdata* pd = new msgpu_pdata();
+    pd->ctx = &c;
+    try {
+        for (u64 i = 0; i < n; i++) {
+            check_shape(heights[i], widths[i]);
+            u64 h = heights[i], w = widths[i];
+            u64 out_h = do_lde ? (h << log_blowup) : h;
+            msgpu_pdata::Mat m{nullptr, out_h, w, true};
+            m.ptr = (u64*)c.alloc(out_h * w * 8);
+            pd->mats.push_back(m);
+            if (w == 0) continue;
+            if (!do_lde) {
+                MSG_CUDA(cudaMemcpyAsync(m.ptr, mats[i], h * w * 8, host_inputs ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                                         c.stream));
+                continue;
+            }
+            DevBuf tmp(c, h * w * 8);
+            if (host_inputs) {
+                MSG_CUDA(cudaMemcpyAsync(tmp.p, mats[i], h * w * 8, cudaMemcpyHostToDevice, c.stream));
+                ntt_coset_lde(c, tmp.u(), m.ptr, tmp.u(), h, w, log_blowup, msh::GL_GENERATOR);
+            } else {
+                ntt_coset_lde(c, mats[i], m.ptr, tmp.u(), h, w, log_blowup, msh::GL_GENERATOR);
+            }
+        }
+        mmcs_build(c, pd);
+    } catch (...) {
+        pdata_destroy(pd);
+        throw;
+    }
+    return pd;
+}
+
+}  // namespace msg
+
+using namespace msg;
+
+extern "C" {
+
+int msgpu_ctx_create(int device, void* stream, msgpu_ctx** out) {
+    return guard([&] {
+        MSG_REQUIRE(out != nullptr, "ctx_create: null output");
+        int count = 0;
+        MSG_CUDA(cudaGetDeviceCount(&count));
+        MSG_REQUIRE(device >= 0 && device < count, "ctx_create: no such CUDA device (libmsgpu has no CPU fallback)");
+        MSG_CUDA(cudaSetDevice(device));
+        msgpu_ctx* h = new msgpu_ctx();
+        h->c.device = device;
+        try {
+            if (stream) {
+                h->c.stream = (cudaStream_t)stream;
+            } else {
+                MSG_CUDA(cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
+                h->c.own_stream = true;
+            }
+            cudaDeviceProp prop;
+            MSG_CUDA(cudaGetDeviceProperties(&prop, device));
+            h->c.sm_count = prop.multiProcessorCount;
+            cudaMemPool_t pool;
+            MSG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+            unsigned long long thr = ~0ull;  // keep freed blocks in the pool: no re-allocation per proof
+            MSG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+            ctx_init_tables(h->c);
+        } catch (...) {
+            delete h;
+            throw;
+        }
+        *out = h;
+    });
+}
+
+void msgpu_ctx_destroy(msgpu_ctx* h) {
+    if (!h) return;
+    cudaSetDevice(h->c.device);
+    cudaStreamSynchronize(h->c.stream);
+    for (void* p : h->c.owned) cudaFree(p);
+    if (h->c.own_stream) cudaStreamDestroy(h->c.stream);
+    delete h;
+}
+
+const char* msgpu_last_error(void) { return g_last_error.c_str(); }
+int msgpu_sync(msgpu_ctx* h) {
+    return guard([&] { h->c.sync(); });
+}
+void* msgpu_stream(msgpu_ctx* h) { return (void*)h->c.stream; }
+uint64_t msgpu_launch_count(msgpu_ctx* h) { return h->c.launches; }
+
+int msgpu_malloc(msgpu_ctx* h, size_t bytes, void** dptr) {
+    return guard([&] { *dptr = h->c.alloc(bytes); });
+}
+int msgpu_free(msgpu_ctx* h, void* dptr) {
+    return guard([&] { h->c.free(dptr); });
+}
+int msgpu_memcpy_h2d(msgpu_ctx* h, void* dst, const void* src, size_t bytes) {
+    return guard([&] {
+        MSG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->c.stream));
+        h->c.sync();
+    });
+}
+int msgpu_memcpy_d2h(msgpu_ctx* h, void* dst, const void* src, size_t bytes) {
+    return guard([&] {
+        MSG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->c.stream));
+        h->c.sync();
+    });
+}
+int msgpu_host_alloc(size_t bytes, void** hptr) {
+    return guard([&] { MSG_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 8, cudaHostAllocDefault)); });
+}
+int msgpu_host_free(void* hptr) {
+    return guard([&] { MSG_CUDA(cudaFreeHost(hptr)); });
+}
+
+// ---- DFT slot -----------------------------------------------------------------------------------
+int msgpu_dft_batch_bitrev(msgpu_ctx* h, const uint64_t* in, uint64_t rows, uint64_t cols, uint64_t* out) {
+    return guard([&] {
+        Ctx& c = h->c;
+        host_transform(c, (const u64*)in, rows, cols, rows, (u64*)out,
+                       [&](u64* di, u64* dout) { ntt_dft_bitrev(c, di, dout, rows, cols, false); });
+    });
+}
+int msgpu_dft_batch(msgpu_ctx* h, const uint64_t* in, uint64_t rows, uint64_t cols, uint64_t* out) {
+    return guard([&] {
+        Ctx& c = h->c;
+        host_transform(c, (const u64*)in, rows, cols, rows, (u64*)out, [&](u64* di, u64* dout) {
+            ntt_dft_bitrev(c, di, di, rows, cols, false);
+            ntt_bit_reverse_rows(c, di, dout, rows, cols);
+        });
+    });
+}
+int msgpu_idft_batch(msgpu_ctx* h, const uint64_t* in, uint64_t rows, uint64_t cols, uint64_t* out) {
+    return guard([&] {
+        Ctx& c = h->c;
+        host_transform(c, (const u64*)in, rows, cols, rows, (u64*)out,
+                       [&](u64* di, u64* dout) { ntt_idft_natural(c, di, dout, di, rows, cols); });
+    });
+}
+int msgpu_coset_lde_batch_bitrev(msgpu_ctx* h, const uint64_t* in, uint64_t rows, uint64_t cols, uint32_t added_bits,
+                                 uint64_t shift, uint64_t* out) {
+    return guard([&] {
+        Ctx& c = h->c;
+        MSG_REQUIRE(shift != 0 && shift < GLD_P, "coset_lde: shift must be a non-zero canonical field element");
+        MSG_REQUIRE(added_bits <= 32, "coset_lde: added_bits too large");
+        host_transform(c, (const u64*)in, rows, cols, rows << added_bits, (u64*)out,
+                       [&](u64* di, u64* dout) { ntt_coset_lde(c, di, dout, di, rows, cols, added_bits, shift); });
+    });
+}
+int msgpu_lde_from_shifted_coefficients(msgpu_ctx* h, const uint64_t* in, uint64_t rows, uint64_t cols,
+                                        uint32_t added_bits, uint64_t* out) {
+    return guard([&] {
+        Ctx& c = h->c;
+        MSG_REQUIRE(added_bits <= 32, "lde: added_bits too large");
+        host_transform(c, (const u64*)in, rows, cols, rows << added_bits, (u64*)out,
+                       [&](u64* di, u64* dout) { ntt_lde_from_coeffs(c, di, dout, rows, cols, added_bits); });
+    });
+}
+int msgpu_dft_batch_bitrev_dev(msgpu_ctx* h, const uint64_t* in, uint64_t rows, uint64_t cols, uint64_t* out) {
+    return guard([&] {
+        check_shape(rows, cols);
+        ntt_dft_bitrev(h->c, (const u64*)in, (u64*)out, rows, cols, false);
+    });
+}
+int msgpu_coset_lde_batch_bitrev_dev(msgpu_ctx* h, const uint64_t* in, uint64_t rows, uint64_t cols,
+                                     uint32_t added_bits, uint64_t shift, uint64_t* out) {
+    return guard([&] {
+        Ctx& c = h->c;
+        check_shape(rows, cols);
+        MSG_REQUIRE(shift != 0 && shift < GLD_P, "coset_lde: shift must be a non-zero canonical field element");
+        if (rows * cols == 0) return;
+        DevBuf tmp(c, rows * cols * 8);
+        ntt_coset_lde(c, (const u64*)in, (u64*)out, tmp.u(), rows, cols, added_bits, shift);
+    });
+}
+int msgpu_lde_from_shifted_coefficients_dev(msgpu_ctx* h, const uint64_t* in, uint64_t rows, uint64_t cols,
+                                            uint32_t added_bits, uint64_t* out) {
+    return guard([&] {
+        check_shape(rows, cols);
+        ntt_lde_from_coeffs(h->c, (const u64*)in, (u64*)out, rows, cols, added_bits);
+    });
+}
+
+// ---- PCS / MMCS slot ------------------------------------------------------------------------------
+int msgpu_commit(msgpu_ctx* h, const uint64_t* const* mats, const uint64_t* heights, const uint64_t* widths,
+                 uint64_t n_mats, uint32_t log_blowup, msgpu_pdata** out, uint8_t* root32) {
+    return guard([&] {
+        msgpu_pdata* pd = commit_impl(h->c, (const u64* const*)mats, (const u64*)heights, (const u64*)widths, n_mats,
+                                      log_blowup, true, true);
+        memcpy(root32, pd->root, 32);
+        *out = pd;
+    });
+}
+int msgpu_commit_dev(msgpu_ctx* h, const uint64_t* const* mats, const uint64_t* heights, const uint64_t* widths,
+                     uint64_t n_mats, uint32_t log_blowup, msgpu_pdata** out, uint8_t* root32) {
+    return guard([&] {
+        msgpu_pdata* pd = commit_impl(h->c, (const u64* const*)mats, (const u64*)heights, (const u64*)widths, n_mats,
+                                      log_blowup, false, true);
+        memcpy(root32, pd->root, 32);
+        *out = pd;
+    });
+}
+int msgpu_mmcs_commit(msgpu_ctx* h, const uint64_t* const* mats, const uint64_t* heights, const uint64_t* widths,
+                      uint64_t n_mats, msgpu_pdata** out, uint8_t* root32) {
+    return guard([&] {
+        msgpu_pdata* pd =
+            commit_impl(h->c, (const u64* const*)mats, (const u64*)heights, (const u64*)widths, n_mats, 0, true, false);
+        memcpy(root32, pd->root, 32);
+        *out = pd;
+    });
+}
+int msgpu_commit_ldes_dev(msgpu_ctx* h, uint64_t* const* ldes, const uint64_t* heights, const uint64_t* widths,
+                          uint64_t n_mats, int take_ownership, msgpu_pdata** out, uint8_t* root32) {
+    return guard([&] {
+        Ctx& c = h->c;
+        MSG_REQUIRE(n_mats > 0, "commit_ldes: no matrices given");
+        msgpu_pdata* pd = new msgpu_pdata();
+        pd->ctx = &c;
+        try {
+            for (u64 i = 0; i < n_mats; i++) {
+                check_shape(heights[i], widths[i]);
+                pd->mats.push_back(msgpu_pdata::Mat{(u64*)ldes[i], heights[i], widths[i], false});
+            }
+            mmcs_build(c, pd);
+        } catch (...) {
+            pdata_destroy(pd);
+            throw;
+        }
+        if (take_ownership)
+            for (auto& m : pd->mats) m.owned = true;
+        memcpy(root32, pd->root, 32);
+        *out = pd;
+    });
+}
+
+void msgpu_pdata_free(msgpu_pdata* pd) {
+    try {
+        pdata_destroy(pd);
+    } catch (...) {
+    }
+}
+uint64_t msgpu_pdata_num_matrices(const msgpu_pdata* pd) { return pd->mats.size(); }
+int msgpu_pdata_matrix(const msgpu_pdata* pd, uint64_t idx, uint64_t** dev_ptr, uint64_t* rows, uint64_t* cols) {
+    return guard([&] {
+        MSG_REQUIRE(idx < pd->mats.size(), "pdata_matrix: index out of range");
+        if (dev_ptr) *dev_ptr = (uint64_t*)pd->mats[idx].ptr;
+        if (rows) *rows = pd->mats[idx].height;
+        if (cols) *cols = pd->mats[idx].width;
+    });
+}
+int msgpu_pdata_read_rows(msgpu_ctx* h, const msgpu_pdata* pd, uint64_t idx, uint64_t row0, uint64_t nrows, uint64_t* out) {
+    return guard([&] {
+        MSG_REQUIRE(idx < pd->mats.size(), "pdata_read_rows: index out of range");
+        auto& m = pd->mats[idx];
+        MSG_REQUIRE(row0 <= m.height && nrows <= m.height - row0, "pdata_read_rows: rows out of range");
+        if (nrows * m.width == 0) return;
+        MSG_CUDA(cudaMemcpyAsync(out, m.ptr + row0 * m.width, nrows * m.width * 8, cudaMemcpyDeviceToHost, h->c.stream));
+        h->c.sync();
+    });
+}
+uint64_t msgpu_pdata_num_layers(const msgpu_pdata* pd) { return pd->layer_len.size(); }
+uint64_t msgpu_pdata_layer_len(const msgpu_pdata* pd, uint64_t layer) {
+    return layer < pd->layer_len.size() ? pd->layer_len[layer] : 0;
+}
+int msgpu_pdata_read_layer(msgpu_ctx* h, const msgpu_pdata* pd, uint64_t layer, uint8_t* out) {
+    return guard([&] {
+        MSG_REQUIRE(layer < pd->layer_len.size(), "pdata_read_layer: layer out of range");
+        MSG_CUDA(cudaMemcpyAsync(out, pd->digests + pd->layer_off[layer] * 32, pd->layer_len[layer] * 32,
+                                 cudaMemcpyDeviceToHost, h->c.stream));
+        h->c.sync();
+    });
+}
+int msgpu_open_batch(msgpu_ctx* h, const msgpu_pdata* pd, const uint64_t* indices, uint64_t n_idx, uint64_t* opened_out,
+                     uint8_t* proof_out) {
+    return guard([&] { mmcs_open_batch(h->c, pd, (const u64*)indices, n_idx, (u64*)opened_out, proof_out); });
+}
+
+int msgpu_blake3_compress_raw(msgpu_ctx* h, const uint32_t* state16, const uint32_t* msg16, uint32_t* out16) {
+    return guard([&] {
+        Ctx& c = h->c;
+        DevBuf buf(c, 48 * 4);
+        u32* d = (u32*)buf.p;
+        MSG_CUDA(cudaMemcpyAsync(d, state16, 64, cudaMemcpyHostToDevice, c.stream));
+        MSG_CUDA(cudaMemcpyAsync(d + 16, msg16, 64, cudaMemcpyHostToDevice, c.stream));
+        b3_compress_raw_dev(c, d, d + 16, d + 32);
+        MSG_CUDA(cudaMemcpyAsync(out16, d + 32, 64, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+// Internal (non-ABI) declarations shared by the .cu translation units of libmsgpu.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+#include <stdexcept>
+
+#include "gl.cuh"
+#include "../host/goldilocks.hpp"
+
+namespace msg {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define MSG_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            throw msg::Error(-2, std::string(#expr) + ": " + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + \
+                                     std::to_string(__LINE__));                                          \
+    } while (0)
+
+#define MSG_REQUIRE(cond, msg_)                                  \
+    do {                                                         \
+        if (!(cond)) throw msg::Error(-1, std::string(msg_));    \
+    } while (0)
+
+struct DevPow {
+    u64* lo = nullptr;
+    u64* hi = nullptr;
+    u32 h1 = 0;
+    gl::PowTable view() const { gl::PowTable t; t.lo = lo; t.hi = hi; t.h1 = h1; return t; }
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    unsigned long long launches = 0;  // kernels of this library launched so far
+    int sm_count = 148;
+    u64* tw_small[2] = {nullptr, nullptr};  // w_1024^{i} / w_1024^{-i}, i < 512
+    std::map<std::tuple<u64, u64, u32>, DevPow> pow_cache;
+    std::map<std::tuple<u32, u32, u64>, gl::PowTable*> coset_cache;  // (log_n, added_bits, shift) -> device array [B]
+    std::vector<void*> owned;  // table allocations freed with the context
+
+    // optional per-launch timing (bench.py roofline): CUDA events on the launching stream
+    struct ProfRec {
+        const char* stage;
+        const char* kernel;
+        cudaEvent_t a, b;
+    };
+    bool profiling = false;
+    const char* stage = "";
+    std::vector<ProfRec> prof;
+
+    void* alloc(size_t bytes);  // stream-ordered
+    void free(void* p);
+    void sync() { MSG_CUDA(cudaStreamSynchronize(stream)); }
+    DevPow pow_table(u64 g, u64 c, u32 bits);
+    const gl::PowTable* coset_tables(u32 log_n, u32 added_bits, u64 shift);
+    const gl::PowTable* lde_coeff_tables(u32 log_n, u32 added_bits);
+};
+
+void ctx_init_tables(Ctx& c);
+
+// Brackets one kernel launch: counts it and, when profiling, records events around it.
+struct KLaunch {
+    Ctx& c;
+    cudaEvent_t b = nullptr;
+    KLaunch(Ctx& c_, const char* kernel) : c(c_) {
+        if (c.profiling) {
+            cudaEvent_t a;
+            MSG_CUDA(cudaEventCreate(&a));
+            MSG_CUDA(cudaEventCreate(&b));
+            MSG_CUDA(cudaEventRecord(a, c.stream));
+            c.prof.push_back(Ctx::ProfRec{c.stage, kernel, a, b});
+        }
+    }
+    ~KLaunch() {
+        c.launches++;
+        if (b) cudaEventRecord(b, c.stream);
+    }
+};
+struct StageScope {
+    Ctx& c;
+    const char* prev;
+    StageScope(Ctx& c_, const char* s) : c(c_), prev(c_.stage) { c.stage = s; }
+    ~StageScope() { c.stage = prev; }
+};
+
+// ---- NTT / LDE (ntt.cu) -------------------------------------------------------------------
+// Forward (or inverse, unnormalised) DFT of every column; natural order in, bit-reversed rows out.
+void ntt_dft_bitrev(Ctx& c, const u64* src, u64* dst, u64 n, u64 w, bool inverse, u64 batch = 1);
+// coset_lde_batch(evals, added_bits, shift).bit_reverse_rows(); tmp holds n*w elements.
+void ntt_coset_lde(Ctx& c, const u64* src, u64* dst, u64* tmp, u64 n, u64 w, u32 added_bits, u64 shift);
+// zero-pad coefficient rows to n << added_bits, one DFT, bit-reversed rows (src/prover.rs:709-717)
+void ntt_lde_from_coeffs(Ctx& c, const u64* src, u64* dst, u64 n, u64 w, u32 added_bits);
+// natural-order inverse DFT (with 1/n); tmp holds n*w elements
+void ntt_idft_natural(Ctx& c, const u64* src, u64* dst, u64* tmp, u64 n, u64 w);
+// dst[r] = src[rev(r)]
+void ntt_bit_reverse_rows(Ctx& c, const u64* src, u64* dst, u64 n, u64 w);
+
+// ---- BLAKE3 Merkle (merkle.cu) ------------------------------------------------------------------
+struct MatRef {
+    const u64* ptr;
+    u64 height;
+    u64 width;
+};
+// digests[i] = BLAKE3(le_bytes(row i of mats[0]) || le_bytes(row i of mats[1]) ...), all mats same height
+void b3_hash_rows(Ctx& c, const std::vector<MatRef>& mats, uint8_t* digests);
+// next[i] = H(prev[2i] || prev[2i+1]), optionally followed by H(that || inject[i])
+void b3_compress_layer(Ctx& c, const uint8_t* prev, const uint8_t* inject, uint8_t* next, u64 next_len);
+
+inline unsigned ilog2(u64 n) {
+    unsigned l = 0;
+    while ((1ull << l) < n) l++;
+    return l;
+}
+inline bool is_pow2(u64 n) { return n && !(n & (n - 1)); }
+
+}  // namespace msg

@@ -1,0 +1,217 @@
+// BLAKE3 Merkle leaf and node kernels for the mixed-matrix commitment scheme the reference wires at
+// src/types.rs:82-84,199-207 (`MerkleTreeMmcs<Val, u8, SerializingHasher<Blake3>,
+// CompressionFunctionFromHasher<Blake3, 2, 32>, 2, 32>`):
+//   leaf  = BLAKE3(canonical u64 LE bytes of the row; rows of same-height matrices concatenated)
+//   node  = BLAKE3(left || right); shorter matrices are injected as H(H(l || r) || leaf(rows_i)).
+// Device values are canonical by invariant (gl.cuh), so rows are hashed as stored.
+#include "internal.hpp"
+#include "blake3.cuh"
+
+namespace msg {
+
+struct LeafMat {
+    const u64* ptr;
+    u32 width;
+    u32 word_off;  // offset of this matrix's words inside the concatenated row message
+};
+
+constexpr int kLeafThreads = 128;
+constexpr int kMaxStack = 24;
+
+// Hash one message of `total_words` 32-bit words provided by get(k).
+template <class Get>
+__device__ __forceinline__ void hash_words(Get get, u32 total_words, u32 out[8]) {
+    const u32 nbytes = total_words * 4u;
+    const u32 nchunks = nbytes == 0 ? 1u : (nbytes + 1023u) / 1024u;
+    u32 stack[kMaxStack][8];
+    u32 sp = 0;
+    u32 cv[8];
+    for (u32 ci = 0; ci < nchunks; ci++) {
+        b3::set_iv(cv);
+        const u32 cbytes = min(1024u, nbytes - ci * 1024u);
+        const u32 nblocks = cbytes == 0 ? 1u : (cbytes + 63u) / 64u;
+        for (u32 b = 0; b < nblocks; b++) {
+            u32 m[16];
+            const u32 wbase = ci * 256u + b * 16u;
+#pragma unroll
+            for (int i = 0; i < 16; i++) m[i] = (wbase + i < total_words) ? get(wbase + i) : 0u;
+            u32 flags = (b == 0 ? b3::CHUNK_START : 0u) |
+                        (b + 1 == nblocks ? (b3::CHUNK_END | (nchunks == 1 ? b3::ROOT : 0u)) : 0u);
+            b3::compress(cv, m, ci, 0, min(64u, cbytes - b * 64u), flags);
+        }
+        if (nchunks == 1) break;
+        if (ci + 1 < nchunks) {
+            // merge completed subtrees: one parent per trailing zero bit of the chunk count
+            u32 total = ci + 1;
+            while ((total & 1u) == 0) {
+                sp--;
+                u32 l[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) l[i] = stack[sp][i];
+                u32 m[16];
+#pragma unroll
+                for (int i = 0; i < 8; i++) { m[i] = l[i]; m[8 + i] = cv[i]; }
+                b3::set_iv(cv);
+                b3::compress(cv, m, 0, 0, 64, b3::PARENT);
+                total >>= 1;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) stack[sp][i] = cv[i];
+            sp++;
+        } else {
+            while (sp > 0) {
+                sp--;
+                u32 m[16];
+#pragma unroll
+                for (int i = 0; i < 8; i++) { m[i] = stack[sp][i]; m[8 + i] = cv[i]; }
+                b3::set_iv(cv);
+                b3::compress(cv, m, 0, 0, 64, b3::PARENT | (sp == 0 ? b3::ROOT : 0u));
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = cv[i];
+}
+
+// One thread per leaf; rows are staged through shared memory with an odd word pitch so that the
+// coalesced global reads turn into conflict-free per-thread row reads.
+__global__ void __launch_bounds__(kLeafThreads) k_hash_rows_staged(const LeafMat* mats, u32 nmats, u64 height,
+                                                                   u32 total_words, u32 pitch, u32 rows_per_cta,
+                                                                   u32* out) {
+    extern __shared__ u32 sm32[];
+    const u64 row0 = (u64)blockIdx.x * rows_per_cta;
+    const u32 nrows = (u32)min((u64)rows_per_cta, height - row0);
+    for (u32 k = 0; k < nmats; k++) {
+        const LeafMat mt = mats[k];
+        const u64* src = mt.ptr + row0 * mt.width;
+        const u32 total = nrows * mt.width;
+        for (u32 e = threadIdx.x; e < total; e += blockDim.x) {
+            u32 r = e / mt.width, c = e % mt.width;
+            u64 v = src[e];
+            u32* d = sm32 + (size_t)r * pitch + mt.word_off + 2 * c;
+            d[0] = (u32)v;
+            d[1] = (u32)(v >> 32);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < nrows) {
+        const u32* row = sm32 + (size_t)threadIdx.x * pitch;
+        u32 dg[8];
+        hash_words([&](u32 k) { return row[k]; }, total_words, dg);
+        uint4* o = reinterpret_cast<uint4*>(out + (row0 + threadIdx.x) * 8);
+        o[0] = make_uint4(dg[0], dg[1], dg[2], dg[3]);
+        o[1] = make_uint4(dg[4], dg[5], dg[6], dg[7]);
+    }
+}
+
+// Fallback for rows too wide to stage (more than ~6000 columns in total): words read from global.
+__global__ void __launch_bounds__(kLeafThreads) k_hash_rows_direct(const LeafMat* mats, u32 nmats, u64 height,
+                                                                   u32 total_words, u32* out) {
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= height) return;
+    u32 dg[8];
+    hash_words(
+        [&](u32 k) {
+            u32 mi = 0;
+            while (mi + 1 < nmats && mats[mi + 1].word_off <= k) mi++;
+            u32 kk = k - mats[mi].word_off;
+            u64 v = mats[mi].ptr[r * mats[mi].width + (kk >> 1)];
+            return (kk & 1) ? (u32)(v >> 32) : (u32)v;
+        },
+        total_words, dg);
+    uint4* o = reinterpret_cast<uint4*>(out + r * 8);
+    o[0] = make_uint4(dg[0], dg[1], dg[2], dg[3]);
+    o[1] = make_uint4(dg[4], dg[5], dg[6], dg[7]);
+}
+
+__global__ void __launch_bounds__(256) k_compress_layer(const uint4* prev, const uint4* inject, uint4* next, u64 next_len) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= next_len) return;
+    uint4 a0 = prev[4 * i], a1 = prev[4 * i + 1], b0 = prev[4 * i + 2], b1 = prev[4 * i + 3];
+    u32 l[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    u32 r[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    u32 d[8];
+    b3::hash_pair(l, r, d);
+    if (inject) {
+        uint4 c0 = inject[2 * i], c1 = inject[2 * i + 1];
+        u32 x[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        u32 d2[8];
+        b3::hash_pair(d, x, d2);
+#pragma unroll
+        for (int k = 0; k < 8; k++) d[k] = d2[k];
+    }
+    next[2 * i] = make_uint4(d[0], d[1], d[2], d[3]);
+    next[2 * i + 1] = make_uint4(d[4], d[5], d[6], d[7]);
+}
+
+// raw compression for the known-answer test
+__global__ void k_compress_raw(const u32* st, const u32* msg, u32* out) {
+    u32 s[16], m[16], o[16];
+    for (int i = 0; i < 16; i++) { s[i] = st[i]; m[i] = msg[i]; }
+    b3::compress_raw(s, m, o);
+    for (int i = 0; i < 16; i++) out[i] = o[i];
+}
+
+void b3_hash_rows(Ctx& c, const std::vector<MatRef>& mats, uint8_t* digests) {
+    MSG_REQUIRE(!mats.empty(), "hash_rows: no matrices");
+    u64 height = mats[0].height;
+    std::vector<LeafMat> lm;
+    u64 words = 0;
+    for (auto& m : mats) {
+        MSG_REQUIRE(m.height == height, "hash_rows: heights differ");
+        MSG_REQUIRE(words + 2 * m.width < (1ull << 30), "hash_rows: row too wide");
+        if (m.width == 0) continue;
+        lm.push_back(LeafMat{m.ptr, (u32)m.width, (u32)words});
+        words += 2 * m.width;
+    }
+    if (height == 0) return;
+    LeafMat* d_mats = (LeafMat*)c.alloc(std::max<size_t>(lm.size(), 1) * sizeof(LeafMat));
+    if (!lm.empty())
+        MSG_CUDA(cudaMemcpyAsync(d_mats, lm.data(), lm.size() * sizeof(LeafMat), cudaMemcpyHostToDevice, c.stream));
+    u32 total_words = (u32)words;
+    u32 pitch = total_words | 1u;
+    size_t budget = 96 * 1024;
+    u32 rows = (u32)std::min<size_t>(kLeafThreads, budget / ((size_t)pitch * 4));
+    if (rows >= 32 || (u64)rows >= height) {
+        if (rows > 32) rows = rows / 32 * 32;
+        if (rows == 0) rows = 1;
+        static bool attr = false;
+        if (!attr) {
+            MSG_CUDA(cudaFuncSetAttribute(k_hash_rows_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+            attr = true;
+        }
+        u64 blocks = (height + rows - 1) / rows;
+        KLaunch kl(c, "k_hash_rows_staged");
+        k_hash_rows_staged<<<(unsigned)blocks, kLeafThreads, (size_t)rows * pitch * 4, c.stream>>>(
+            d_mats, (u32)lm.size(), height, total_words, pitch, rows, (u32*)digests);
+    } else {
+        u64 blocks = (height + kLeafThreads - 1) / kLeafThreads;
+        KLaunch kl(c, "k_hash_rows_direct");
+        k_hash_rows_direct<<<(unsigned)blocks, kLeafThreads, 0, c.stream>>>(d_mats, (u32)lm.size(), height, total_words,
+                                                                            (u32*)digests);
+    }
+    MSG_CUDA(cudaGetLastError());
+    // the host vector `lm` was copied with a pageable-memory async copy, which is staged before return
+    c.free(d_mats);
+}
+
+void b3_compress_layer(Ctx& c, const uint8_t* prev, const uint8_t* inject, uint8_t* next, u64 next_len) {
+    if (next_len == 0) return;
+    u64 blocks = (next_len + 255) / 256;
+    {
+        KLaunch kl(c, "k_compress_layer");
+        k_compress_layer<<<(unsigned)blocks, 256, 0, c.stream>>>((const uint4*)prev, (const uint4*)inject, (uint4*)next,
+                                                                 next_len);
+    }
+    MSG_CUDA(cudaGetLastError());
+}
+
+void b3_compress_raw_dev(Ctx& c, const u32* st, const u32* msg, u32* out) {
+    {
+        KLaunch kl(c, "k_compress_raw");
+        k_compress_raw<<<1, 1, 0, c.stream>>>(st, msg, out);
+    }
+    MSG_CUDA(cudaGetLastError());
+}
+
+}  // namespace msg

@@ -1,0 +1,28 @@
+// Device-resident prover data of the mixed-matrix commitment scheme (p3 `MerkleTree` restated for
+// the device): matrices in commit order + all digest layers. See merkle.cu for the hash kernels.
+#pragma once
+#include "internal.hpp"
+
+struct msgpu_pdata {
+    struct Mat {
+        u64* ptr;
+        u64 height, width;
+        bool owned;
+    };
+    msg::Ctx* ctx = nullptr;
+    std::vector<Mat> mats;           // original (commit) order
+    uint8_t* digests = nullptr;      // all layers back to back
+    std::vector<u64> layer_off;      // offset (in digests) of each layer
+    std::vector<u64> layer_len;      // layer 0 = leaf digests of the tallest matrices
+    u64 max_height = 0;
+    u64 total_width = 0;
+    uint8_t root[32];
+};
+
+namespace msg {
+// Builds the tree over pd->mats (already filled in). Writes pd->root (synchronises the stream).
+void mmcs_build(Ctx& c, msgpu_pdata* pd);
+void mmcs_open_batch(Ctx& c, const msgpu_pdata* pd, const u64* indices_host, u64 n_idx, u64* opened_host,
+                     uint8_t* proof_host);
+void pdata_destroy(msgpu_pdata* pd);
+}  // namespace msg

@@ -1,0 +1,261 @@
+"""Host-side mirror of the reference's DFT / PCS / MMCS objects over libmsgpu.
+
+Names and argument meaning follow the trait methods the reference calls:
+  GpuDft.dft_batch / coset_lde_batch            <- TwoAdicSubgroupDft (src/prover.rs:440,650,716)
+  GpuPcs.commit / commit_ldes / get_evaluations_on_domain / natural_domain_for_degree
+                                                 <- Pcs (src/prover.rs:346-351,419,454-468,526)
+  GpuMmcs.commit / open_batch / verify-free      <- Mmcs (src/types.rs:82-84,199-207)
+Matrices are numpy uint64 arrays of canonical Goldilocks values, shape (rows, cols)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import check
+
+GENERATOR = 7
+
+
+def _as_matrix(m):
+    a = np.ascontiguousarray(m, dtype=np.uint64)
+    if a.ndim != 2:
+        raise ValueError("matrix must be 2-D (rows, cols)")
+    return a
+
+
+class GpuContext:
+    """One CUDA device + stream. `stream` may be an existing cudaStream_t handle (int), e.g.
+    torch.cuda.current_stream().cuda_stream, so that the caller's CUDA events bracket our launches."""
+
+    def __init__(self, device=0, stream=None):
+        self.L = _ffi.lib()
+        h = C.c_void_p()
+        check(self.L.msgpu_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.msgpu_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(self.L.msgpu_sync(self.h))
+
+    @property
+    def launches(self):
+        return int(self.L.msgpu_launch_count(self.h))
+
+    @property
+    def stream(self):
+        return self.L.msgpu_stream(self.h)
+
+    # raw device buffers (uint64 elements)
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        check(self.L.msgpu_malloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def free(self, ptr):
+        check(self.L.msgpu_free(self.h, C.c_void_p(ptr)))
+
+    def upload(self, arr):
+        a = np.ascontiguousarray(arr)
+        p = self.malloc(max(a.nbytes, 8))
+        if a.nbytes:
+            check(self.L.msgpu_memcpy_h2d(self.h, C.c_void_p(p), a.ctypes.data_as(C.c_void_p), a.nbytes))
+        return p
+
+    def download(self, ptr, shape, dtype=np.uint64):
+        out = np.empty(shape, dtype=dtype)
+        if out.nbytes:
+            check(self.L.msgpu_memcpy_d2h(self.h, out.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), out.nbytes))
+        return out
+
+
+class GpuDft:
+    """`TwoAdicSubgroupDft<Goldilocks>` slot (reference `type Dft`, src/types.rs:200)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.L = ctx.L
+
+    def _call(self, fn, m, out_rows, *extra):
+        a = _as_matrix(m)
+        out = np.empty((out_rows, a.shape[1]), dtype=np.uint64)
+        check(fn(self.ctx.h, a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1], *extra, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def dft_batch(self, m):
+        return self._call(self.L.msgpu_dft_batch, m, len(m))
+
+    def dft_batch_bitrev(self, m):
+        """dft_batch(m).bit_reverse_rows() (src/prover.rs:650,716)."""
+        return self._call(self.L.msgpu_dft_batch_bitrev, m, len(m))
+
+    def idft_batch(self, m):
+        return self._call(self.L.msgpu_idft_batch, m, len(m))
+
+    def coset_lde_batch_bitrev(self, m, added_bits, shift=GENERATOR):
+        """coset_lde_batch(m, added_bits, shift).bit_reverse_rows() (src/prover.rs:681-692)."""
+        return self._call(self.L.msgpu_coset_lde_batch_bitrev, m, len(m) << added_bits, added_bits, shift)
+
+    def lde_from_shifted_coefficients(self, m, added_bits):
+        """src/prover.rs:709-717."""
+        return self._call(self.L.msgpu_lde_from_shifted_coefficients, m, len(m) << added_bits, added_bits)
+
+
+class ProverData:
+    """Device-resident `ProverData`: committed matrices (bit-reversed rows) + digest layers."""
+
+    def __init__(self, ctx, handle, root):
+        self.ctx = ctx
+        self.L = ctx.L
+        self.h = handle
+        self.root = root
+
+    def free(self):
+        if getattr(self, "h", None):
+            self.L.msgpu_pdata_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.free()
+        except Exception:
+            pass
+
+    @property
+    def num_matrices(self):
+        return int(self.L.msgpu_pdata_num_matrices(self.h))
+
+    def matrix_info(self, idx):
+        p = C.c_void_p()
+        r = C.c_uint64()
+        c = C.c_uint64()
+        check(self.L.msgpu_pdata_matrix(self.h, idx, C.byref(p), C.byref(r), C.byref(c)))
+        return p.value, int(r.value), int(c.value)
+
+    def read_rows(self, idx, row0=0, nrows=None):
+        _, rows, cols = self.matrix_info(idx)
+        if nrows is None:
+            nrows = rows - row0
+        out = np.empty((nrows, cols), dtype=np.uint64)
+        check(self.L.msgpu_pdata_read_rows(self.ctx.h, self.h, idx, row0, nrows, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def layers(self):
+        out = []
+        for i in range(int(self.L.msgpu_pdata_num_layers(self.h))):
+            ln = int(self.L.msgpu_pdata_layer_len(self.h, i))
+            buf = np.empty((ln, 32), dtype=np.uint8)
+            check(self.L.msgpu_pdata_read_layer(self.ctx.h, self.h, i, buf.ctypes.data_as(C.c_void_p)))
+            out.append(buf)
+        return out
+
+    def open_batch(self, indices):
+        """Mmcs::open_batch for many indices: returns (opened[n_idx, sum widths], proofs[n_idx, depth, 32])."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        infos = [self.matrix_info(i) for i in range(self.num_matrices)]
+        tw = sum(c for _, _, c in infos)
+        depth = max(r for _, r, _ in infos).bit_length() - 1
+        opened = np.zeros((len(idx), tw), dtype=np.uint64)
+        proofs = np.zeros((len(idx), depth, 32), dtype=np.uint8)
+        check(self.L.msgpu_open_batch(self.ctx.h, self.h, idx.ctypes.data_as(C.c_void_p), len(idx),
+                                      opened.ctypes.data_as(C.c_void_p), proofs.ctypes.data_as(C.c_void_p)))
+        return opened, proofs
+
+
+def _mat_args(mats):
+    n = len(mats)
+    ptrs = (C.c_void_p * n)(*[m.ctypes.data for m in mats])
+    hs = (C.c_uint64 * n)(*[m.shape[0] for m in mats])
+    ws = (C.c_uint64 * n)(*[m.shape[1] for m in mats])
+    return ptrs, hs, ws
+
+
+class GpuMmcs:
+    """`MerkleTreeMmcs<..Blake3..>` slot (reference `type Mmcs`, src/types.rs:82-84; `new_mmcs` :202-207)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.L = ctx.L
+
+    def commit(self, mats):
+        mats = [_as_matrix(m) for m in mats]
+        ptrs, hs, ws = _mat_args(mats)
+        h = C.c_void_p()
+        root = np.zeros(32, dtype=np.uint8)
+        check(self.L.msgpu_mmcs_commit(self.ctx.h, ptrs, hs, ws, len(mats), C.byref(h), root.ctypes.data_as(C.c_void_p)))
+        return root, ProverData(self.ctx, h, root)
+
+
+class GpuPcs:
+    """`TwoAdicFriPcs<Val, Dft, Mmcs, ExtMmcs>` slot (reference `type Pcs`, src/types.rs:85;
+    `new_pcs` :209-223), commitment side."""
+
+    ZK = False  # reference asserts !Pcs::ZK before commit_ldes (src/prover.rs:522-525)
+
+    def __init__(self, ctx, log_blowup, cap_height=0):
+        if cap_height != 0:
+            raise ValueError("cap_height must be 0 (the only value the reference uses)")
+        self.ctx = ctx
+        self.L = ctx.L
+        self.log_blowup = log_blowup
+
+    @staticmethod
+    def natural_domain_for_degree(degree):
+        """(log_n, shift) of the two-adic coset H_n with shift 1."""
+        assert degree & (degree - 1) == 0
+        return degree.bit_length() - 1, 1
+
+    def commit(self, evaluations):
+        """`evaluations`: list of matrices over their natural domains. Returns (root, ProverData)."""
+        mats = [_as_matrix(m) for m in evaluations]
+        ptrs, hs, ws = _mat_args(mats)
+        h = C.c_void_p()
+        root = np.zeros(32, dtype=np.uint8)
+        check(self.L.msgpu_commit(self.ctx.h, ptrs, hs, ws, len(mats), self.log_blowup, C.byref(h),
+                                  root.ctypes.data_as(C.c_void_p)))
+        return root, ProverData(self.ctx, h, root)
+
+    def commit_dev(self, ptrs_shapes):
+        """Same with device-resident inputs: list of (device_ptr, rows, cols)."""
+        n = len(ptrs_shapes)
+        ptrs = (C.c_void_p * n)(*[p for p, _, _ in ptrs_shapes])
+        hs = (C.c_uint64 * n)(*[r for _, r, _ in ptrs_shapes])
+        ws = (C.c_uint64 * n)(*[c for _, _, c in ptrs_shapes])
+        h = C.c_void_p()
+        root = np.zeros(32, dtype=np.uint8)
+        check(self.L.msgpu_commit_dev(self.ctx.h, ptrs, hs, ws, n, self.log_blowup, C.byref(h),
+                                      root.ctypes.data_as(C.c_void_p)))
+        return root, ProverData(self.ctx, h, root)
+
+    def commit_ldes(self, ptrs_shapes, take_ownership=False):
+        """Pcs::commit_ldes (src/prover.rs:526) on device-resident LDEs: list of (device_ptr, rows, cols)."""
+        n = len(ptrs_shapes)
+        ptrs = (C.c_void_p * n)(*[p for p, _, _ in ptrs_shapes])
+        hs = (C.c_uint64 * n)(*[r for _, r, _ in ptrs_shapes])
+        ws = (C.c_uint64 * n)(*[c for _, _, c in ptrs_shapes])
+        h = C.c_void_p()
+        root = np.zeros(32, dtype=np.uint8)
+        check(self.L.msgpu_commit_ldes_dev(self.ctx.h, ptrs, hs, ws, n, 1 if take_ownership else 0, C.byref(h),
+                                           root.ctypes.data_as(C.c_void_p)))
+        return root, ProverData(self.ctx, h, root)
+
+    def get_evaluations_on_domain(self, pdata, idx, log_quotient_size):
+        """View of the committed LDE on the coset GENERATOR * H_{2^log_quotient_size}: the first
+        2^log_quotient_size stored rows, bit-reversed (src/prover.rs:454-468).
+        Returns (device_ptr, rows, cols); no copy."""
+        ptr, rows, cols = pdata.matrix_info(idx)
+        nq = 1 << log_quotient_size
+        if nq > rows:
+            raise ValueError("quotient domain larger than the committed LDE (needs quotient_degree <= blowup)")
+        return ptr, nq, cols
