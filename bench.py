@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- commitment hot path of multi-stark on B200 (see DESIGN.md "Measurement").
+
+A step = one pass of the hot path over one batch of synthetic input: the two trace commitments of
+BASELINE.json configs[1] (U32-add circuit with lookups at 2^20 rows + the 256-row byte table,
+log_blowup 1): stage-1 `pcs.commit` (reference src/prover.rs:350) and stage-2 `pcs.commit`
+(src/prover.rs:419) -- coset LDE of every matrix + BLAKE3 Merkle tree, roots read back.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]       our CUDA path (one JSON line on rank 0)
+  python bench.py --impl reference ...                      CPU restatement of the reference path
+
+metric = LDE+Merkle Gelem/s (committed LDE elements sum(n*B*w) per second, whole job).
+`value`: inputs resident in HBM.  `e2e`: through the host-pointer C-ABI call (`msgpu_commit`) with
+pinned host buffers, H2D copies and the root D2H inside the timed region."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P = 2**64 - 2**32 + 1
+
+
+# ------------------------------------------------------------------------------------------------
+# workload (reference benches/multi_stark.rs:171-217): U32Add trace rows = [x bytes, y bytes, z bytes,
+# carry, 1] from two xorshift32 streams; byte table multiplicities. Stage-2 (lookup accumulator)
+# columns are synthetic field elements of the stage-2 shape (26 / 2 base columns).
+# ------------------------------------------------------------------------------------------------
+def xorshift_stream(seed, n):
+    out = np.empty(n, dtype=np.uint32)
+    x = seed
+    for i in range(n):
+        x ^= (x << 13) & 0xFFFFFFFF
+        x ^= x >> 17
+        x ^= (x << 5) & 0xFFFFFFFF
+        out[i] = x
+    return out
+
+
+def u32_add_workload(log_rows, seed=0):
+    n = 1 << log_rows
+    cache = os.path.join("/tmp", "msb200_u32add_%d.npz" % log_rows)
+    if os.path.exists(cache):
+        z = np.load(cache)
+        x, y = z["x"], z["y"]
+    else:
+        x = xorshift_stream(0xDEADBEEF, n)
+        y = xorshift_stream(0xCAFEBABE, n)
+        try:
+            np.savez(cache, x=x, y=y)
+        except OSError:
+            pass
+    zsum = x.astype(np.uint64) + y.astype(np.uint64)
+    z = (zsum & 0xFFFFFFFF).astype(np.uint32)
+    carry = (zsum >> 32).astype(np.uint64)
+    main = np.empty((n, 14), dtype=np.uint64)
+    for k, v in enumerate((x, y, z)):
+        for b in range(4):
+            main[:, 4 * k + b] = (v >> (8 * b)) & 0xFF
+    main[:, 12] = carry
+    main[:, 13] = 1
+    mult = np.bincount(main[:, :12].astype(np.int64).reshape(-1), minlength=256).astype(np.uint64)
+    byte_main = mult.reshape(256, 1)
+    rng = np.random.default_rng(seed + 1)
+    s2_main = rng.integers(0, P, size=(n, 26), dtype=np.uint64)
+    s2_byte = rng.integers(0, P, size=(256, 2), dtype=np.uint64)
+    # the two commit calls of prove(): stage 1 then stage 2, matrices in circuit order
+    return [[byte_main, main], [s2_byte, s2_main]]
+
+
+def committed_elements(stages, log_blowup):
+    return sum(m.shape[0] * m.shape[1] for st in stages for m in st) << log_blowup
+
+
+def lde_bytes(stages, log_blowup):
+    """LDE of n x w moves 8*n*w*(1+B) compulsory bytes."""
+    return sum(8 * m.shape[0] * m.shape[1] * (1 + (1 << log_blowup)) for st in stages for m in st)
+
+
+def merkle_bytes(stages, log_blowup):
+    """8*nB*W + 32*nB (leaves) + 96*(nB - 1) (nodes) per tree."""
+    tot = 0
+    for st in stages:
+        nb = max(m.shape[0] for m in st) << log_blowup
+        tot += sum(8 * (m.shape[0] << log_blowup) * m.shape[1] + 32 * (m.shape[0] << log_blowup) for m in st)
+        tot += 96 * (nb - 1)
+    return tot
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def load_oracle():
+    """CPU restatement of the reference path (oracle/): ONLY for the cpu_baseline / --impl reference legs."""
+    from tests import _oracle
+    return _oracle, _oracle.lib()
+
+
+def cpu_commit_time(stages, log_blowup, reps=1):
+    orc, L = load_oracle()
+    # warm the twiddle caches on a tiny instance of the same shapes
+    for st in stages:
+        _, h = orc.pcs_commit(L, [m[:min(len(m), 64)] for m in st], log_blowup)
+        L.orc_mmcs_free(h)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        for st in stages:
+            _, h = orc.pcs_commit(L, st, log_blowup)
+            L.orc_mmcs_free(h)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best, int(L.orc_num_threads())
+
+
+def sample_stages(stages, log_sample):
+    """Bounded sample of the workload for the CPU legs: the first 2^log_sample rows of the tall matrices."""
+    n = 1 << log_sample
+    return [[m if m.shape[0] <= n else m[:n] for m in st] for st in stages]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    stages = u32_add_workload(args.log_rows)
+    log_sample = min(args.log_rows, args.cpu_log_rows)
+    sample = sample_stages(stages, log_sample)
+    for _ in range(min(args.warmup, 1)):
+        cpu_commit_time(sample, args.log_blowup)
+    times = []
+    threads = 1
+    for _ in range(args.steps):
+        dt, threads = cpu_commit_time(sample, args.log_blowup)
+        times.append(dt)
+    elems = committed_elements(sample, args.log_blowup)
+    ms = 1e3 * float(np.mean(times))
+    value = elems / (ms / 1e3) / 1e9
+    desc = "first 2^%d of 2^%d rows of each trace matrix, %d steps" % (log_sample, args.log_rows, args.steps)
+    print(json.dumps({
+        "impl": "reference", "metric": "lde_merkle_gelem_per_s", "value": value, "unit": "Gelem/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "Gelem/s", "cores": threads, "kind": "port", "sample": desc,
+                         "note": "C++/OpenMP restatement of the reference path (oracle/); the Rust reference cannot be "
+                                 "built here (no cargo, Plonky3 un-vendored)"},
+        "e2e": {"value": value, "unit": "Gelem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args):
+    return {"workload": "BASELINE configs[1]: U32-add circuit with lookups at 2^%d rows + 256-row byte table, "
+                        "stage-1 (w=1,14) and stage-2 (w=2,26) pcs.commit, log_blowup=%d" % (args.log_rows, args.log_blowup),
+            "log_rows": args.log_rows, "log_blowup": args.log_blowup,
+            "cache": "inputs (%d MB/step) and LDE outputs exceed the 126 MB L2; no explicit flush" %
+                     ((40 << args.log_rows) * 8 >> 20)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-rows", type=int, default=20)
+    ap.add_argument("--log-blowup", type=int, default=1)
+    ap.add_argument("--cpu-log-rows", type=int, default=18, help="rows of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import multi_stark_b200 as ms
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libmsgpu has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    stages = u32_add_workload(args.log_rows, seed=rank)
+    B = args.log_blowup
+    stream = torch.cuda.Stream()  # a real (non-default) stream shared by torch's events and libmsgpu's launches
+    torch.cuda.set_stream(stream)
+    ctx = ms.GpuContext(local_rank, stream=stream.cuda_stream)
+    pcs = ms.GpuPcs(ctx, B)
+
+    # host side: pinned buffers (what a Rust caller would hand to msgpu_commit); device side: resident copies
+    pinned = [[torch.from_numpy(m.view(np.int64)).pin_memory() for m in st] for st in stages]
+    pinned_np = [[t.numpy().view(np.uint64) for t in st] for st in pinned]
+    resident = [[t.cuda(non_blocking=True) for t in st] for st in pinned]
+    resident_args = [[(t.data_ptr(), t.shape[0], t.shape[1]) for t in st] for st in resident]
+    torch.cuda.synchronize()
+
+    def step_resident():
+        roots = []
+        for st in resident_args:
+            root, pd = pcs.commit_dev(st)
+            roots.append(bytes(root))
+            pd.free()
+        return roots
+
+    def step_e2e():
+        roots = []
+        for st in pinned_np:
+            root, pd = pcs.commit(st)
+            roots.append(bytes(root))
+            pd.free()
+        return roots
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        if profile:
+            ctx.profile_begin()
+        l0 = ctx.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_total = e0.elapsed_time(e1)
+        prof = ctx.profile_end() if profile else None
+        launches = ctx.launches - l0
+        if world > 1:
+            t = torch.tensor([ms_total], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_total = float(t.item())
+        barrier()
+        return ms_total, launches, prof, out
+
+    for _ in range(max(args.warmup, 3)):
+        r_res = step_resident()
+    for _ in range(2):
+        r_e2e = step_e2e()
+    assert r_res == r_e2e, "resident and host-pointer paths disagree"
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_res, launches, prof, _ = timed(step_resident, args.steps, profile=True)
+    clocks = sampler.stop()
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps)
+
+    elems = committed_elements(stages, B)
+    ms_step = ms_res / args.steps
+    value = world * elems / (ms_step / 1e3) / 1e9
+    e2e_value = world * elems / (ms_e2e / args.steps / 1e3) / 1e9
+    h2d = sum(m.nbytes for st in stages for m in st)
+
+    # roofline of the dominant stage: algorithmic bytes / CUDA-event time of its launches
+    peak, peak_src = measured_peaks()
+    stage_ms, stage_launch, kernels = {}, {}, []
+    for rec in prof:
+        stage_ms[rec["stage"]] = stage_ms.get(rec["stage"], 0.0) + rec["ms"] / args.steps
+        stage_launch[rec["stage"]] = stage_launch.get(rec["stage"], 0) + rec["launches"] // args.steps
+        kernels.append({"stage": rec["stage"], "kernel": rec["kernel"], "launches_per_step": rec["launches"] // args.steps,
+                        "ms_per_step": rec["ms"] / args.steps})
+    alg = {"lde": lde_bytes(stages, B), "merkle": merkle_bytes(stages, B)}
+    stages_out = []
+    for st, msv in stage_ms.items():
+        if st in alg and msv > 0:
+            gbs = alg[st] / (msv / 1e3) / 1e9
+            stages_out.append({"stage": st, "ms_per_step": msv, "launches_per_step": stage_launch[st],
+                               "algorithmic_bytes": alg[st], "achieved_gbs": gbs, "frac": gbs / peak})
+    dom = max(stages_out, key=lambda s: s["ms_per_step"]) if stages_out else None
+    roofline = None
+    if dom:
+        roofline = {"bound": "hbm", "kernel": "%s stage (%d launches/step)" % (dom["stage"], dom["launches_per_step"]),
+                    "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_step": dom["algorithmic_bytes"],
+                    "share_of_step": dom["ms_per_step"] / ms_step, "stages": stages_out, "kernels": kernels}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        log_sample = min(args.log_rows, args.cpu_log_rows)
+        sample = sample_stages(stages, log_sample)
+        dt, threads = cpu_commit_time(sample, B, reps=2)
+        cpu = {"value": committed_elements(sample, B) / dt / 1e9, "unit": "Gelem/s", "cores": threads, "kind": "port",
+               "sample": "first 2^%d of 2^%d rows of each trace matrix, best of 2" % (log_sample, args.log_rows)}
+        # parity spot check of the timed path against the oracle on the sample
+        orc, L = load_oracle()
+        for st_full, st in zip(stages, sample):
+            want, h = orc.pcs_commit(L, st, B)
+            L.orc_mmcs_free(h)
+            got, pd = pcs.commit(st)
+            pd.free()
+            assert bytes(got) == want, "GPU root differs from the oracle"
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "lde_merkle_gelem_per_s", "value": value, "unit": "Gelem/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args),
+            "e2e": {"value": e2e_value, "unit": "Gelem/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

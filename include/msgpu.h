@@ -44,6 +44,12 @@ void* msgpu_stream(msgpu_ctx* ctx);
 /* number of kernels this library has launched on the context (bench.py `gpu_launches`) */
 uint64_t msgpu_launch_count(msgpu_ctx* ctx);
 
+/* Per-launch timing with CUDA events on the context's stream (bench.py roofline). Between begin and
+ * end every kernel launch of the library is bracketed by two events; end synchronises and writes a
+ * JSON array [{"stage", "kernel", "launches", "ms"}] (NUL-terminated) into json_out. */
+int msgpu_profile_begin(msgpu_ctx* ctx);
+int msgpu_profile_end(msgpu_ctx* ctx, char* json_out, size_t cap);
+
 /* ---- memory ----------------------------------------------------------------------------------- */
 int msgpu_malloc(msgpu_ctx* ctx, size_t bytes, void** dptr);
 int msgpu_free(msgpu_ctx* ctx, void* dptr);

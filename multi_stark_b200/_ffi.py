@@ -19,6 +19,8 @@ SIGNATURES = {
     "msgpu_sync": (C.c_int, [C.c_void_p]),
     "msgpu_stream": (C.c_void_p, [C.c_void_p]),
     "msgpu_launch_count": (C.c_uint64, [C.c_void_p]),
+    "msgpu_profile_begin": (C.c_int, [C.c_void_p]),
+    "msgpu_profile_end": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "msgpu_malloc": (C.c_int, [C.c_void_p, C.c_size_t, c_vpp]),
     "msgpu_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "msgpu_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),

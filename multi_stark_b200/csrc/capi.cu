@@ -89,6 +89,7 @@ static msgpu_pdata* commit_impl(Ctx& c, const u64* const* mats, const u64* heigh
                                          c.stream));
                 continue;
             }
+            StageScope stage_scope(c, "lde");
             DevBuf tmp(c, h * w * 8);
             if (host_inputs) {
                 MSG_CUDA(cudaMemcpyAsync(tmp.p, mats[i], h * w * 8, cudaMemcpyHostToDevice, c.stream));
@@ -182,6 +183,47 @@ int msgpu_host_alloc(size_t bytes, void** hptr) {
 }
 int msgpu_host_free(void* hptr) {
     return guard([&] { MSG_CUDA(cudaFreeHost(hptr)); });
+}
+
+int msgpu_profile_begin(msgpu_ctx* h) {
+    return guard([&] {
+        Ctx& c = h->c;
+        for (auto& r : c.prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        c.prof.clear();
+        c.profiling = true;
+    });
+}
+int msgpu_profile_end(msgpu_ctx* h, char* json_out, size_t cap) {
+    return guard([&] {
+        Ctx& c = h->c;
+        c.profiling = false;
+        c.sync();
+        // aggregate by (stage, kernel)
+        std::map<std::pair<std::string, std::string>, std::pair<double, unsigned long long>> agg;
+        std::vector<std::pair<std::string, std::string>> order;
+        for (auto& r : c.prof) {
+            float ms = 0;
+            MSG_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+            auto key = std::make_pair(std::string(r.stage), std::string(r.kernel));
+            if (!agg.count(key)) order.push_back(key);
+            agg[key].first += ms;
+            agg[key].second += 1;
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+        c.prof.clear();
+        std::string js = "[";
+        for (size_t i = 0; i < order.size(); i++) {
+            auto& v = agg[order[i]];
+            char buf[256];
+            snprintf(buf, sizeof buf, "%s{\"stage\": \"%s\", \"kernel\": \"%s\", \"launches\": %llu, \"ms\": %.6f}",
+                     i ? ", " : "", order[i].first.c_str(), order[i].second.c_str(), v.second, v.first);
+            js += buf;
+        }
+        js += "]";
+        MSG_REQUIRE(json_out && js.size() + 1 <= cap, "profile_end: output buffer too small");
+        memcpy(json_out, js.c_str(), js.size() + 1);
+    });
 }
 
 // ---- DFT slot -----------------------------------------------------------------------------------

@@ -8,6 +8,7 @@
 namespace msg {
 
 void mmcs_build(Ctx& c, msgpu_pdata* pd) {
+    StageScope stage_scope(c, "merkle");
     MSG_REQUIRE(!pd->mats.empty(), "commit: no matrices given");
     std::vector<size_t> order(pd->mats.size());
     std::iota(order.begin(), order.end(), 0);
@@ -126,10 +127,12 @@ void mmcs_open_batch(Ctx& c, const msgpu_pdata* pd, const u64* indices_host, u64
     }
     if (log_max) {
         u64 total = n_idx * log_max * 2;
-        k_open_proof<<<(unsigned)((total + 127) / 128), 128, 0, c.stream>>>((const uint4*)pd->digests, d_off, log_max, d_idx,
-                                                                            n_idx, (uint4*)d_proof);
+        {
+            KLaunch kl(c, "k_open_proof");
+            k_open_proof<<<(unsigned)((total + 127) / 128), 128, 0, c.stream>>>((const uint4*)pd->digests, d_off, log_max,
+                                                                                d_idx, n_idx, (uint4*)d_proof);
+        }
         MSG_CUDA(cudaGetLastError());
-        c.launches++;
         MSG_CUDA(cudaMemcpyAsync(proof_host, d_proof, n_idx * log_max * 32, cudaMemcpyDeviceToHost, c.stream));
     }
     c.sync();

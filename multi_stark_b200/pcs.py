@@ -56,6 +56,15 @@ class GpuContext:
     def stream(self):
         return self.L.msgpu_stream(self.h)
 
+    def profile_begin(self):
+        check(self.L.msgpu_profile_begin(self.h))
+
+    def profile_end(self):
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        check(self.L.msgpu_profile_end(self.h, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
     # raw device buffers (uint64 elements)
     def malloc(self, nbytes):
         p = C.c_void_p()

@@ -143,3 +143,23 @@ int orc_mmcs_verify(const uint8_t* root32, const u64* heights, const u64* widths
 void orc_mmcs_free(void* h) { delete (OrcTree*)h; }
 
 }  // extern "C"
+
+// ---- Pcs::commit restated (src/prover.rs:350,419): coset LDE (shift GENERATOR) of every matrix in
+// bit-reversed row order, then one MMCS over the LDEs. Returns an OrcTree handle (LDE matrices inside).
+extern "C" void* orc_pcs_commit(const u64* const* mats, const u64* heights, const u64* widths, u64 n, u32 log_blowup,
+                                uint8_t* root32) {
+    auto* t = new OrcTree();
+    for (u64 i = 0; i < n; i++)
+        t->mats.push_back(coset_lde_batch_bitrev(to_matrix(mats[i], heights[i], widths[i]), log_blowup, Fp(GL_GENERATOR)));
+    std::vector<MatView> views;
+    for (auto& m : t->mats) views.push_back(MatView{m.values.data(), m.height(), m.width});
+    try {
+        t->tree = merkle_commit(views);
+    } catch (const std::exception&) {
+        delete t;
+        return nullptr;
+    }
+    memcpy(root32, t->tree.root().data(), 32);
+    return t;
+}
+extern "C" void orc_mmcs_matrix(void* h, u64 idx, u64* out) { from_matrix(((OrcTree*)h)->mats[idx], out); }

@@ -51,6 +51,8 @@ def lib():
         "orc_mmcs_open": (None, [C.c_void_p, C.c_uint64, u64p, u8p]),
         "orc_mmcs_verify": (C.c_int, [u8p, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u8p, C.c_uint64]),
         "orc_mmcs_free": (None, [C.c_void_p]),
+        "orc_pcs_commit": (C.c_void_p, [C.POINTER(C.c_void_p), u64p, u64p, C.c_uint64, C.c_uint32, u8p]),
+        "orc_mmcs_matrix": (None, [C.c_void_p, C.c_uint64, u64p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -118,3 +120,16 @@ class MmcsTree:
         if getattr(self, "h", None):
             self.L.orc_mmcs_free(self.h)
             self.h = None
+
+
+def pcs_commit(L, mats, log_blowup):
+    """Oracle Pcs::commit; returns (root bytes, handle). Free with L.orc_mmcs_free(handle)."""
+    mats = [np.ascontiguousarray(m, dtype=np.uint64) for m in mats]
+    n = len(mats)
+    ptrs = (C.c_void_p * n)(*[m.ctypes.data for m in mats])
+    hs = np.array([m.shape[0] for m in mats], dtype=np.uint64)
+    ws = np.array([m.shape[1] for m in mats], dtype=np.uint64)
+    root = np.zeros(32, dtype=np.uint8)
+    h = L.orc_pcs_commit(ptrs, hs, ws, n, log_blowup, root)
+    assert h, "orc_pcs_commit failed"
+    return bytes(root), h
