@@ -121,6 +121,60 @@ int msgpu_pdata_read_layer(msgpu_ctx* ctx, const msgpu_pdata* pd, uint64_t layer
 int msgpu_open_batch(msgpu_ctx* ctx, const msgpu_pdata* pd, const uint64_t* indices, uint64_t n_idx,
                      uint64_t* opened_out, uint8_t* proof_out);
 
+/* ---- compiled constraint programs (reference `ConstraintGraph`, src/graph.rs:35-76) --------------------
+ * The host compiles a circuit (src/graph.rs:120-188) and hands the flat node vector over; the library
+ * lowers it to bytecode with liveness-based slot allocation for the device interpreter. */
+typedef struct msgpu_program msgpu_program;
+typedef struct msgpu_graph_desc {
+    uint32_t n_nodes;
+    const uint8_t* op;   /* 0 Const 1 Var 2 Public 3 IsFirstRow 4 IsLastRow 5 IsTransition 6 Add 7 Sub 8 Mul 9 Neg
+                            (src/graph.rs:35-46) */
+    const uint32_t* a;   /* Add/Sub/Mul/Neg: first child; Public: index; Var: source (0 preprocessed, 1 main,
+                            2 stage 2) | row offset << 2 (0 current, 1 next)  (src/expr.rs:15-35) */
+    const uint32_t* b;   /* Add/Sub/Mul: second child; Var: column index */
+    const uint64_t* imm; /* Const: canonical value */
+    uint32_t n_zeros;
+    const uint32_t* zeros;          /* constraint roots in fold order (sorted node ids, src/graph.rs:155-156) */
+    uint32_t n_lookups;
+    const uint32_t* lookup_mult;    /* node id of each lookup's multiplicity */
+    const uint32_t* lookup_arg_off; /* n_lookups + 1 offsets into lookup_args */
+    const uint32_t* lookup_args;    /* node ids of the arguments */
+    uint32_t lookup_prefix_len;     /* nodes[..lookup_prefix_len] cover the lookup expressions */
+    uint32_t pre_width, main_width, stage2_width;
+} msgpu_graph_desc;
+int msgpu_program_create(msgpu_ctx* ctx, const msgpu_graph_desc* desc, msgpu_program** out);
+void msgpu_program_free(msgpu_program* prog);
+
+/* Stage-2 (logUp accumulator) trace of one circuit, built on the device from the natural-order traces:
+ * `compute_lookup_values` (src/system.rs:275-328: sweep of the lookup prefix per row, wrap-around next row)
+ * + `LookupValues::stage_2_traces` (src/lookup.rs:472-555: messages beta + fingerprint(gamma, args), batch
+ * inverse, exclusive running sum of multiplicity / message in (row, lookup) order, starting at zero).
+ * main_dev: rows x main_width; pre_dev: rows x pre_width or NULL. stage2_out_dev: rows x stage2_width
+ * (device, written). local_sum receives the circuit's total (2 u64), to be added to the running accumulator. */
+int msgpu_stage2_trace(msgpu_ctx* ctx, const msgpu_program* prog, const uint64_t* pre_dev, const uint64_t* main_dev,
+                       uint64_t rows, const uint64_t* beta2, const uint64_t* gamma2, uint64_t* stage2_out_dev,
+                       uint64_t* local_sum2);
+/* Sum over claims of 1 / (beta + fingerprint(gamma, claim)) (src/prover.rs:381-387). `claims` is a HOST array of
+ * n_claims x claim_len values (all claims of one length per call). out2 += is NOT applied: out2 receives the sum. */
+int msgpu_claims_accumulator(msgpu_ctx* ctx, const uint64_t* claims, uint64_t n_claims, uint64_t claim_len,
+                             const uint64_t* beta2, const uint64_t* gamma2, uint64_t* out2);
+
+/* The quotient stage of one circuit (src/prover.rs:437-519): evaluates the folded constraints on the
+ * quotient domain GENERATOR * H_{n*q} from the committed LDEs (`quotient_values`, src/prover.rs:756-962,
+ * incl. the sweep src/eval.rs:67-106, `logup_constraint_values` src/lookup.rs:152-208, selectors, the
+ * reversed-alpha-power fold and the division by Z_H), then `shifted_quotient_slices` (src/prover.rs:631-679)
+ * and `lde_from_shifted_coefficients` (src/prover.rs:709-717). pd_pre may be NULL. publics8 = (beta, gamma,
+ * acc, next_acc) as base coordinates. Returns a device matrix of (n << log_blowup) rows x 2q columns from
+ * msgpu_malloc (pass it to msgpu_commit_ldes_dev with take_ownership = 1).
+ * quotient_values_out (optional, HOST, n*q*2 values) receives the quotient evaluations in natural order. */
+int msgpu_quotient(msgpu_ctx* ctx, const msgpu_program* prog, const msgpu_pdata* pd_pre, uint64_t idx_pre,
+                   const msgpu_pdata* pd_s1, uint64_t idx_s1, const msgpu_pdata* pd_s2, uint64_t idx_s2, uint32_t log_n,
+                   uint32_t log_quotient_degree, uint32_t log_blowup, const uint64_t* publics8, const uint64_t* alpha2,
+                   uint64_t** lde_out_dev, uint64_t* quotient_values_out);
+/* `shifted_quotient_slices` alone (host in/out; the reference's pinning test src/prover.rs:1006-1041):
+ * in = nq x d quotient evaluations in natural order, out = (nq / q) x (q * d). */
+int msgpu_shifted_quotient_slices(msgpu_ctx* ctx, const uint64_t* in, uint64_t nq, uint64_t d, uint64_t q, uint64_t* out);
+
 /* ---- test hooks --------------------------------------------------------------------------------- */
 /* raw 7-round BLAKE3 compression of a 16-word state and 16 message words (known-answer vector of
  * reference src/test_circuits/blake3.rs:2646-2746); host pointers */

@@ -51,6 +51,15 @@ SIGNATURES = {
     "msgpu_pdata_layer_len": (C.c_uint64, [C.c_void_p, C.c_uint64]),
     "msgpu_pdata_read_layer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "msgpu_open_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "msgpu_program_create": (C.c_int, [C.c_void_p, C.c_void_p, c_vpp]),
+    "msgpu_program_free": (None, [C.c_void_p]),
+    "msgpu_stage2_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
+    "msgpu_claims_accumulator": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]),
+    "msgpu_quotient": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
+                                 C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, c_vpp, C.c_void_p]),
+    "msgpu_shifted_quotient_slices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "msgpu_blake3_compress_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
@@ -88,3 +97,32 @@ def lib():
 def check(code):
     if code != 0:
         raise MsgpuError(code, (lib().msgpu_last_error() or b"").decode("utf-8", "replace"))
+
+
+# ---- libmshost.so: host-side protocol layer (system assembly, workloads, prove driver) ---------------
+_HOST = None
+HOST_SIGNATURES = {
+    "msh_last_error": (C.c_char_p, []),
+    "msh_system_create": (C.c_void_p, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "msh_system_free": (None, [C.c_void_p]),
+    "msh_system_num_circuits": (C.c_uint32, [C.c_void_p]),
+    "msh_circuit_info": (None, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "msh_circuit_graph": (C.c_void_p, [C.c_void_p, C.c_uint32]),
+    "msh_circuit_preprocessed": (None, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "msh_u32add_workload": (None, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "msh_fib_trace": (None, [C.c_uint64, C.c_void_p]),
+}
+
+
+def host_lib():
+    global _HOST
+    if _HOST is not None:
+        return _HOST
+    lib()  # builds both libraries if needed and loads libmsgpu first
+    H = C.CDLL(_build.HOST_LIB)
+    for name, (res, args) in HOST_SIGNATURES.items():
+        fn = getattr(H, name)
+        fn.restype = res
+        fn.argtypes = args
+    _HOST = H
+    return H

@@ -29,7 +29,7 @@ def _deps():
 
 
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(os.path.join(HERE, "libmshost.so")):
         return True
     t = os.path.getmtime(LIB)
     return any(os.path.getmtime(d) > t for d in _deps())
@@ -57,7 +57,22 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    build_host()
     return LIB
+
+
+HOST_LIB = os.path.join(HERE, "libmshost.so")
+
+
+def build_host():
+    """libmshost.so: the host-side protocol layer (C++17, no CUDA) over the libmsgpu C ABI."""
+    src = sorted(os.path.join(HERE, "host", f) for f in os.listdir(os.path.join(HERE, "host")) if f.endswith(".cpp"))
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-o", HOST_LIB, *src,
+           "-L" + HERE, "-lmsgpu", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("host library build failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return HOST_LIB
 
 
 if __name__ == "__main__":

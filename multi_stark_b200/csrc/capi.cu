@@ -1,17 +1,13 @@
 // extern "C" surface of libmsgpu (include/msgpu.h). Every entry point catches C++ exceptions and
 // turns them into error codes + a thread-local message; nothing unwinds across the ABI.
-#include "../../include/msgpu.h"
-#include "internal.hpp"
+#include "capi_common.hpp"
 #include "mmcs.hpp"
 #include <cstring>
-
-struct msgpu_ctx {
-    msg::Ctx c;
-};
 
 namespace msg {
 
 static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
 
 void* Ctx::alloc(size_t bytes) {
     void* p = nullptr;
@@ -24,34 +20,6 @@ void Ctx::free(void* p) {
 }
 
 void b3_compress_raw_dev(Ctx& c, const u32* st, const u32* msg, u32* out);
-
-template <class F>
-static int guard(F&& f) {
-    try {
-        f();
-        return MSGPU_OK;
-    } catch (const Error& e) {
-        g_last_error = e.what();
-        return e.code;
-    } catch (const std::exception& e) {
-        g_last_error = e.what();
-        return MSGPU_ERR_INTERNAL;
-    } catch (...) {
-        g_last_error = "unknown error";
-        return MSGPU_ERR_INTERNAL;
-    }
-}
-
-struct DevBuf {  // RAII stream-ordered buffer
-    Ctx& c;
-    void* p = nullptr;
-    DevBuf(Ctx& c_, size_t bytes) : c(c_) { p = c.alloc(bytes); }
-    ~DevBuf() {
-        if (p) cudaFreeAsync(p, c.stream);
-    }
-    u64* u() const { return (u64*)p; }
-    void* release() { void* r = p; p = nullptr; return r; }
-};
 
 static void check_shape(u64 rows, u64 cols) {
     MSG_REQUIRE(is_pow2(rows), "matrix height must be a power of two");

@@ -16,33 +16,98 @@ typedef unsigned int u32;
 
 namespace gl {
 
-__device__ __forceinline__ u64 canon(u64 x) { return x >= GLD_P ? x - GLD_P : x; }
+// All arithmetic is written as 32-bit carry chains (add.cc / addc / madc): a conditional
+// "+- p" becomes an add of the carry mask (2^64 - p = 2^32 - 1 has a single non-zero word), so there are
+// no 64-bit compares or selects on the hot path.
+
+__device__ __forceinline__ u64 pack(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
+
+// x any u64 -> canonical
+__device__ __forceinline__ u64 canon(u64 x) {
+    u32 x0 = (u32)x, x1 = (u32)(x >> 32), r0, r1;
+    asm("{\n\t"
+        ".reg .u32 t, k;\n\t"
+        "add.cc.u32 t, %2, 0xffffffff;\n\t"   // x + (2^32 - 1) carries out of 64 bits iff x >= p
+        "addc.cc.u32 t, %3, 0;\n\t"
+        "addc.u32 k, 0, 0;\n\t"
+        "neg.s32 k, k;\n\t"                   // mask
+        "add.cc.u32 %0, %2, k;\n\t"           // x - p == x + (2^32 - 1) mod 2^64
+        "addc.u32 %1, %3, 0;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"(x0), "r"(x1));
+    return pack(r0, r1);
+}
+
+// a any u64, b canonical (< p) -> some u64 congruent to a + b (NOT necessarily canonical)
+__device__ __forceinline__ u64 add_lazy(u64 a, u64 b) {
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), r0, r1;
+    asm("{\n\t"
+        ".reg .u32 k;\n\t"
+        "add.cc.u32 %0, %2, %4;\n\t"
+        "addc.cc.u32 %1, %3, %5;\n\t"
+        "addc.u32 k, 0, 0;\n\t"
+        "neg.s32 k, k;\n\t"
+        "add.cc.u32 %0, %0, k;\n\t"   // + (2^32 - 1) when the 64-bit sum wrapped; cannot wrap again since b < p
+        "addc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return pack(r0, r1);
+}
+// a any u64, b canonical (< p) -> some u64 congruent to a - b
+__device__ __forceinline__ u64 sub_lazy(u64 a, u64 b) {
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), r0, r1;
+    asm("{\n\t"
+        ".reg .u32 m;\n\t"
+        "sub.cc.u32 %0, %2, %4;\n\t"
+        "subc.cc.u32 %1, %3, %5;\n\t"
+        "subc.u32 m, 0, 0;\n\t"       // 0xffffffff on borrow
+        "sub.cc.u32 %0, %0, m;\n\t"   // - (2^32 - 1) == + p; cannot borrow again since b < p
+        "subc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return pack(r0, r1);
+}
 
 // a, b canonical -> canonical.
-__device__ __forceinline__ u64 add(u64 a, u64 b) {
-    u64 s = a + b;
-    u64 t = s + GLD_EPS;  // == s - p (mod 2^64); carries out iff s >= p
-    // a + b < 2p, so at most one subtraction of p is needed
-    return (s < a || t < s) ? t : s;
-}
-__device__ __forceinline__ u64 sub(u64 a, u64 b) {
-    u64 d = a - b;
-    return a < b ? d - GLD_EPS : d;  // d + p (mod 2^64)
-}
+__device__ __forceinline__ u64 add(u64 a, u64 b) { return canon(add_lazy(a, b)); }
+// a, b canonical -> canonical (a - b + p < 2^64 and < p after the fix, so sub_lazy is already canonical)
+__device__ __forceinline__ u64 sub(u64 a, u64 b) { return sub_lazy(a, b); }
 __device__ __forceinline__ u64 neg(u64 a) { return a ? GLD_P - a : 0; }
 
-// 128-bit (hi:lo) -> canonical. 2^64 = 2^32 - 1, 2^96 = -1 (mod p).
-__device__ __forceinline__ u64 reduce128(u64 lo, u64 hi) {
-    u32 hh = (u32)(hi >> 32), hl = (u32)hi;
-    u64 t0 = lo - hh;
-    if (lo < hh) t0 -= GLD_EPS;
-    u64 t1 = (u64)hl * GLD_EPS;
-    u64 r = t0 + t1;
-    if (r < t1) r += GLD_EPS;
-    return canon(r);
+// 128-bit (hi:lo) -> u64 congruent mod p (not canonical). 2^64 = 2^32 - 1, 2^96 = -1 (mod p).
+__device__ __forceinline__ u64 reduce128_lazy(u64 lo, u64 hi) {
+    u32 l0 = (u32)lo, l1 = (u32)(lo >> 32), hl = (u32)hi, hh = (u32)(hi >> 32), r0, r1;
+    asm("{\n\t"
+        ".reg .u32 m, k, t0, t1;\n\t"
+        // t = lo - hh (+p on borrow)
+        "sub.cc.u32 %0, %2, %5;\n\t"
+        "subc.cc.u32 %1, %3, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t"
+        // u = hl * (2^32 - 1) = (hl << 32) - hl
+        "sub.cc.u32 t0, 0, %4;\n\t"
+        "subc.u32 t1, %4, 0;\n\t"
+        // r = t + u (+ (2^32 - 1) on carry; cannot carry twice, u <= (2^32-1)^2)
+        "add.cc.u32 %0, %0, t0;\n\t"
+        "addc.cc.u32 %1, %1, t1;\n\t"
+        "addc.u32 k, 0, 0;\n\t"
+        "neg.s32 k, k;\n\t"
+        "add.cc.u32 %0, %0, k;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"(l0), "r"(l1), "r"(hl), "r"(hh));
+    return pack(r0, r1);
 }
+__device__ __forceinline__ u64 reduce128(u64 lo, u64 hi) { return canon(reduce128_lazy(lo, hi)); }
 // any u64 operands (not necessarily canonical) -> canonical
 __device__ __forceinline__ u64 mul(u64 a, u64 b) { return reduce128(a * b, __umul64hi(a, b)); }
+// any u64 operands -> some congruent u64
+__device__ __forceinline__ u64 mul_lazy(u64 a, u64 b) { return reduce128_lazy(a * b, __umul64hi(a, b)); }
 __device__ __forceinline__ u64 sqr(u64 a) { return mul(a, a); }
 
 __device__ __forceinline__ u64 pow(u64 a, u64 e) {

@@ -49,6 +49,10 @@ struct Ctx {
     std::map<std::tuple<u64, u64, u32>, DevPow> pow_cache;
     std::map<std::tuple<u32, u32, u64>, gl::PowTable*> coset_cache;  // (log_n, added_bits, shift) -> device array [B]
     std::vector<void*> owned;  // table allocations freed with the context
+    struct SelCache {
+        u64 *first, *last, *inv_zh;
+    };
+    std::map<std::pair<u32, u32>, SelCache> sel_cache;  // selectors on the quotient coset per (log_n, log_q)
 
     // optional per-launch timing (bench.py roofline): CUDA events on the launching stream
     struct ProfRec {

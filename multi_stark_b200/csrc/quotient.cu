@@ -1,0 +1,844 @@
+// Constraint programs on the device: the quotient stage and the stage-2 (logUp) trace construction.
+//
+// Replaces, for one circuit, the reference's
+//   quotient_values + quotient_values_inner      src/prover.rs:756-962
+//   ConstraintGraph::sweep_range                 src/eval.rs:67-106
+//   logup_constraint_values (D = 2 path)         src/lookup.rs:152-208
+//   selectors_on_coset (p3-commit)               call src/prover.rs:775
+//   shifted_quotient_slices                      src/prover.rs:631-679
+//   compute_lookup_values                        src/system.rs:275-328
+//   LookupValues::stage_2_traces                 src/lookup.rs:472-555
+//   initial accumulator over the claims          src/prover.rs:381-387
+//
+// The compiled ConstraintGraph (a flat, topologically ordered node vector) is lowered on the host side of
+// this library to bytecode with liveness-based slot allocation; one thread evaluates one row with its slot
+// file in local memory (instructions are uniform across the warp, so the fetches broadcast). Rows of the
+// committed LDEs are read where they lie: the quotient domain GENERATOR * H_{nq} is the first nq stored
+// rows of every LDE in bit-reversed order, so the "current row" stream is fully coalesced.
+#include "capi_common.hpp"
+#include "mmcs.hpp"
+#include <algorithm>
+#include <cstring>
+
+namespace msg {
+
+enum : u32 { OP_CONST = 0, OP_VAR = 1, OP_PUBLIC = 2, OP_FIRST = 3, OP_LAST = 4, OP_TRANS = 5, OP_ADD = 6, OP_SUB = 7, OP_MUL = 8, OP_NEG = 9 };
+
+struct alignas(16) Instr {  // 32 bytes: two 16-byte uniform loads per instruction
+    u32 op, dst, a, b;
+    u64 imm;
+    u64 pad;
+};
+
+struct Lowered {
+    std::vector<Instr> code;
+    std::vector<u32> slot_of;  // node id -> slot (only meaningful for pinned nodes after the run)
+    u32 n_slots = 0;
+};
+
+// Lower nodes [0, len) keeping `pinned` nodes alive to the end. Dead nodes are dropped.
+static Lowered lower(const msgpu_graph_desc& g, u32 len, const std::vector<u32>& pinned) {
+    const u32 NONE = 0xffffffffu;
+    std::vector<u32> last_use(len, NONE);
+    std::vector<char> pin(len, 0), live(len, 0);
+    for (u32 p : pinned) {
+        MSG_REQUIRE(p < len, "program: pinned node outside the evaluated range");
+        pin[p] = 1;
+        live[p] = 1;
+    }
+    auto nchildren = [&](u32 i) -> int {
+        uint8_t op = g.op[i];
+        if (op == OP_ADD || op == OP_SUB || op == OP_MUL) return 2;
+        if (op == OP_NEG) return 1;
+        return 0;
+    };
+    for (u32 i = len; i-- > 0;) {  // liveness, children have smaller ids
+        if (!live[i]) continue;
+        int nc = nchildren(i);
+        if (nc >= 1) {
+            MSG_REQUIRE(g.a[i] < i, "program: nodes are not topologically ordered");
+            live[g.a[i]] = 1;
+            if (last_use[g.a[i]] == NONE) last_use[g.a[i]] = i;
+        }
+        if (nc == 2) {
+            MSG_REQUIRE(g.b[i] < i, "program: nodes are not topologically ordered");
+            live[g.b[i]] = 1;
+            if (last_use[g.b[i]] == NONE) last_use[g.b[i]] = i;
+        }
+    }
+    Lowered out;
+    out.slot_of.assign(len, NONE);
+    std::vector<u32> free_slots;
+    for (u32 i = 0; i < len; i++) {
+        if (!live[i]) continue;
+        Instr in{};
+        in.op = g.op[i];
+        MSG_REQUIRE(in.op <= OP_NEG, "program: bad opcode");
+        int nc = nchildren(i);
+        if (nc >= 1) in.a = out.slot_of[g.a[i]];
+        if (nc == 2) in.b = out.slot_of[g.b[i]];
+        if (in.op == OP_CONST) {
+            MSG_REQUIRE(g.imm[i] < GLD_P, "program: constant is not canonical");
+            in.imm = g.imm[i];
+        }
+        if (in.op == OP_VAR) {
+            u32 src = g.a[i] & 3, width = src == 0 ? g.pre_width : src == 1 ? g.main_width : g.stage2_width;
+            MSG_REQUIRE(src <= 2 && (g.a[i] >> 2) <= 1 && g.b[i] < width, "program: column reference out of range");
+            in.a = g.a[i];
+            in.b = g.b[i];
+        }
+        if (in.op == OP_PUBLIC) {
+            MSG_REQUIRE(g.a[i] < 8, "program: public index out of range");
+            in.a = g.a[i];
+        }
+        // operands dying here release their slots first: the interpreter reads both operands before writing
+        if (nc >= 1 && !pin[g.a[i]] && last_use[g.a[i]] == i) free_slots.push_back(out.slot_of[g.a[i]]);
+        if (nc == 2 && g.b[i] != g.a[i] && !pin[g.b[i]] && last_use[g.b[i]] == i) free_slots.push_back(out.slot_of[g.b[i]]);
+        u32 slot;
+        if (!free_slots.empty()) {
+            slot = free_slots.back();
+            free_slots.pop_back();
+        } else {
+            slot = out.n_slots++;
+        }
+        out.slot_of[i] = slot;
+        in.dst = slot;
+        out.code.push_back(in);
+    }
+    if (out.n_slots == 0) out.n_slots = 1;
+    return out;
+}
+
+}  // namespace msg
+
+struct msgpu_program {
+    msg::Ctx* ctx = nullptr;
+    msg::Instr* d_full = nullptr;
+    msg::Instr* d_prefix = nullptr;
+    u32 n_full = 0, n_prefix = 0, slots_full = 0, slots_prefix = 0;
+    u32 n_zeros = 0, n_lookups = 0, n_args = 0;
+    u32* d_zero_slots = nullptr;                       // full program
+    u32 *d_mult_full = nullptr, *d_args_full = nullptr;    // slots in the full program
+    u32 *d_mult_prefix = nullptr, *d_args_prefix = nullptr;  // slots in the prefix program
+    u32* d_arg_off = nullptr;
+    u32 pre_width = 0, main_width = 0, stage2_width = 0;
+    std::vector<void*> owned;
+};
+
+namespace msg {
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ gl::e2 e2_mul_k(gl::e2 x, gl::e2 y) { return gl::e2_mul(x, y); }
+
+// a^(p-2) with 63 squarings + 10 multiplications (p - 2 = (2^32 - 2) * 2^32 + (2^32 - 1))
+__device__ __forceinline__ u64 fp_inv(u64 x) {
+    auto sqn = [](u64 v, int n) { for (int i = 0; i < n; i++) v = gl::mul(v, v); return v; };
+    u64 t2 = gl::mul(sqn(x, 1), x);
+    u64 t4 = gl::mul(sqn(t2, 2), t2);
+    u64 t8 = gl::mul(sqn(t4, 4), t4);
+    u64 t16 = gl::mul(sqn(t8, 8), t8);
+    u64 t24 = gl::mul(sqn(t16, 8), t8);
+    u64 t28 = gl::mul(sqn(t24, 4), t4);
+    u64 t30 = gl::mul(sqn(t28, 2), t2);
+    u64 t31 = gl::mul(sqn(t30, 1), x);
+    u64 a = sqn(t31, 1);       // x^(2^32 - 2)
+    u64 b = gl::mul(a, x);     // x^(2^32 - 1)
+    return gl::mul(sqn(a, 32), b);
+}
+__device__ __forceinline__ gl::e2 e2_inverse(gl::e2 x) {
+    u64 norm = gl::sub(gl::sqr(x.a), gl::mul7(gl::sqr(x.b)));
+    u64 ni = fp_inv(norm);
+    return gl::e2_make(gl::mul(x.a, ni), gl::mul(gl::neg(x.b), ni));
+}
+
+struct RowCtx {
+    const u64* rows[3][2];  // [source][offset] -> pointer to the row
+    const u64* publics;
+    u64 first, last, trans;
+};
+
+template <int NSLOT>
+__device__ __forceinline__ void run_program(const Instr* __restrict__ prog, u32 n, u64* slots, const RowCtx& cx) {
+    for (u32 pc = 0; pc < n; pc++) {
+        const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(prog + pc));
+        const u64 imm = __ldg(reinterpret_cast<const u64*>(prog + pc) + 2);
+        static_assert(sizeof(Instr) == 32, "Instr must be 32 bytes");
+        const u32 op = w0.x, dst = w0.y, a = w0.z, b = w0.w;
+        u64 v;
+        switch (op) {
+            case OP_CONST: v = imm; break;
+            case OP_VAR: v = cx.rows[a & 3][a >> 2][b]; break;
+            case OP_PUBLIC: v = cx.publics[a]; break;
+            case OP_FIRST: v = cx.first; break;
+            case OP_LAST: v = cx.last; break;
+            case OP_TRANS: v = cx.trans; break;
+            case OP_ADD: v = gl::add(slots[a], slots[b]); break;
+            case OP_SUB: v = gl::sub(slots[a], slots[b]); break;
+            case OP_MUL: v = gl::mul(slots[a], slots[b]); break;
+            default: v = gl::neg(slots[a]); break;
+        }
+        slots[dst] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// selectors on the quotient coset, in STORED (bit-reversed) order; cached per (log_n, log_q)
+// ------------------------------------------------------------------------------------------------
+struct SelParams {
+    gl::PowTable xtab;   // 7 * w_{nq}^e
+    const u64* zh;       // q entries: Z_H on the coset, indexed by i mod q
+    u64 g_inv;           // w_n^{-1}
+    u64* first;
+    u64* last;
+    u32 log_nq, log_q;
+};
+constexpr int kSelPerThread = 4;
+__global__ void __launch_bounds__(256) k_selectors(SelParams p) {
+    const u64 nq = 1ull << p.log_nq;
+    u64 s0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * kSelPerThread;
+    if (s0 >= nq) return;
+    u64 den[2 * kSelPerThread], pref[2 * kSelPerThread], zh[kSelPerThread];
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < kSelPerThread; k++) {
+        u64 s = s0 + k;
+        if (s >= nq) break;
+        u64 i = gl::rev_bits((u32)s, p.log_nq);
+        u64 x = gl::pow_lookup(p.xtab, i);
+        den[2 * k] = gl::sub(x, 1);
+        den[2 * k + 1] = gl::sub(x, p.g_inv);
+        zh[k] = p.zh[i & ((1ull << p.log_q) - 1)];
+        cnt = k + 1;
+    }
+    u64 acc = 1;
+    for (int k = 0; k < 2 * cnt; k++) { pref[k] = acc; acc = gl::mul(acc, den[k]); }
+    u64 inv = fp_inv(acc);
+    for (int k = 2 * cnt; k-- > 0;) {
+        u64 d = den[k];
+        den[k] = gl::mul(inv, pref[k]);
+        inv = gl::mul(inv, d);
+    }
+    for (int k = 0; k < cnt; k++) {
+        p.first[s0 + k] = gl::mul(zh[k], den[2 * k]);
+        p.last[s0 + k] = gl::mul(zh[k], den[2 * k + 1]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// quotient evaluation: one thread per stored row of the quotient domain
+// ------------------------------------------------------------------------------------------------
+struct QuotParams {
+    const Instr* prog;
+    const u32* zero_slots;
+    const u32 *lk_mult, *lk_argoff, *lk_args;
+    const u64 *pre, *s1, *s2;
+    const u64* apow;  // constraint_count x 2: weight of constraint j = alpha^{k-1-j}
+    const u64 *sel_first, *sel_last, *inv_zh;
+    u64* out;  // nq x 2, natural order
+    gl::PowTable xtab;
+    u64 publics[8];
+    u64 delta[2];
+    u64 g_inv;
+    u32 n_instr, n_zeros, n_lookups;
+    u32 wpre, w1, w2;
+    u32 log_nq, log_q;
+};
+
+template <int NSLOT>
+__global__ void __launch_bounds__(128) k_quotient_eval(QuotParams p) {
+    const u64 nq = 1ull << p.log_nq;
+    const u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nq) return;
+    const u64 i = gl::rev_bits((u32)s, p.log_nq);
+    const u64 inext = (i + (1ull << p.log_q)) & (nq - 1);
+    const u64 sn = gl::rev_bits((u32)inext, p.log_nq);
+    RowCtx cx;
+    cx.rows[0][0] = p.pre + s * p.wpre;
+    cx.rows[0][1] = p.pre + sn * p.wpre;
+    cx.rows[1][0] = p.s1 + s * p.w1;
+    cx.rows[1][1] = p.s1 + sn * p.w1;
+    cx.rows[2][0] = p.s2 + s * p.w2;
+    cx.rows[2][1] = p.s2 + sn * p.w2;
+    cx.publics = p.publics;
+    cx.first = p.sel_first[s];
+    cx.last = p.sel_last[s];
+    cx.trans = gl::sub(gl::pow_lookup(p.xtab, i), p.g_inv);
+    u64 slots[NSLOT];
+    run_program<NSLOT>(p.prog, p.n_instr, slots, cx);
+
+    u64 acc0 = 0, acc1 = 0;
+    u32 ci = 0;
+    for (u32 j = 0; j < p.n_zeros; j++, ci++) {
+        u64 v = slots[p.zero_slots[j]];
+        acc0 = gl::add(acc0, gl::mul(v, __ldg(p.apow + 2 * ci)));
+        acc1 = gl::add(acc1, gl::mul(v, __ldg(p.apow + 2 * ci + 1)));
+    }
+    // logUp constraint values (src/lookup.rs:167-208)
+    const u64* s2c = cx.rows[2][0];
+    const u64* s2n = cx.rows[2][1];
+    const gl::e2 beta = gl::e2_make(p.publics[0], p.publics[1]), gamma = gl::e2_make(p.publics[2], p.publics[3]);
+    const gl::e2 inj = gl::e2_make(gl::mul(cx.last, p.delta[0]), gl::mul(cx.last, p.delta[1]));
+    auto fold = [&](u64 v) {
+        acc0 = gl::add(acc0, gl::mul(v, __ldg(p.apow + 2 * ci)));
+        acc1 = gl::add(acc1, gl::mul(v, __ldg(p.apow + 2 * ci + 1)));
+        ci++;
+    };
+    if (p.n_lookups == 0) {
+        fold(gl::add(gl::sub(s2n[0], s2c[0]), inj.a));
+        fold(gl::add(gl::sub(s2n[1], s2c[1]), inj.b));
+    } else {
+        for (u32 j = 0; j < p.n_lookups; j++) {
+            gl::e2 source = gl::e2_make(s2c[2 * j], s2c[2 * j + 1]);
+            gl::e2 target = j + 1 < p.n_lookups ? gl::e2_make(s2c[2 * j + 2], s2c[2 * j + 3])
+                                                : gl::e2_make(gl::add(s2n[0], inj.a), gl::add(s2n[1], inj.b));
+            gl::e2 f = gl::e2_make(0, 0);
+            for (u32 k = p.lk_argoff[j + 1]; k-- > p.lk_argoff[j];) {
+                f = gl::e2_mul(f, gamma);
+                f.a = gl::add(f.a, slots[p.lk_args[k]]);
+            }
+            gl::e2 c = gl::e2_mul(gl::e2_add(f, beta), gl::e2_sub(target, source));
+            fold(gl::sub(c.a, slots[p.lk_mult[j]]));
+            fold(c.b);
+        }
+    }
+    const u64 iv = p.inv_zh[i & ((1ull << p.log_q) - 1)];
+    p.out[2 * i] = gl::mul(acc0, iv);
+    p.out[2 * i + 1] = gl::mul(acc1, iv);
+}
+
+// out[r][k*d + c] = S[rev((N - (k*n + r)) mod N)][c] * weights[k]     (src/prover.rs:659-677)
+__global__ void k_quotient_slices(const u64* S, u64* out, u32 log_big, u32 log_n, u32 d, const u64* weights) {
+    const u64 big = 1ull << log_big, n = 1ull << log_n, q = big >> log_n;
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= big) return;
+    u64 r = t / q, k = t % q;
+    u64 j = k * n + r;
+    u64 src = gl::rev_bits((u32)((big - j) & (big - 1)), log_big);
+    u64 w = weights[k];
+    for (u32 c = 0; c < d; c++) out[r * (q * d) + k * d + c] = gl::mul(S[src * d + c], w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage-2 trace construction
+// ------------------------------------------------------------------------------------------------
+struct MsgParams {
+    const Instr* prog;
+    const u32 *lk_mult, *lk_argoff, *lk_args;
+    const u64 *pre, *main;
+    u64* msgs;   // rows * L x 2
+    u64* mults;  // rows * L
+    u64 rows;
+    u64 beta[2], gamma[2];
+    u32 n_instr, n_lookups, wpre, wmain;
+};
+template <int NSLOT>
+__global__ void __launch_bounds__(128) k_lookup_messages(MsgParams p) {
+    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.rows) return;
+    const u64 rn = r + 1 == p.rows ? 0 : r + 1;
+    RowCtx cx;
+    cx.rows[0][0] = p.pre + r * p.wpre;
+    cx.rows[0][1] = p.pre + rn * p.wpre;
+    cx.rows[1][0] = p.main + r * p.wmain;
+    cx.rows[1][1] = p.main + rn * p.wmain;
+    cx.rows[2][0] = cx.rows[2][1] = nullptr;  // lookup expressions cannot read stage 2 (src/graph.rs:343-346)
+    cx.publics = nullptr;
+    cx.first = r == 0;
+    cx.last = r + 1 == p.rows;
+    cx.trans = r + 1 != p.rows;
+    u64 slots[NSLOT];
+    run_program<NSLOT>(p.prog, p.n_instr, slots, cx);
+    const gl::e2 beta = gl::e2_make(p.beta[0], p.beta[1]), gamma = gl::e2_make(p.gamma[0], p.gamma[1]);
+    for (u32 j = 0; j < p.n_lookups; j++) {
+        gl::e2 f = gl::e2_make(0, 0);
+        for (u32 k = p.lk_argoff[j + 1]; k-- > p.lk_argoff[j];) {
+            f = gl::e2_mul(f, gamma);
+            f.a = gl::add(f.a, slots[p.lk_args[k]]);
+        }
+        f = gl::e2_add(f, beta);
+        u64 idx = r * p.n_lookups + j;
+        p.msgs[2 * idx] = f.a;
+        p.msgs[2 * idx + 1] = f.b;
+        p.mults[idx] = slots[p.lk_mult[j]];
+    }
+}
+
+constexpr int kScanPerThread = 8;
+constexpr int kScanThreads = 256;
+constexpr int kScanPerBlock = kScanPerThread * kScanThreads;
+
+// block reduction of extension values; result valid in thread 0
+__device__ __forceinline__ gl::e2 block_sum(gl::e2 v, gl::e2* sm) {
+    for (int off = 16; off > 0; off >>= 1) {
+        v.a = gl::add(v.a, __shfl_down_sync(0xffffffffu, v.a, off));
+        v.b = gl::add(v.b, __shfl_down_sync(0xffffffffu, v.b, off));
+    }
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sm[wid] = v;
+    __syncthreads();
+    gl::e2 r = gl::e2_make(0, 0);
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) r = gl::e2_add(r, sm[w]);
+    return r;
+}
+
+// msgs[i] <- mults[i] / msgs[i] (Montgomery batches of 8 per thread); block_sums[b] = sum of the block's terms
+__global__ void __launch_bounds__(kScanThreads) k_terms_and_block_sums(u64* msgs, const u64* mults, u64 total, u64* block_sums) {
+    __shared__ gl::e2 sm[kScanThreads / 32];
+    u64 i0 = ((u64)blockIdx.x * kScanThreads + threadIdx.x) * kScanPerThread;
+    gl::e2 v[kScanPerThread], pref[kScanPerThread];
+    int cnt = 0;
+    for (int k = 0; k < kScanPerThread; k++)
+        if (i0 + k < total) { v[k] = gl::e2_make(msgs[2 * (i0 + k)], msgs[2 * (i0 + k) + 1]); cnt = k + 1; }
+    gl::e2 acc = gl::e2_make(1, 0);
+    for (int k = 0; k < cnt; k++) { pref[k] = acc; acc = gl::e2_mul(acc, v[k]); }
+    gl::e2 inv = cnt ? e2_inverse(acc) : acc;
+    gl::e2 sum = gl::e2_make(0, 0);
+    for (int k = cnt; k-- > 0;) {
+        gl::e2 x = v[k];
+        gl::e2 xi = gl::e2_mul(inv, pref[k]);
+        inv = gl::e2_mul(inv, x);
+        gl::e2 term = gl::e2_mul_base(xi, mults[i0 + k]);
+        msgs[2 * (i0 + k)] = term.a;
+        msgs[2 * (i0 + k) + 1] = term.b;
+        sum = gl::e2_add(sum, term);
+    }
+    gl::e2 bs = block_sum(sum, sm);
+    if (threadIdx.x == 0) { block_sums[2 * blockIdx.x] = bs.a; block_sums[2 * blockIdx.x + 1] = bs.b; }
+}
+
+// in-place exclusive scan of the block sums (single block); total written after the last element
+__global__ void __launch_bounds__(1024) k_scan_block_sums(u64* block_sums, u64 nblocks) {
+    __shared__ gl::e2 sm[1024];
+    // each thread owns a contiguous chunk
+    u64 per = (nblocks + blockDim.x - 1) / blockDim.x;
+    u64 lo = (u64)threadIdx.x * per, hi = min(nblocks, lo + per);
+    gl::e2 s = gl::e2_make(0, 0);
+    for (u64 i = lo; i < hi; i++) s = gl::e2_add(s, gl::e2_make(block_sums[2 * i], block_sums[2 * i + 1]));
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the 1024 chunk sums
+    for (int off = 1; off < (int)blockDim.x; off <<= 1) {
+        gl::e2 t = sm[threadIdx.x];
+        if ((int)threadIdx.x >= off) t = gl::e2_add(t, sm[threadIdx.x - off]);
+        __syncthreads();
+        sm[threadIdx.x] = t;
+        __syncthreads();
+    }
+    gl::e2 run = threadIdx.x ? sm[threadIdx.x - 1] : gl::e2_make(0, 0);
+    for (u64 i = lo; i < hi; i++) {
+        gl::e2 v = gl::e2_make(block_sums[2 * i], block_sums[2 * i + 1]);
+        block_sums[2 * i] = run.a;
+        block_sums[2 * i + 1] = run.b;
+        run = gl::e2_add(run, v);
+    }
+    if (threadIdx.x == blockDim.x - 1) {
+        gl::e2 tot = sm[blockDim.x - 1];
+        block_sums[2 * nblocks] = tot.a;
+        block_sums[2 * nblocks + 1] = tot.b;
+    }
+}
+
+// out[i] = block_offset + exclusive prefix of terms within the block
+__global__ void __launch_bounds__(kScanThreads) k_scan_write(const u64* terms, u64 total, const u64* block_offsets, u64* out) {
+    __shared__ gl::e2 sm[kScanThreads];
+    u64 i0 = ((u64)blockIdx.x * kScanThreads + threadIdx.x) * kScanPerThread;
+    gl::e2 v[kScanPerThread];
+    gl::e2 s = gl::e2_make(0, 0);
+    for (int k = 0; k < kScanPerThread; k++) {
+        v[k] = i0 + k < total ? gl::e2_make(terms[2 * (i0 + k)], terms[2 * (i0 + k) + 1]) : gl::e2_make(0, 0);
+        s = gl::e2_add(s, v[k]);
+    }
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 1; off < kScanThreads; off <<= 1) {
+        gl::e2 t = sm[threadIdx.x];
+        if ((int)threadIdx.x >= off) t = gl::e2_add(t, sm[threadIdx.x - off]);
+        __syncthreads();
+        sm[threadIdx.x] = t;
+        __syncthreads();
+    }
+    gl::e2 run = gl::e2_make(block_offsets[2 * blockIdx.x], block_offsets[2 * blockIdx.x + 1]);
+    if (threadIdx.x) run = gl::e2_add(run, sm[threadIdx.x - 1]);
+    for (int k = 0; k < kScanPerThread; k++) {
+        if (i0 + k >= total) break;
+        out[2 * (i0 + k)] = run.a;
+        out[2 * (i0 + k) + 1] = run.b;
+        run = gl::e2_add(run, v[k]);
+    }
+}
+
+// partial[b] = sum over the block's claims of 1 / (beta + fingerprint(gamma, claim))
+__global__ void __launch_bounds__(kScanThreads) k_claims(const u64* claims, u64 n_claims, u32 len, gl::e2 beta, gl::e2 gamma,
+                                                         u64* partial) {
+    __shared__ gl::e2 sm[kScanThreads / 32];
+    u64 i0 = ((u64)blockIdx.x * kScanThreads + threadIdx.x) * kScanPerThread;
+    gl::e2 v[kScanPerThread], pref[kScanPerThread];
+    int cnt = 0;
+    for (int k = 0; k < kScanPerThread; k++) {
+        if (i0 + k >= n_claims) break;
+        const u64* c = claims + (i0 + k) * len;
+        gl::e2 f = gl::e2_make(0, 0);
+        for (u32 a = len; a-- > 0;) {
+            f = gl::e2_mul(f, gamma);
+            f.a = gl::add(f.a, c[a]);
+        }
+        v[k] = gl::e2_add(f, beta);
+        cnt = k + 1;
+    }
+    gl::e2 acc = gl::e2_make(1, 0);
+    for (int k = 0; k < cnt; k++) { pref[k] = acc; acc = gl::e2_mul(acc, v[k]); }
+    gl::e2 inv = cnt ? e2_inverse(acc) : acc;
+    gl::e2 sum = gl::e2_make(0, 0);
+    for (int k = cnt; k-- > 0;) {
+        sum = gl::e2_add(sum, gl::e2_mul(inv, pref[k]));
+        inv = gl::e2_mul(inv, v[k]);
+    }
+    gl::e2 bs = block_sum(sum, sm);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = bs.a; partial[2 * blockIdx.x + 1] = bs.b; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <class T>
+static T* upload_vec(Ctx& c, msgpu_program* prog, const std::vector<T>& v) {
+    T* d = nullptr;
+    MSG_CUDA(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(T)));
+    prog->owned.push_back(d);
+    if (!v.empty()) MSG_CUDA(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c.stream));
+    return d;
+}
+
+static msgpu_program* program_create(Ctx& c, const msgpu_graph_desc& g) {
+    MSG_REQUIRE(g.lookup_prefix_len <= g.n_nodes, "program: lookup prefix longer than the node vector");
+    MSG_REQUIRE(g.stage2_width == 2 * std::max<u32>(g.n_lookups, 1), "program: stage-2 width must be 2 * max(lookups, 1)");
+    std::vector<u32> pin_lk, pin_all;
+    u32 n_args = g.n_lookups ? g.lookup_arg_off[g.n_lookups] : 0;
+    for (u32 j = 0; j < g.n_lookups; j++) pin_lk.push_back(g.lookup_mult[j]);
+    for (u32 k = 0; k < n_args; k++) pin_lk.push_back(g.lookup_args[k]);
+    pin_all = pin_lk;
+    for (u32 j = 0; j < g.n_zeros; j++) pin_all.push_back(g.zeros[j]);
+    for (u32 p : pin_lk) MSG_REQUIRE(p < g.lookup_prefix_len, "program: lookup node outside the prefix");
+    Lowered full = lower(g, g.n_nodes, pin_all);
+    Lowered prefix = lower(g, g.lookup_prefix_len, pin_lk);
+    MSG_REQUIRE(full.n_slots <= 4096 && prefix.n_slots <= 4096, "program: circuit needs more than 4096 live values");
+    auto* prog = new msgpu_program();
+    prog->ctx = &c;
+    try {
+        prog->n_full = (u32)full.code.size();
+        prog->n_prefix = (u32)prefix.code.size();
+        prog->slots_full = full.n_slots;
+        prog->slots_prefix = prefix.n_slots;
+        prog->n_zeros = g.n_zeros;
+        prog->n_lookups = g.n_lookups;
+        prog->n_args = n_args;
+        prog->pre_width = g.pre_width;
+        prog->main_width = g.main_width;
+        prog->stage2_width = g.stage2_width;
+        prog->d_full = upload_vec(c, prog, full.code);
+        prog->d_prefix = upload_vec(c, prog, prefix.code);
+        std::vector<u32> zs, mf, af, mp, ap, off;
+        for (u32 j = 0; j < g.n_zeros; j++) zs.push_back(full.slot_of[g.zeros[j]]);
+        for (u32 j = 0; j < g.n_lookups; j++) { mf.push_back(full.slot_of[g.lookup_mult[j]]); mp.push_back(prefix.slot_of[g.lookup_mult[j]]); }
+        for (u32 k = 0; k < n_args; k++) { af.push_back(full.slot_of[g.lookup_args[k]]); ap.push_back(prefix.slot_of[g.lookup_args[k]]); }
+        for (u32 j = 0; j <= g.n_lookups; j++) off.push_back(g.n_lookups ? g.lookup_arg_off[j] : 0);
+        prog->d_zero_slots = upload_vec(c, prog, zs);
+        prog->d_mult_full = upload_vec(c, prog, mf);
+        prog->d_args_full = upload_vec(c, prog, af);
+        prog->d_mult_prefix = upload_vec(c, prog, mp);
+        prog->d_args_prefix = upload_vec(c, prog, ap);
+        prog->d_arg_off = upload_vec(c, prog, off);
+        c.sync();
+    } catch (...) {
+        for (void* p : prog->owned) cudaFree(p);
+        delete prog;
+        throw;
+    }
+    return prog;
+}
+
+using SelCache = Ctx::SelCache;
+
+static gl::PowTable coset_x_table(Ctx& c, u32 log_nq) {
+    return c.pow_table(msh::two_adic_generator(log_nq).v, msh::GL_GENERATOR, log_nq).view();
+}
+
+static SelCache selectors(Ctx& c, u32 log_n, u32 log_q) {
+    auto& cache = c.sel_cache;
+    auto key = std::make_pair(log_n, log_q);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    u32 log_nq = log_n + log_q;
+    u64 nq = 1ull << log_nq, q = 1ull << log_q;
+    std::vector<u64> zh(q), izh(q);
+    msh::Fp s_pow_n = msh::Fp(msh::GL_GENERATOR).exp_power_of_2(log_n), wq = msh::two_adic_generator(log_q), acc = msh::Fp::one();
+    for (u64 i = 0; i < q; i++) {
+        msh::Fp z = s_pow_n * acc - msh::Fp::one();
+        zh[i] = z.v;
+        izh[i] = z.inverse().v;
+        acc *= wq;
+    }
+    SelCache sc{};
+    u64* d_zh = nullptr;
+    MSG_CUDA(cudaMalloc(&sc.first, nq * 8));
+    MSG_CUDA(cudaMalloc(&sc.last, nq * 8));
+    MSG_CUDA(cudaMalloc(&sc.inv_zh, q * 8));
+    MSG_CUDA(cudaMalloc(&d_zh, q * 8));
+    for (void* p : {(void*)sc.first, (void*)sc.last, (void*)sc.inv_zh, (void*)d_zh}) c.owned.push_back(p);
+    MSG_CUDA(cudaMemcpyAsync(d_zh, zh.data(), q * 8, cudaMemcpyHostToDevice, c.stream));
+    MSG_CUDA(cudaMemcpyAsync(sc.inv_zh, izh.data(), q * 8, cudaMemcpyHostToDevice, c.stream));
+    SelParams sp{};
+    sp.xtab = coset_x_table(c, log_nq);
+    sp.zh = d_zh;
+    sp.g_inv = msh::two_adic_generator(log_n).inverse().v;
+    sp.first = sc.first;
+    sp.last = sc.last;
+    sp.log_nq = log_nq;
+    sp.log_q = log_q;
+    u64 threads = (nq + kSelPerThread - 1) / kSelPerThread;
+    {
+        StageScope ss(c, "quotient");
+        KLaunch kl(c, "k_selectors");
+        k_selectors<<<(unsigned)((threads + 255) / 256), 256, 0, c.stream>>>(sp);
+    }
+    MSG_CUDA(cudaGetLastError());
+    c.sync();  // zh / izh host vectors die here
+    cache[key] = sc;
+    return sc;
+}
+
+template <class K>
+static void launch_by_slots(u32 n_slots, K&& launch) {
+    if (n_slots <= 32) launch(std::integral_constant<int, 32>());
+    else if (n_slots <= 64) launch(std::integral_constant<int, 64>());
+    else if (n_slots <= 128) launch(std::integral_constant<int, 128>());
+    else if (n_slots <= 256) launch(std::integral_constant<int, 256>());
+    else if (n_slots <= 1024) launch(std::integral_constant<int, 1024>());
+    else launch(std::integral_constant<int, 4096>());
+}
+
+static void quotient_slices(Ctx& c, const u64* S, u64* out, u32 log_big, u32 log_n, u32 d) {
+    u64 big = 1ull << log_big, n = 1ull << log_n, q = big >> log_n;
+    std::vector<u64> w(q);
+    msh::Fp ninv = msh::Fp((msh::u64)big).inverse();
+    msh::Fp step = msh::Fp(msh::GL_GENERATOR).pow((msh::u64)n).inverse(), acc = msh::Fp::one();
+    for (u64 k = 0; k < q; k++) { w[k] = (acc * ninv).v; acc *= step; }
+    DevBuf dw(c, q * 8);
+    MSG_CUDA(cudaMemcpyAsync(dw.p, w.data(), q * 8, cudaMemcpyHostToDevice, c.stream));
+    {
+        KLaunch kl(c, "k_quotient_slices");
+        k_quotient_slices<<<(unsigned)((big + 255) / 256), 256, 0, c.stream>>>(S, out, log_big, log_n, d, dw.u());
+    }
+    MSG_CUDA(cudaGetLastError());
+    c.sync();  // `w` dies here (pageable source of an async copy)
+}
+
+static void view_of(const msgpu_pdata* pd, u64 idx, u64 nq, u32 width, const u64** ptr) {
+    MSG_REQUIRE(pd && idx < pd->mats.size(), "quotient: matrix index out of range");
+    auto& m = pd->mats[idx];
+    MSG_REQUIRE(m.width == width, "quotient: committed width does not match the program");
+    MSG_REQUIRE(m.height >= nq, "quotient: quotient domain larger than the committed LDE (quotient degree > blowup)");
+    *ptr = m.ptr;
+}
+
+}  // namespace msg
+
+using namespace msg;
+
+extern "C" {
+
+int msgpu_program_create(msgpu_ctx* h, const msgpu_graph_desc* desc, msgpu_program** out) {
+    return guard([&] {
+        MSG_REQUIRE(desc && out, "program_create: null argument");
+        *out = program_create(h->c, *desc);
+    });
+}
+void msgpu_program_free(msgpu_program* prog) {
+    if (!prog) return;
+    cudaStreamSynchronize(prog->ctx->stream);
+    for (void* p : prog->owned) cudaFree(p);
+    delete prog;
+}
+
+int msgpu_stage2_trace(msgpu_ctx* h, const msgpu_program* prog, const uint64_t* pre_dev, const uint64_t* main_dev,
+                       uint64_t rows, const uint64_t* beta2, const uint64_t* gamma2, uint64_t* stage2_out_dev,
+                       uint64_t* local_sum2) {
+    return guard([&] {
+        Ctx& c = h->c;
+        StageScope ss(c, "stage2");
+        MSG_REQUIRE(prog && main_dev && stage2_out_dev && local_sum2, "stage2_trace: null argument");
+        MSG_REQUIRE(prog->pre_width == 0 || pre_dev, "stage2_trace: circuit has a preprocessed trace but none was given");
+        local_sum2[0] = local_sum2[1] = 0;
+        if (rows == 0) return;
+        u32 L = prog->n_lookups;
+        if (L == 0) {  // pass-through accumulator column, zero by convention (src/lookup.rs:520-524)
+            MSG_CUDA(cudaMemsetAsync(stage2_out_dev, 0, rows * 2 * 8, c.stream));
+            return;
+        }
+        u64 total = rows * L;
+        u64 nblocks = (total + kScanPerBlock - 1) / kScanPerBlock;
+        DevBuf msgs(c, total * 16), mults(c, total * 8), bsums(c, (nblocks + 1) * 16);
+        MsgParams mp{};
+        mp.prog = prog->d_prefix;
+        mp.n_instr = prog->n_prefix;
+        mp.lk_mult = prog->d_mult_prefix;
+        mp.lk_argoff = prog->d_arg_off;
+        mp.lk_args = prog->d_args_prefix;
+        mp.pre = (const u64*)pre_dev;
+        mp.main = (const u64*)main_dev;
+        mp.msgs = msgs.u();
+        mp.mults = mults.u();
+        mp.rows = rows;
+        mp.beta[0] = beta2[0]; mp.beta[1] = beta2[1];
+        mp.gamma[0] = gamma2[0]; mp.gamma[1] = gamma2[1];
+        mp.n_lookups = L;
+        mp.wpre = prog->pre_width;
+        mp.wmain = prog->main_width;
+        launch_by_slots(prog->slots_prefix, [&](auto ns) {
+            KLaunch kl(c, "k_lookup_messages");
+            k_lookup_messages<decltype(ns)::value><<<(unsigned)((rows + 127) / 128), 128, 0, c.stream>>>(mp);
+        });
+        MSG_CUDA(cudaGetLastError());
+        {
+            KLaunch kl(c, "k_terms_and_block_sums");
+            k_terms_and_block_sums<<<(unsigned)nblocks, kScanThreads, 0, c.stream>>>(msgs.u(), mults.u(), total, bsums.u());
+        }
+        MSG_CUDA(cudaGetLastError());
+        {
+            KLaunch kl(c, "k_scan_block_sums");
+            k_scan_block_sums<<<1, 1024, 0, c.stream>>>(bsums.u(), nblocks);
+        }
+        MSG_CUDA(cudaGetLastError());
+        {
+            KLaunch kl(c, "k_scan_write");
+            k_scan_write<<<(unsigned)nblocks, kScanThreads, 0, c.stream>>>(msgs.u(), total, bsums.u(), (u64*)stage2_out_dev);
+        }
+        MSG_CUDA(cudaGetLastError());
+        MSG_CUDA(cudaMemcpyAsync(local_sum2, bsums.u() + 2 * nblocks, 16, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+    });
+}
+
+int msgpu_claims_accumulator(msgpu_ctx* h, const uint64_t* claims, uint64_t n_claims, uint64_t claim_len,
+                             const uint64_t* beta2, const uint64_t* gamma2, uint64_t* out2) {
+    return guard([&] {
+        Ctx& c = h->c;
+        StageScope ss(c, "stage2");
+        out2[0] = out2[1] = 0;
+        if (n_claims == 0) return;
+        MSG_REQUIRE(claim_len < (1ull << 31), "claims: claim too long");
+        u64 nblocks = (n_claims + kScanPerBlock - 1) / kScanPerBlock;
+        DevBuf d(c, n_claims * std::max<u64>(claim_len, 1) * 8), part(c, nblocks * 16);
+        if (claim_len) MSG_CUDA(cudaMemcpyAsync(d.p, claims, n_claims * claim_len * 8, cudaMemcpyHostToDevice, c.stream));
+        {
+            KLaunch kl(c, "k_claims");
+            k_claims<<<(unsigned)nblocks, kScanThreads, 0, c.stream>>>(d.u(), n_claims, (u32)claim_len,
+                                                                       gl::e2{beta2[0], beta2[1]}, gl::e2{gamma2[0], gamma2[1]}, part.u());
+        }
+        MSG_CUDA(cudaGetLastError());
+        std::vector<u64> hp(nblocks * 2);
+        MSG_CUDA(cudaMemcpyAsync(hp.data(), part.p, nblocks * 16, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+        msh::Fp2 acc;
+        for (u64 b = 0; b < nblocks; b++) acc += msh::Fp2(msh::Fp(hp[2 * b]), msh::Fp(hp[2 * b + 1]));
+        out2[0] = acc.c[0].v;
+        out2[1] = acc.c[1].v;
+    });
+}
+
+int msgpu_quotient(msgpu_ctx* h, const msgpu_program* prog, const msgpu_pdata* pd_pre, uint64_t idx_pre,
+                   const msgpu_pdata* pd_s1, uint64_t idx_s1, const msgpu_pdata* pd_s2, uint64_t idx_s2, uint32_t log_n,
+                   uint32_t log_q, uint32_t log_blowup, const uint64_t* publics8, const uint64_t* alpha2,
+                   uint64_t** lde_out_dev, uint64_t* quotient_values_out) {
+    return guard([&] {
+        Ctx& c = h->c;
+        StageScope ss(c, "quotient");
+        MSG_REQUIRE(prog && pd_s1 && pd_s2 && publics8 && alpha2 && lde_out_dev, "quotient: null argument");
+        MSG_REQUIRE(log_q <= log_blowup, "quotient: quotient degree exceeds the blowup");
+        MSG_REQUIRE(log_n + log_blowup <= 32, "quotient: domain exceeds the two-adicity of the field");
+        const u32 log_nq = log_n + log_q;
+        const u64 nq = 1ull << log_nq, n = 1ull << log_n, q = 1ull << log_q;
+        QuotParams qp{};
+        qp.pre = nullptr;
+        if (prog->pre_width) {
+            MSG_REQUIRE(pd_pre, "quotient: circuit has a preprocessed trace but no preprocessed commitment was given");
+            view_of(pd_pre, idx_pre, nq, prog->pre_width, &qp.pre);
+        }
+        view_of(pd_s1, idx_s1, nq, prog->main_width, &qp.s1);
+        view_of(pd_s2, idx_s2, nq, prog->stage2_width, &qp.s2);
+        for (int i = 0; i < 8; i++) MSG_REQUIRE(publics8[i] < GLD_P, "quotient: public value is not canonical");
+        SelCache sel = selectors(c, log_n, log_q);
+        // alpha powers reversed (src/prover.rs:798-808): constraint j of k weighted by alpha^{k-1-j}
+        u32 k = prog->n_zeros + 2 * std::max<u32>(prog->n_lookups, 1);
+        std::vector<u64> apow(2 * (size_t)k);
+        msh::Fp2 alpha{msh::Fp(alpha2[0]), msh::Fp(alpha2[1])}, acc = msh::Fp2::one();
+        for (u32 j = 0; j < k; j++) {
+            apow[2 * (size_t)(k - 1 - j)] = acc.c[0].v;
+            apow[2 * (size_t)(k - 1 - j) + 1] = acc.c[1].v;
+            acc *= alpha;
+        }
+        DevBuf d_apow(c, apow.size() * 8), qv(c, nq * 16);
+        MSG_CUDA(cudaMemcpyAsync(d_apow.p, apow.data(), apow.size() * 8, cudaMemcpyHostToDevice, c.stream));
+        msh::Fp inj_norm = (msh::Fp((msh::u64)n) * msh::two_adic_generator(log_n)).inverse();
+        qp.prog = prog->d_full;
+        qp.n_instr = prog->n_full;
+        qp.zero_slots = prog->d_zero_slots;
+        qp.n_zeros = prog->n_zeros;
+        qp.n_lookups = prog->n_lookups;
+        qp.lk_mult = prog->d_mult_full;
+        qp.lk_argoff = prog->d_arg_off;
+        qp.lk_args = prog->d_args_full;
+        qp.wpre = prog->pre_width;
+        qp.w1 = prog->main_width;
+        qp.w2 = prog->stage2_width;
+        qp.apow = d_apow.u();
+        qp.sel_first = sel.first;
+        qp.sel_last = sel.last;
+        qp.inv_zh = sel.inv_zh;
+        qp.out = qv.u();
+        qp.xtab = coset_x_table(c, log_nq);
+        for (int i = 0; i < 8; i++) qp.publics[i] = publics8[i];
+        qp.delta[0] = ((msh::Fp(publics8[6]) - msh::Fp(publics8[4])) * inj_norm).v;
+        qp.delta[1] = ((msh::Fp(publics8[7]) - msh::Fp(publics8[5])) * inj_norm).v;
+        qp.g_inv = msh::two_adic_generator(log_n).inverse().v;
+        qp.log_nq = log_nq;
+        qp.log_q = log_q;
+        launch_by_slots(prog->slots_full, [&](auto ns) {
+            KLaunch kl(c, "k_quotient_eval");
+            k_quotient_eval<decltype(ns)::value><<<(unsigned)((nq + 127) / 128), 128, 0, c.stream>>>(qp);
+        });
+        MSG_CUDA(cudaGetLastError());
+        if (quotient_values_out) MSG_CUDA(cudaMemcpyAsync(quotient_values_out, qv.p, nq * 16, cudaMemcpyDeviceToHost, c.stream));
+        // shifted_quotient_slices: one DFT of the nq x 2 matrix + gather; then the LDE from coefficients
+        ntt_dft_bitrev(c, qv.u(), qv.u(), nq, 2, false);
+        DevBuf sl(c, n * q * 16);
+        quotient_slices(c, qv.u(), sl.u(), log_nq, log_n, 2);
+        u64* lde = (u64*)c.alloc((n << log_blowup) * q * 16);
+        try {
+            ntt_lde_from_coeffs(c, sl.u(), lde, n, 2 * q, log_blowup);
+            c.sync();  // apow (pageable) must outlive the copy; also surfaces kernel faults here
+        } catch (...) {
+            c.free(lde);
+            throw;
+        }
+        *lde_out_dev = (uint64_t*)lde;
+    });
+}
+
+int msgpu_shifted_quotient_slices(msgpu_ctx* h, const uint64_t* in, uint64_t nq, uint64_t d, uint64_t q, uint64_t* out) {
+    return guard([&] {
+        Ctx& c = h->c;
+        MSG_REQUIRE(is_pow2(nq) && is_pow2(q) && q <= nq && d > 0, "shifted_quotient_slices: bad shape");
+        DevBuf din(c, nq * d * 8), dout(c, nq * d * 8);
+        MSG_CUDA(cudaMemcpyAsync(din.p, in, nq * d * 8, cudaMemcpyHostToDevice, c.stream));
+        ntt_dft_bitrev(c, din.u(), din.u(), nq, d, false);
+        quotient_slices(c, din.u(), dout.u(), ilog2(nq), ilog2(nq / q), (u32)d);
+        MSG_CUDA(cudaMemcpyAsync(out, dout.p, nq * d * 8, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+"""Host-side system objects: mirror of the reference's `System` / `Circuit` (src/system.rs:52-203) and of
+the benchmark workload (benches/multi_stark.rs:171-238), over libmshost.so; plus the device programs
+(`msgpu_program`) compiled from each circuit's ConstraintGraph."""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import check
+
+INFO_FIELDS = ["main_width", "pre_width", "pre_height", "num_lookups", "stage2_width", "constraint_count",
+               "max_constraint_degree", "quotient_degree", "n_nodes", "n_zeros", "lookup_prefix_len", "preprocessed_index"]
+
+
+class System:
+    """A named system (see named_system_inputs in host/system.hpp): "u32_add", "mixed", "fib"."""
+
+    def __init__(self, kind, log_blowup=1, log_final_poly_len=0, max_log_arity=1, num_queries=100, commit_pow_bits=0,
+                 query_pow_bits=0):
+        self.H = _ffi.host_lib()
+        self.kind = kind
+        self.params = dict(log_blowup=log_blowup, log_final_poly_len=log_final_poly_len, max_log_arity=max_log_arity,
+                           num_queries=num_queries, commit_pow_bits=commit_pow_bits, query_pow_bits=query_pow_bits)
+        self.h = self.H.msh_system_create(kind.encode(), log_blowup, log_final_poly_len, max_log_arity, num_queries,
+                                          commit_pow_bits, query_pow_bits)
+        if not self.h:
+            raise ValueError((self.H.msh_last_error() or b"").decode())
+        self.num_circuits = int(self.H.msh_system_num_circuits(self.h))
+        self.circuits = []
+        for i in range(self.num_circuits):
+            buf = np.zeros(12, dtype=np.uint64)
+            self.H.msh_circuit_info(self.h, i, buf.ctypes.data_as(C.c_void_p))
+            info = {k: int(v) for k, v in zip(INFO_FIELDS, buf)}
+            if info["preprocessed_index"] == 2**64 - 1:
+                info["preprocessed_index"] = None
+            self.circuits.append(info)
+
+    def preprocessed(self, i):
+        c = self.circuits[i]
+        out = np.zeros((c["pre_height"], c["pre_width"]), dtype=np.uint64)
+        if out.size:
+            self.H.msh_circuit_preprocessed(self.h, i, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def graph_desc(self, i):
+        return self.H.msh_circuit_graph(self.h, i)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.H.msh_system_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def u32_add_workload(num_adds):
+    """(byte_trace 256x1, add_trace next_pow2(num_adds)x14, claims num_adds x 4)."""
+    H = _ffi.host_lib()
+    h = 1
+    while h < num_adds:
+        h *= 2
+    byte = np.zeros((256, 1), dtype=np.uint64)
+    add = np.zeros((h, 14), dtype=np.uint64)
+    claims = np.zeros((num_adds, 4), dtype=np.uint64)
+    H.msh_u32add_workload(num_adds, byte.ctypes.data_as(C.c_void_p), add.ctypes.data_as(C.c_void_p),
+                          claims.ctypes.data_as(C.c_void_p))
+    return byte, add, claims
+
+
+def fib_trace(rows):
+    H = _ffi.host_lib()
+    out = np.zeros((rows, 3), dtype=np.uint64)
+    H.msh_fib_trace(rows, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+class Program:
+    """Device bytecode of one circuit (`msgpu_program`)."""
+
+    def __init__(self, ctx, system, circuit_index):
+        self.ctx = ctx
+        self.L = ctx.L
+        self.info = system.circuits[circuit_index]
+        h = C.c_void_p()
+        check(self.L.msgpu_program_create(ctx.h, system.graph_desc(circuit_index), C.byref(h)))
+        self.h = h
+
+    def free(self):
+        if getattr(self, "h", None):
+            self.L.msgpu_program_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.free()
+        except Exception:
+            pass
+
+    def stage2_trace(self, main_dev, rows, beta, gamma, pre_dev=None):
+        """msgpu_stage2_trace: returns (device ptr of rows x stage2_width, local_sum[2])."""
+        w = self.info["stage2_width"]
+        out = self.ctx.malloc(max(rows * w * 8, 8))
+        b = np.asarray(beta, dtype=np.uint64)
+        g = np.asarray(gamma, dtype=np.uint64)
+        ls = np.zeros(2, dtype=np.uint64)
+        check(self.L.msgpu_stage2_trace(self.ctx.h, self.h, C.c_void_p(pre_dev) if pre_dev else None, C.c_void_p(main_dev), rows,
+                                        b.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p), C.c_void_p(out),
+                                        ls.ctypes.data_as(C.c_void_p)))
+        return out, ls
+
+    def quotient(self, pd_pre, idx_pre, pd_s1, idx_s1, pd_s2, idx_s2, log_n, log_q, log_blowup, publics8, alpha,
+                 want_values=False):
+        """msgpu_quotient: returns (device ptr of the quotient LDE, rows, cols[, quotient values nq x 2])."""
+        pub = np.asarray(publics8, dtype=np.uint64)
+        al = np.asarray(alpha, dtype=np.uint64)
+        lde = C.c_void_p()
+        nq = 1 << (log_n + log_q)
+        vals = np.zeros((nq, 2), dtype=np.uint64) if want_values else None
+        check(self.L.msgpu_quotient(self.ctx.h, self.h, pd_pre.h if pd_pre is not None else None, idx_pre, pd_s1.h, idx_s1,
+                                    pd_s2.h, idx_s2, log_n, log_q, log_blowup, pub.ctypes.data_as(C.c_void_p),
+                                    al.ctypes.data_as(C.c_void_p), C.byref(lde),
+                                    vals.ctypes.data_as(C.c_void_p) if want_values else None))
+        rows, cols = 1 << (log_n + log_blowup), 2 << log_q
+        return (lde.value, rows, cols, vals) if want_values else (lde.value, rows, cols)
+
+
+def claims_accumulator(ctx, claims, beta, gamma):
+    cl = np.ascontiguousarray(claims, dtype=np.uint64)
+    b = np.asarray(beta, dtype=np.uint64)
+    g = np.asarray(gamma, dtype=np.uint64)
+    out = np.zeros(2, dtype=np.uint64)
+    check(ctx.L.msgpu_claims_accumulator(ctx.h, cl.ctypes.data_as(C.c_void_p), cl.shape[0], cl.shape[1],
+                                         b.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def shifted_quotient_slices(ctx, m, q):
+    a = np.ascontiguousarray(m, dtype=np.uint64)
+    out = np.zeros((a.shape[0] // q, a.shape[1] * q), dtype=np.uint64)
+    check(ctx.L.msgpu_shifted_quotient_slices(ctx.h, a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1], q,
+                                              out.ctypes.data_as(C.c_void_p)))
+    return out

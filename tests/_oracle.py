@@ -51,6 +51,16 @@ def lib():
         "orc_mmcs_open": (None, [C.c_void_p, C.c_uint64, u64p, u8p]),
         "orc_mmcs_verify": (C.c_int, [u8p, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u8p, C.c_uint64]),
         "orc_mmcs_free": (None, [C.c_void_p]),
+        "orc_system_create": (C.c_void_p, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+        "orc_system_free": (None, [C.c_void_p]),
+        "orc_graph_num_nodes": (C.c_uint64, [C.c_void_p, C.c_uint32]),
+        "orc_graph_nodes": (None, [C.c_void_p, C.c_uint32, u8p, u32p, u32p, u64p, u32p]),
+        "orc_graph_num_zeros": (C.c_uint64, [C.c_void_p, C.c_uint32]),
+        "orc_graph_zeros": (None, [C.c_void_p, C.c_uint32, u32p]),
+        "orc_stage2_trace": (None, [C.c_void_p, C.c_uint32, u64p, C.c_uint64, u64p, u64p, u64p, u64p]),
+        "orc_claims_accumulator": (None, [u64p, C.c_uint64, C.c_uint64, u64p, u64p, u64p]),
+        "orc_quotient_values": (None, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, u64p, u64p, u64p, u64p, u64p]),
+        "orc_selectors_on_coset": (None, [C.c_uint32, C.c_uint32, C.c_uint64, u64p, u64p, u64p, u64p]),
         "orc_pcs_commit": (C.c_void_p, [C.POINTER(C.c_void_p), u64p, u64p, C.c_uint64, C.c_uint32, u8p]),
         "orc_mmcs_matrix": (None, [C.c_void_p, C.c_uint64, u64p]),
     }
