@@ -175,6 +175,38 @@ int msgpu_quotient(msgpu_ctx* ctx, const msgpu_program* prog, const msgpu_pdata*
  * in = nq x d quotient evaluations in natural order, out = (nq / q) x (q * d). */
 int msgpu_shifted_quotient_slices(msgpu_ctx* ctx, const uint64_t* in, uint64_t nq, uint64_t d, uint64_t q, uint64_t* out);
 
+/* ---- Pcs::open (reference src/prover.rs:580; p3-fri TwoAdicFriPcs::open + prove_fri) ------------------
+ * The Fiat-Shamir transcript stays with the caller (it is generic Rust in the reference); the device does
+ * the arithmetic between transcript steps:
+ *   open_begin      barycentric evaluation of every column of every matrix at its points (from the first
+ *                   height >> log_blowup stored rows = the coset GENERATOR * H); caller observes the values
+ *   open_reduce     after alpha: per LDE height, sum over (matrix, point) of
+ *                   alpha^offset * (Mred(z) - Mred(x)) / (z - x), Mred = sum_c alpha^c column_c; x in bit-reversed order
+ *   fri_commit_round / fri_fold   commit phase: Merkle-commit the current vector as rows of 2 extension elements
+ *                   (ExtensionMmcs: 4 base columns), then after beta fold
+ *                   (1/2 + beta/2 g^-rev(i)) lo + (1/2 - beta/2 g^-rev(i)) hi and roll in the next-height input
+ *                   times beta^2
+ *   fri_read_current  the folded vector (for the final polynomial)
+ *   fri_layer_pdata   prover data of commit-phase layer i, to answer queries with msgpu_open_batch */
+typedef struct msgpu_open msgpu_open;
+/* n_points[m] / points: for every matrix of every round, in order, the number of opening points and then the
+ * points themselves (2 u64 each), concatenated. n_values receives the total number of extension values. */
+int msgpu_open_begin(msgpu_ctx* ctx, uint64_t n_rounds, const msgpu_pdata* const* pds, const uint64_t* n_points,
+                     const uint64_t* points, uint32_t log_blowup, msgpu_open** out, uint64_t* n_values);
+/* opened values, order round / matrix / point / column, 2 u64 each (host buffer of 2 * n_values) */
+int msgpu_open_values(msgpu_open* op, uint64_t* out);
+/* builds the FRI inputs; n_inputs receives their count, log_max_height the log2 length of the first */
+int msgpu_open_reduce(msgpu_open* op, const uint64_t* alpha2, uint64_t* n_inputs, uint32_t* log_max_height);
+/* HOST copy of FRI input k (tallest first): 2 * len u64; len_out receives its length. Test hook. */
+int msgpu_open_read_input(msgpu_open* op, uint64_t k, uint64_t* out, uint64_t* len_out);
+int msgpu_fri_current_len(msgpu_open* op, uint64_t* len);
+int msgpu_fri_commit_round(msgpu_open* op, uint8_t* root32);
+int msgpu_fri_fold(msgpu_open* op, const uint64_t* beta2);
+int msgpu_fri_read_current(msgpu_open* op, uint64_t* out);
+uint64_t msgpu_fri_num_layers(const msgpu_open* op);
+const msgpu_pdata* msgpu_fri_layer_pdata(const msgpu_open* op, uint64_t layer);
+void msgpu_open_free(msgpu_open* op);
+
 /* ---- test hooks --------------------------------------------------------------------------------- */
 /* raw 7-round BLAKE3 compression of a 16-word state and 16 message words (known-answer vector of
  * reference src/test_circuits/blake3.rs:2646-2746); host pointers */

@@ -6,7 +6,7 @@ There is no CPU fallback: importing works without a GPU (so the ABI can be check
 compute call needs a CUDA device and raises `MsgpuError` otherwise."""
 from ._ffi import MsgpuError, lib, lib_path  # noqa: F401
 from .pcs import GpuContext, GpuDft, GpuMmcs, GpuPcs, ProverData  # noqa: F401
-from .system import Program, System, claims_accumulator, fib_trace, shifted_quotient_slices, u32_add_workload  # noqa: F401
+from .system import Program, Prover, System, claims_accumulator, fib_trace, shifted_quotient_slices, u32_add_workload  # noqa: F401
 
 P = 2**64 - 2**32 + 1
 GENERATOR = 7

@@ -60,6 +60,17 @@ SIGNATURES = {
     "msgpu_quotient": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
                                  C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, c_vpp, C.c_void_p]),
     "msgpu_shifted_quotient_slices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "msgpu_open_begin": (C.c_int, [C.c_void_p, C.c_uint64, c_vpp, c_u64p, c_u64p, C.c_uint32, c_vpp, c_u64p]),
+    "msgpu_open_values": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "msgpu_open_reduce": (C.c_int, [C.c_void_p, C.c_void_p, c_u64p, c_u32p]),
+    "msgpu_open_read_input": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, c_u64p]),
+    "msgpu_fri_current_len": (C.c_int, [C.c_void_p, c_u64p]),
+    "msgpu_fri_commit_round": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "msgpu_fri_fold": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "msgpu_fri_read_current": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "msgpu_fri_num_layers": (C.c_uint64, [C.c_void_p]),
+    "msgpu_fri_layer_pdata": (C.c_void_p, [C.c_void_p, C.c_uint64]),
+    "msgpu_open_free": (None, [C.c_void_p]),
     "msgpu_blake3_compress_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
@@ -111,6 +122,11 @@ HOST_SIGNATURES = {
     "msh_circuit_preprocessed": (None, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "msh_u32add_workload": (None, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "msh_fib_trace": (None, [C.c_uint64, C.c_void_p]),
+    "msh_prover_create": (C.c_void_p, [C.c_void_p, C.c_void_p]),
+    "msh_prover_free": (None, [C.c_void_p]),
+    "msh_prover_preprocessed_commit": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "msh_prove": (C.c_int, [C.c_void_p, c_vpp, c_u64p, c_u64p, c_u64p, C.c_uint64, c_vpp, c_u64p, C.POINTER(C.c_double)]),
+    "msh_bytes_free": (None, [C.c_void_p]),
 }
 
 

@@ -1,0 +1,520 @@
+// Opening phase on the device: barycentric evaluation, reduced openings, FRI fold + commit rounds.
+// Restates the arithmetic of p3-fri 0.5.1 `TwoAdicFriPcs::open` / `prove_fri` / `TwoAdicFriFolding::fold_matrix`
+// (not vendored in the reference; call site src/prover.rs:580, rounds built at src/prover.rs:540-579); semantics as in
+// SURVEY Appendix A.6. PARITY UNPINNED against real p3 outputs (no golden FRI data exists in the reference tree);
+// pinned by the tests against the CPU restatement and a restated verifier.
+#include "capi_common.hpp"
+#include "mmcs.hpp"
+#include <algorithm>
+#include <cstring>
+#include <memory>
+
+namespace msg {
+
+__device__ __forceinline__ u64 fp_inv_d(u64 x) {
+    auto sqn = [](u64 v, int n) { for (int i = 0; i < n; i++) v = gl::mul(v, v); return v; };
+    u64 t2 = gl::mul(sqn(x, 1), x);
+    u64 t4 = gl::mul(sqn(t2, 2), t2);
+    u64 t8 = gl::mul(sqn(t4, 4), t4);
+    u64 t16 = gl::mul(sqn(t8, 8), t8);
+    u64 t24 = gl::mul(sqn(t16, 8), t8);
+    u64 t28 = gl::mul(sqn(t24, 4), t4);
+    u64 t30 = gl::mul(sqn(t28, 2), t2);
+    u64 t31 = gl::mul(sqn(t30, 1), x);
+    u64 a = sqn(t31, 1);
+    u64 b = gl::mul(a, x);
+    return gl::mul(sqn(a, 32), b);
+}
+__device__ __forceinline__ gl::e2 e2_inverse_d(gl::e2 x) {
+    u64 norm = gl::sub(gl::sqr(x.a), gl::mul7(gl::sqr(x.b)));
+    u64 ni = fp_inv_d(norm);
+    return gl::e2_make(gl::mul(x.a, ni), gl::mul(gl::neg(x.b), ni));
+}
+
+// invden[i] = 1 / (z - x_i), x_i = GENERATOR * w_H^{rev(i)}  (the LDE domain in stored order)
+constexpr int kInvPerThread = 8;
+__global__ void __launch_bounds__(256) k_inv_denoms(u64* invden, u32 log_h, gl::e2 z, gl::PowTable xtab) {
+    const u64 H = 1ull << log_h;
+    u64 i0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * kInvPerThread;
+    if (i0 >= H) return;
+    gl::e2 v[kInvPerThread], pref[kInvPerThread];
+    int cnt = 0;
+    for (int k = 0; k < kInvPerThread; k++) {
+        if (i0 + k >= H) break;
+        u64 x = gl::pow_lookup(xtab, gl::rev_bits((u32)(i0 + k), log_h));
+        v[k] = gl::e2_make(gl::sub(z.a, x), z.b);
+        cnt = k + 1;
+    }
+    gl::e2 acc = gl::e2_make(1, 0);
+    for (int k = 0; k < cnt; k++) { pref[k] = acc; acc = gl::e2_mul(acc, v[k]); }
+    gl::e2 inv = e2_inverse_d(acc);
+    for (int k = cnt; k-- > 0;) {
+        gl::e2 r = gl::e2_mul(inv, pref[k]);
+        inv = gl::e2_mul(inv, v[k]);
+        invden[2 * (i0 + k)] = r.a;
+        invden[2 * (i0 + k) + 1] = r.b;
+    }
+}
+
+// partial[cta][c][p] = sum over the CTA's rows of M[i][c] * x_i * invden_p[i]   (i < h, the low coset)
+constexpr int kMaxPts = 4;
+struct BaryParams {
+    const u64* M;
+    const u64* invden[kMaxPts];
+    u64* partial;
+    gl::PowTable xtab;  // GENERATOR * w_h^e
+    u64 h;
+    u32 w, log_h, npts, c0, wc;  // this launch covers columns [c0, c0 + wc)
+    u32 rows_per_step;
+};
+__global__ void __launch_bounds__(256) k_bary_partial(BaryParams p) {
+    extern __shared__ u64 sm_b[];
+    const u32 t = threadIdx.x;
+    const u32 active = p.rows_per_step * p.wc;
+    gl::e2 acc[kMaxPts];
+    for (u32 k = 0; k < kMaxPts; k++) acc[k] = gl::e2_make(0, 0);
+    const u32 c = t % p.wc, lane_row = t / p.wc;
+    if (t < active) {
+        for (u64 r = (u64)blockIdx.x * p.rows_per_step + lane_row; r < p.h; r += (u64)gridDim.x * p.rows_per_step) {
+            u64 x = gl::pow_lookup(p.xtab, gl::rev_bits((u32)r, p.log_h));
+            u64 mx = gl::mul(p.M[r * p.w + p.c0 + c], x);
+            for (u32 k = 0; k < p.npts; k++) {
+                gl::e2 d = gl::e2_make(p.invden[k][2 * r], p.invden[k][2 * r + 1]);
+                acc[k] = gl::e2_add(acc[k], gl::e2_mul_base(d, mx));
+            }
+        }
+    }
+    // reduce over the row lanes of each column
+    u64* sm = sm_b;  // [rows_per_step][wc][npts][2]
+    if (t < active)
+        for (u32 k = 0; k < p.npts; k++) {
+            sm[((lane_row * p.wc + c) * p.npts + k) * 2] = acc[k].a;
+            sm[((lane_row * p.wc + c) * p.npts + k) * 2 + 1] = acc[k].b;
+        }
+    __syncthreads();
+    if (t < p.wc) {
+        for (u32 k = 0; k < p.npts; k++) {
+            gl::e2 s = gl::e2_make(0, 0);
+            for (u32 l = 0; l < p.rows_per_step; l++)
+                s = gl::e2_add(s, gl::e2_make(sm[((l * p.wc + t) * p.npts + k) * 2], sm[((l * p.wc + t) * p.npts + k) * 2 + 1]));
+            u64* o = p.partial + (((u64)blockIdx.x * p.wc + t) * p.npts + k) * 2;
+            o[0] = s.a;
+            o[1] = s.b;
+        }
+    }
+}
+
+// ro[i] += sum_p aoff_p * (yred_p - Mred_i) * invden_p[i],  Mred_i = sum_c alpha^c M[i][c]
+struct ReduceParams {
+    const u64* M;
+    const u64* apow;  // w x 2
+    const u64* invden[kMaxPts];
+    u64* ro;
+    u64 H;
+    u64 aoff[kMaxPts][2], yred[kMaxPts][2];
+    u32 w, npts;
+};
+constexpr int kRedRows = 128;
+__global__ void __launch_bounds__(kRedRows) k_reduce_openings(ReduceParams p) {
+    extern __shared__ u64 sm_r[];
+    const u32 pitch = p.w | 1;
+    u64* tile = sm_r;                          // [kRedRows][pitch]
+    u64* ap = sm_r + (size_t)kRedRows * pitch;  // [w][2]
+    const u64 row0 = (u64)blockIdx.x * kRedRows;
+    const u32 nrows = (u32)min((u64)kRedRows, p.H - row0);
+    for (u32 e = threadIdx.x; e < 2 * p.w; e += blockDim.x) ap[e] = p.apow[e];
+    const u64* src = p.M + row0 * p.w;
+    for (u32 e = threadIdx.x; e < nrows * p.w; e += blockDim.x) tile[(e / p.w) * pitch + e % p.w] = src[e];
+    __syncthreads();
+    if (threadIdx.x >= nrows) return;
+    const u64* row = tile + (size_t)threadIdx.x * pitch;
+    u64 m0 = 0, m1 = 0;
+    for (u32 c = 0; c < p.w; c++) {
+        u64 v = row[c];
+        m0 = gl::add(m0, gl::mul(v, ap[2 * c]));
+        m1 = gl::add(m1, gl::mul(v, ap[2 * c + 1]));
+    }
+    const u64 i = row0 + threadIdx.x;
+    gl::e2 acc = gl::e2_make(p.ro[2 * i], p.ro[2 * i + 1]);
+    for (u32 k = 0; k < p.npts; k++) {
+        gl::e2 diff = gl::e2_make(gl::sub(p.yred[k][0], m0), gl::sub(p.yred[k][1], m1));
+        gl::e2 d = gl::e2_make(p.invden[k][2 * i], p.invden[k][2 * i + 1]);
+        gl::e2 t = gl::e2_mul(gl::e2_mul(gl::e2_make(p.aoff[k][0], p.aoff[k][1]), diff), d);
+        acc = gl::e2_add(acc, t);
+    }
+    p.ro[2 * i] = acc.a;
+    p.ro[2 * i + 1] = acc.b;
+}
+
+// out[i] = (lo + hi)/2 + (beta/2) * g^{-rev(i)} * (lo - hi)  [+ beta^2 * roll[i]],  (lo, hi) = in[2i], in[2i+1]
+__global__ void __launch_bounds__(256) k_fri_fold(const u64* in, u64* out, u64 half_len, u32 log_half, gl::e2 half_beta,
+                                                  gl::PowTable ginv_tab, const u64* roll, gl::e2 beta_sq) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half_len) return;
+    gl::e2 lo = gl::e2_make(in[4 * i], in[4 * i + 1]), hi = gl::e2_make(in[4 * i + 2], in[4 * i + 3]);
+    gl::e2 s = gl::e2_add(lo, hi), d = gl::e2_sub(lo, hi);
+    s = gl::e2_make(gl::halve(s.a), gl::halve(s.b));
+    u64 gp = gl::pow_lookup(ginv_tab, gl::rev_bits((u32)i, log_half));
+    gl::e2 t = gl::e2_mul_base(gl::e2_mul(half_beta, d), gp);
+    gl::e2 r = gl::e2_add(s, t);
+    if (roll) r = gl::e2_add(r, gl::e2_mul(beta_sq, gl::e2_make(roll[2 * i], roll[2 * i + 1])));
+    out[2 * i] = r.a;
+    out[2 * i + 1] = r.b;
+}
+
+}  // namespace msg
+
+struct msgpu_open {
+    struct Mat {
+        const u64* ptr;
+        u64 height, width;
+        u32 log_h;
+        std::vector<msh::Fp2> points;
+        std::vector<std::vector<msh::Fp2>> values;  // [point][column]
+    };
+    msg::Ctx* ctx = nullptr;
+    u32 log_blowup = 0;
+    std::vector<std::vector<Mat>> rounds;
+    struct InvDen {
+        msh::Fp2 z;
+        u32 log_h;
+        u64* ptr;
+    };
+    std::vector<InvDen> invdens;
+    u64 n_values = 0;
+    // FRI
+    struct Input {
+        u64* ptr;
+        u64 len;
+    };
+    std::vector<Input> inputs;  // tallest first
+    size_t next_input = 0;
+    u64* cur = nullptr;
+    u64 cur_len = 0;
+    bool cur_committed = false;
+    std::vector<msgpu_pdata*> layers;
+};
+
+namespace msg {
+
+static gl::PowTable lde_x_table(Ctx& c, u32 log_h) {
+    return c.pow_table(msh::two_adic_generator(log_h).v, msh::GL_GENERATOR, log_h).view();
+}
+
+static u64* find_invden(msgpu_open* op, const msh::Fp2& z, u32 log_h) {
+    for (auto& d : op->invdens)
+        if (d.z == z && d.log_h >= log_h) return d.ptr;
+    throw Error(-3, "open: missing inverse denominators");
+}
+
+static void open_destroy(msgpu_open* op) {
+    if (!op) return;
+    Ctx& c = *op->ctx;
+    for (auto& d : op->invdens) c.free(d.ptr);
+    for (size_t k = op->next_input; k < op->inputs.size(); k++) c.free(op->inputs[k].ptr);
+    if (op->cur && !op->cur_committed) c.free(op->cur);
+    for (auto* pd : op->layers) pdata_destroy(pd);
+    delete op;
+}
+
+static void evaluate_all(Ctx& c, msgpu_open* op) {
+    StageScope ss(c, "open");
+    // 1. inverse denominators per distinct point, at the largest LDE height opened there
+    for (auto& round : op->rounds)
+        for (auto& m : round)
+            for (auto& z : m.points) {
+                bool found = false;
+                for (auto& d : op->invdens)
+                    if (d.z == z) { d.log_h = std::max(d.log_h, m.log_h); found = true; }
+                if (!found) op->invdens.push_back(msgpu_open::InvDen{z, m.log_h, nullptr});
+            }
+    for (auto& d : op->invdens) {
+        u64 H = 1ull << d.log_h;
+        d.ptr = (u64*)c.alloc(H * 16);
+        u64 threads = (H + kInvPerThread - 1) / kInvPerThread;
+        {
+            KLaunch kl(c, "k_inv_denoms");
+            k_inv_denoms<<<(unsigned)((threads + 255) / 256), 256, 0, c.stream>>>(d.ptr, d.log_h, gl::e2{d.z.c[0].v, d.z.c[1].v},
+                                                                                lde_x_table(c, d.log_h));
+        }
+        MSG_CUDA(cudaGetLastError());
+    }
+    // 2. barycentric sums per matrix (all of its points in one pass over the low coset)
+    struct Pending {
+        msgpu_open::Mat* m;
+        u64* d_partial;
+        std::vector<u64> h_partial;
+        u32 ctas, npts, c0, wc;
+        size_t p0;
+    };
+    std::vector<Pending> pend;
+    for (auto& round : op->rounds)
+        for (auto& m : round) {
+            m.values.assign(m.points.size(), std::vector<msh::Fp2>(m.width));
+            if (m.width == 0) continue;
+            u64 h = m.height >> op->log_blowup;
+            u32 log_h = m.log_h - op->log_blowup;
+            for (size_t p0 = 0; p0 < m.points.size(); p0 += kMaxPts) {
+                u32 npts = (u32)std::min<size_t>(kMaxPts, m.points.size() - p0);
+                for (u32 c0 = 0; c0 < m.width; c0 += 256) {
+                    BaryParams bp{};
+                    bp.M = m.ptr;
+                    bp.h = h;
+                    bp.w = (u32)m.width;
+                    bp.log_h = log_h;
+                    bp.npts = npts;
+                    bp.c0 = c0;
+                    bp.wc = (u32)std::min<u64>(256, m.width - c0);
+                    bp.rows_per_step = 256 / bp.wc;
+                    bp.xtab = lde_x_table(c, log_h);
+                    for (u32 k = 0; k < npts; k++) bp.invden[k] = find_invden(op, m.points[p0 + k], m.log_h);
+                    u64 want = (h + bp.rows_per_step - 1) / bp.rows_per_step;
+                    u32 ctas = (u32)std::min<u64>(want, (u64)c.sm_count * 4);
+                    Pending pd{&m, nullptr, {}, ctas, npts, c0, bp.wc, p0};
+                    pd.d_partial = (u64*)c.alloc((size_t)ctas * bp.wc * npts * 16);
+                    bp.partial = pd.d_partial;
+                    size_t smem = (size_t)bp.rows_per_step * bp.wc * npts * 16;
+                    {
+                        KLaunch kl(c, "k_bary_partial");
+                        k_bary_partial<<<ctas, 256, smem, c.stream>>>(bp);
+                    }
+                    MSG_CUDA(cudaGetLastError());
+                    pd.h_partial.resize((size_t)ctas * bp.wc * npts * 2);
+                    MSG_CUDA(cudaMemcpyAsync(pd.h_partial.data(), pd.d_partial, pd.h_partial.size() * 8, cudaMemcpyDeviceToHost, c.stream));
+                    pend.push_back(std::move(pd));
+                }
+            }
+        }
+    c.sync();
+    for (auto& pd : pend) {
+        c.free(pd.d_partial);
+        auto& m = *pd.m;
+        u32 log_h = m.log_h - op->log_blowup;
+        // y = sum * (z^h - g^h) / (h * g^h),  g = GENERATOR
+        msh::Fp shift_pow = msh::Fp(msh::GL_GENERATOR).exp_power_of_2(log_h);
+        msh::Fp denom_inv = (shift_pow * msh::Fp((msh::u64)1 << log_h)).inverse();
+        for (u32 k = 0; k < pd.npts; k++) {
+            msh::Fp2 z = m.points[pd.p0 + k];
+            msh::Fp2 scale = (z.exp_power_of_2(log_h) - shift_pow) * denom_inv;
+            for (u32 cc = 0; cc < pd.wc; cc++) {
+                msh::Fp2 s;
+                for (u32 b = 0; b < pd.ctas; b++) {
+                    size_t o = (((size_t)b * pd.wc + cc) * pd.npts + k) * 2;
+                    s += msh::Fp2(msh::Fp(pd.h_partial[o]), msh::Fp(pd.h_partial[o + 1]));
+                }
+                m.values[pd.p0 + k][pd.c0 + cc] = s * scale;
+            }
+        }
+    }
+}
+
+static void reduce_all(Ctx& c, msgpu_open* op, msh::Fp2 alpha) {
+    StageScope ss(c, "open");
+    size_t max_w = 1;
+    for (auto& round : op->rounds)
+        for (auto& m : round) max_w = std::max<size_t>(max_w, m.width);
+    std::vector<msh::Fp2> apow(max_w);
+    msh::Fp2 acc = msh::Fp2::one();
+    for (size_t i = 0; i < max_w; i++) { apow[i] = acc; acc *= alpha; }
+    std::vector<u64> apow_flat(2 * max_w);
+    for (size_t i = 0; i < max_w; i++) { apow_flat[2 * i] = apow[i].c[0].v; apow_flat[2 * i + 1] = apow[i].c[1].v; }
+    DevBuf d_apow(c, apow_flat.size() * 8);
+    MSG_CUDA(cudaMemcpyAsync(d_apow.p, apow_flat.data(), apow_flat.size() * 8, cudaMemcpyHostToDevice, c.stream));
+    u64* ro[33] = {nullptr};
+    u64 num_reduced[33] = {0};
+    static bool attr = false;
+    if (!attr) {
+        MSG_CUDA(cudaFuncSetAttribute(k_reduce_openings, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    for (auto& round : op->rounds)
+        for (auto& m : round) {
+            u32 lh = m.log_h;
+            if (!ro[lh]) {  // p3 creates the height's vector for every matrix of every round, opened or not
+                ro[lh] = (u64*)c.alloc(m.height * 16);
+                MSG_CUDA(cudaMemsetAsync(ro[lh], 0, m.height * 16, c.stream));
+            }
+            if (m.points.empty()) continue;
+            for (size_t p0 = 0; p0 < m.points.size(); p0 += kMaxPts) {
+                u32 npts = (u32)std::min<size_t>(kMaxPts, m.points.size() - p0);
+                ReduceParams rp{};
+                rp.M = m.ptr;
+                rp.apow = d_apow.u();
+                rp.ro = ro[lh];
+                rp.H = m.height;
+                rp.w = (u32)m.width;
+                rp.npts = npts;
+                for (u32 k = 0; k < npts; k++) {
+                    rp.invden[k] = find_invden(op, m.points[p0 + k], lh);
+                    msh::Fp2 aoff = alpha.pow(num_reduced[lh]);
+                    msh::Fp2 yred;
+                    for (size_t cc = 0; cc < m.width; cc++) yred += apow[cc] * m.values[p0 + k][cc];
+                    rp.aoff[k][0] = aoff.c[0].v; rp.aoff[k][1] = aoff.c[1].v;
+                    rp.yred[k][0] = yred.c[0].v; rp.yred[k][1] = yred.c[1].v;
+                    num_reduced[lh] += m.width;
+                }
+                size_t smem = ((size_t)kRedRows * (m.width | 1) + 2 * m.width) * 8;
+                MSG_REQUIRE(smem <= 200 * 1024, "open: matrix too wide for the reduced-openings kernel");
+                {
+                    KLaunch kl(c, "k_reduce_openings");
+                    k_reduce_openings<<<(unsigned)((m.height + kRedRows - 1) / kRedRows), kRedRows, smem, c.stream>>>(rp);
+                }
+                MSG_CUDA(cudaGetLastError());
+            }
+        }
+    for (int lh = 32; lh >= 0; lh--)
+        if (ro[lh]) op->inputs.push_back(msgpu_open::Input{ro[lh], 1ull << lh});
+    c.sync();  // apow_flat (pageable) must outlive its copy
+    MSG_REQUIRE(!op->inputs.empty(), "open: nothing to open");
+    op->cur = op->inputs[0].ptr;
+    op->cur_len = op->inputs[0].len;
+    op->next_input = 1;
+    op->cur_committed = false;
+}
+
+}  // namespace msg
+
+using namespace msg;
+
+extern "C" {
+
+int msgpu_open_begin(msgpu_ctx* h, uint64_t n_rounds, const msgpu_pdata* const* pds, const uint64_t* n_points,
+                     const uint64_t* points, uint32_t log_blowup, msgpu_open** out, uint64_t* n_values) {
+    return guard([&] {
+        Ctx& c = h->c;
+        MSG_REQUIRE(pds && out && n_values, "open_begin: null argument");
+        auto op = std::unique_ptr<msgpu_open, void (*)(msgpu_open*)>(new msgpu_open(), [](msgpu_open* o) {
+            try { open_destroy(o); } catch (...) {}
+        });
+        op->ctx = &c;
+        op->log_blowup = log_blowup;
+        size_t mi = 0, pi = 0;
+        u64 total = 0;
+        for (u64 r = 0; r < n_rounds; r++) {
+            MSG_REQUIRE(pds[r], "open_begin: null prover data");
+            std::vector<msgpu_open::Mat> round;
+            for (auto& pm : pds[r]->mats) {
+                msgpu_open::Mat m{pm.ptr, pm.height, pm.width, ilog2(pm.height), {}, {}};
+                MSG_REQUIRE(m.log_h >= log_blowup, "open_begin: committed matrix shorter than the blowup");
+                u64 np = n_points[mi++];
+                for (u64 k = 0; k < np; k++, pi++) {
+                    MSG_REQUIRE(points[2 * pi] < GLD_P && points[2 * pi + 1] < GLD_P, "open_begin: point is not canonical");
+                    m.points.push_back(msh::Fp2(msh::Fp(points[2 * pi]), msh::Fp(points[2 * pi + 1])));
+                }
+                total += np * pm.width;
+                round.push_back(std::move(m));
+            }
+            op->rounds.push_back(std::move(round));
+        }
+        op->n_values = total;
+        evaluate_all(c, op.get());
+        *n_values = total;
+        *out = op.release();
+    });
+}
+
+int msgpu_open_values(msgpu_open* op, uint64_t* out) {
+    return guard([&] {
+        size_t o = 0;
+        for (auto& round : op->rounds)
+            for (auto& m : round)
+                for (auto& pv : m.values)
+                    for (auto& v : pv) { out[o++] = v.c[0].v; out[o++] = v.c[1].v; }
+    });
+}
+
+int msgpu_open_reduce(msgpu_open* op, const uint64_t* alpha2, uint64_t* n_inputs, uint32_t* log_max_height) {
+    return guard([&] {
+        MSG_REQUIRE(op->inputs.empty(), "open_reduce: already reduced");
+        reduce_all(*op->ctx, op, msh::Fp2(msh::Fp(alpha2[0]), msh::Fp(alpha2[1])));
+        if (n_inputs) *n_inputs = op->inputs.size();
+        if (log_max_height) *log_max_height = ilog2(op->inputs[0].len);
+    });
+}
+
+int msgpu_open_read_input(msgpu_open* op, uint64_t k, uint64_t* out, uint64_t* len_out) {
+    return guard([&] {
+        MSG_REQUIRE(k < op->inputs.size() && (k == 0 || k >= op->next_input), "open_read_input: input already consumed");
+        Ctx& c = *op->ctx;
+        if (len_out) *len_out = op->inputs[k].len;
+        if (out) {
+            MSG_CUDA(cudaMemcpyAsync(out, op->inputs[k].ptr, op->inputs[k].len * 16, cudaMemcpyDeviceToHost, c.stream));
+            c.sync();
+        }
+    });
+}
+
+int msgpu_fri_current_len(msgpu_open* op, uint64_t* len) {
+    return guard([&] {
+        MSG_REQUIRE(op->cur, "fri: open_reduce has not run");
+        *len = op->cur_len;
+    });
+}
+
+int msgpu_fri_commit_round(msgpu_open* op, uint8_t* root32) {
+    return guard([&] {
+        Ctx& c = *op->ctx;
+        StageScope ss(c, "fri");
+        MSG_REQUIRE(op->cur && !op->cur_committed, "fri_commit_round: nothing to commit");
+        MSG_REQUIRE(op->cur_len >= 2, "fri_commit_round: vector too short to fold");
+        msgpu_pdata* pd = new msgpu_pdata();
+        pd->ctx = &c;
+        // rows of 2 extension elements = 4 base columns (ExtensionMmcs flattening)
+        pd->mats.push_back(msgpu_pdata::Mat{op->cur, op->cur_len / 2, 4, true});
+        op->cur_committed = true;  // the layer owns the buffer from here on
+        op->layers.push_back(pd);
+        mmcs_build(c, pd);
+        memcpy(root32, pd->root, 32);
+    });
+}
+
+int msgpu_fri_fold(msgpu_open* op, const uint64_t* beta2) {
+    return guard([&] {
+        Ctx& c = *op->ctx;
+        StageScope ss(c, "fri");
+        MSG_REQUIRE(op->cur && op->cur_committed, "fri_fold: commit the current vector first");
+        u64 half = op->cur_len / 2;
+        u32 log_half = ilog2(half);
+        msh::Fp2 beta{msh::Fp(beta2[0]), msh::Fp(beta2[1])};
+        msh::Fp2 hb = beta.halve(), bsq = beta.square();
+        const u64* roll = nullptr;
+        if (op->next_input < op->inputs.size() && op->inputs[op->next_input].len == half) roll = op->inputs[op->next_input].ptr;
+        u64* out = (u64*)c.alloc(half * 16);
+        gl::PowTable tab = c.pow_table(msh::two_adic_generator(log_half + 1).inverse().v, 1, log_half + 1).view();
+        {
+            KLaunch kl(c, "k_fri_fold");
+            k_fri_fold<<<(unsigned)((half + 255) / 256), 256, 0, c.stream>>>(op->cur, out, half, log_half, gl::e2{hb.c[0].v, hb.c[1].v},
+                                                                             tab, roll, gl::e2{bsq.c[0].v, bsq.c[1].v});
+        }
+        MSG_CUDA(cudaGetLastError());
+        if (roll) {
+            c.free(op->inputs[op->next_input].ptr);
+            op->next_input++;
+        }
+        op->cur = out;
+        op->cur_len = half;
+        op->cur_committed = false;
+    });
+}
+
+int msgpu_fri_read_current(msgpu_open* op, uint64_t* out) {
+    return guard([&] {
+        Ctx& c = *op->ctx;
+        MSG_REQUIRE(op->cur, "fri: open_reduce has not run");
+        MSG_CUDA(cudaMemcpyAsync(out, op->cur, op->cur_len * 16, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+    });
+}
+
+uint64_t msgpu_fri_num_layers(const msgpu_open* op) { return op->layers.size(); }
+const msgpu_pdata* msgpu_fri_layer_pdata(const msgpu_open* op, uint64_t layer) {
+    return layer < op->layers.size() ? op->layers[layer] : nullptr;
+}
+void msgpu_open_free(msgpu_open* op) {
+    try {
+        open_destroy(op);
+    } catch (...) {
+    }
+}
+
+}  // extern "C"

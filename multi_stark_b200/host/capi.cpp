@@ -2,6 +2,8 @@
 // prover.hpp -- the prove() driver over the libmsgpu C ABI). Python (tests, bench.py) binds these with ctypes.
 #include "system.hpp"
 #include "program.hpp"
+#include "gpu_backend.hpp"
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -73,5 +75,75 @@ void msh_fib_trace(uint64_t rows, uint64_t* out) {
     Matrix m = circuits::fib_cubic_trace(rows);
     for (size_t i = 0; i < m.values.size(); i++) out[i] = m.values[i].v;
 }
+
+// ---- prove(): System::prove_multiple_claims (src/prover.rs:289-603) over the libmsgpu C ABI -----------------------
+struct msh_prover {
+    msh_system* sys;
+    std::unique_ptr<GpuBackend> backend;
+    std::unique_ptr<Prover> prover;
+};
+
+// Builds the device programs and commits the preprocessed traces (System::new tail, src/system.rs:180-196).
+msh_prover* msh_prover_create(msh_system* s, msgpu_ctx* ctx) {
+    try {
+        auto p = std::make_unique<msh_prover>();
+        p->sys = s;
+        p->backend = std::make_unique<GpuBackend>(ctx, s->shape);
+        p->prover = std::make_unique<Prover>(s->shape, *p->backend);
+        return p.release();
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+void msh_prover_free(msh_prover* p) { delete p; }
+// the preprocessed commitment (verifier key); returns 0 if the system has no preprocessed trace
+int msh_prover_preprocessed_commit(const msh_prover* p, uint8_t* out32) {
+    const ProverKey& k = p->prover->key();
+    if (!k.has_preprocessed) return 0;
+    memcpy(out32, k.preprocessed_commit.data(), 32);
+    return 1;
+}
+// traces[i]: HOST heights[i] x main_width of circuit i, canonical values (heights[i] = 0: circuit inactive).
+// claims: flat values, offsets[n_claims + 1]. proof_out receives Proof::to_bytes (src/prover.rs:246-249), to be released with
+// msh_bytes_free. stage_ms[6] (optional): stage1_commit, claims, stage2_commit, quotient, fri_open, total (host wall clock).
+int msh_prove(msh_prover* p, const uint64_t* const* traces, const uint64_t* heights, const uint64_t* claims, const uint64_t* offsets,
+              uint64_t n_claims, uint8_t** proof_out, uint64_t* proof_len, double* stage_ms) {
+    try {
+        const SystemShape& shape = p->sys->shape;
+        std::vector<Matrix> mats;
+        for (size_t i = 0; i < shape.circuits.size(); i++) {
+            size_t w = shape.circuits[i].main_width, n = (size_t)heights[i] * w;
+            Matrix m(heights[i], w);
+            for (size_t k = 0; k < n; k++) {
+                if (traces[i][k] >= GL_P) throw std::runtime_error("trace value is not canonical");
+                m.values[k].v = traces[i][k];
+            }
+            mats.push_back(std::move(m));
+        }
+        std::vector<const Matrix*> ptrs;
+        for (auto& m : mats) ptrs.push_back(&m);
+        std::vector<std::vector<Fp>> cl(n_claims);
+        for (uint64_t i = 0; i < n_claims; i++)
+            for (uint64_t k = offsets[i]; k < offsets[i + 1]; k++) cl[i].push_back(Fp(claims[k]));
+        ProveTimings tm;
+        Proof proof = p->prover->prove(cl, ptrs, &tm);
+        std::vector<u8> bytes = proof_to_bytes(proof);
+        *proof_out = (uint8_t*)malloc(bytes.size());
+        memcpy(*proof_out, bytes.data(), bytes.size());
+        *proof_len = bytes.size();
+        if (stage_ms) {
+            const char* names[5] = {"stark/stage1_commit", "stark/claims", "stark/stage2_commit", "stark/quotient", "stark/fri_open"};
+            double total = 0;
+            for (int i = 0; i < 5; i++) { stage_ms[i] = tm.ms[names[i]]; total += stage_ms[i]; }
+            stage_ms[5] = total;
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+void msh_bytes_free(uint8_t* b) { free(b); }
 
 }  // extern "C"

@@ -145,3 +145,67 @@ def shifted_quotient_slices(ctx, m, q):
     check(ctx.L.msgpu_shifted_quotient_slices(ctx.h, a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1], q,
                                               out.ctypes.data_as(C.c_void_p)))
     return out
+
+
+STAGE_NAMES = ["stark/stage1_commit", "stark/claims", "stark/stage2_commit", "stark/quotient", "stark/fri_open", "stark/prove"]
+
+
+class Prover:
+    """`System::prove_multiple_claims` (src/prover.rs:289-603) on the device: the host runs the Fiat-Shamir transcript
+    (host/prover.hpp, host/pcs.hpp); every matrix stays in HBM between the LDE, Merkle, quotient and opening stages."""
+
+    def __init__(self, ctx, system):
+        self.H = _ffi.host_lib()
+        self.ctx = ctx
+        self.system = system
+        self.h = self.H.msh_prover_create(system.h, ctx.h)
+        if not self.h:
+            raise _ffi.MsgpuError(-3, (self.H.msh_last_error() or b"").decode())
+        self.last_stage_ms = None
+
+    def preprocessed_commit(self):
+        out = np.zeros(32, dtype=np.uint8)
+        return bytes(out) if self.H.msh_prover_preprocessed_commit(self.h, out.ctypes.data_as(C.c_void_p)) else None
+
+    def prove(self, traces, claims):
+        """traces: one (h x main_width) uint64 array per circuit (h = 0 deactivates the circuit);
+        claims: sequence of 1-D uint64 arrays. Returns `Proof::to_bytes`."""
+        mats = [np.ascontiguousarray(t, dtype=np.uint64) for t in traces]
+        n = len(mats)
+        ptrs = (C.c_void_p * n)(*[m.ctypes.data if m.size else None for m in mats])
+        hs = (C.c_uint64 * n)(*[m.shape[0] for m in mats])
+        if isinstance(claims, np.ndarray) and claims.ndim == 2:
+            flat = np.ascontiguousarray(claims, dtype=np.uint64).ravel()
+            offs = np.arange(claims.shape[0] + 1, dtype=np.uint64) * np.uint64(claims.shape[1])
+            n_claims = claims.shape[0]
+        else:
+            n_claims = len(claims)
+            offs = np.zeros(n_claims + 1, dtype=np.uint64)
+            for i, c in enumerate(claims):
+                offs[i + 1] = offs[i] + len(c)
+            flat = (np.concatenate([np.asarray(c, dtype=np.uint64).ravel() for c in claims]) if n_claims
+                    else np.zeros(0, dtype=np.uint64))
+        if flat.size == 0:
+            flat = np.zeros(1, dtype=np.uint64)
+        out, ln = C.c_void_p(), C.c_uint64()
+        ms = (C.c_double * 6)()
+        rc = self.H.msh_prove(self.h, ptrs, hs, flat.ctypes.data_as(_ffi.c_u64p), offs.ctypes.data_as(_ffi.c_u64p), n_claims,
+                              C.byref(out), C.byref(ln), ms)
+        if rc != 0:
+            raise _ffi.MsgpuError(rc, (self.H.msh_last_error() or b"").decode())
+        data = C.string_at(out.value, ln.value)
+        self.H.msh_bytes_free(out)
+        self.last_stage_ms = dict(zip(STAGE_NAMES, ms))
+        return data
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.H.msh_prover_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.close()
+        except Exception:
+            pass

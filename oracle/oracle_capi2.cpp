@@ -1,14 +1,10 @@
 // ORACLE C entry points, part 2 (test infrastructure, not product code): systems, stage-2 traces, quotient
 // values. Loaded with ctypes by tests/, __graft_entry__.smoke() and bench.py's CPU legs ONLY.
-#include "cpu_eval.hpp"
+#include "orc_system.hpp"
 #include <cstring>
 #include <memory>
 
 using namespace orc;
-
-struct OrcSystem {
-    SystemShape shape;
-};
 
 static Matrix to_matrix2(const u64* in, u64 rows, u64 cols) {
     Matrix m(rows, cols);

@@ -63,6 +63,12 @@ def lib():
         "orc_selectors_on_coset": (None, [C.c_uint32, C.c_uint32, C.c_uint64, u64p, u64p, u64p, u64p]),
         "orc_pcs_commit": (C.c_void_p, [C.POINTER(C.c_void_p), u64p, u64p, C.c_uint64, C.c_uint32, u8p]),
         "orc_mmcs_matrix": (None, [C.c_void_p, C.c_uint64, u64p]),
+        "orc_last_error": (C.c_char_p, []),
+        "orc_prove": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), u64p, u64p, u64p, C.c_uint64, C.POINTER(C.c_void_p),
+                                C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
+        "orc_bytes_free": (None, [C.c_void_p]),
+        "orc_preprocessed_commit": (C.c_int, [C.c_void_p, u8p]),
+        "orc_verify": (C.c_int, [C.c_void_p, u64p, u64p, C.c_uint64, u8p, C.c_uint64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -143,3 +149,65 @@ def pcs_commit(L, mats, log_blowup):
     h = L.orc_pcs_commit(ptrs, hs, ws, n, log_blowup, root)
     assert h, "orc_pcs_commit failed"
     return bytes(root), h
+
+
+VERIFY_ERRORS = {0: "Ok", 1: "InvalidClaim", 2: "InvalidOpeningArgument", 3: "InvalidProofShape", 4: "InvalidSystem",
+                 5: "OodEvaluationMismatch", 6: "UnbalancedChannel", -1: "Deserialize"}
+
+
+def flatten_claims(claims):
+    """list of 1-D arrays -> (flat u64 values, offsets[n+1])"""
+    offs = np.zeros(len(claims) + 1, dtype=np.uint64)
+    for i, c in enumerate(claims):
+        offs[i + 1] = offs[i] + len(c)
+    flat = np.concatenate([np.asarray(c, dtype=np.uint64).ravel() for c in claims]) if len(claims) else np.zeros(0, dtype=np.uint64)
+    if flat.size == 0:
+        flat = np.zeros(1, dtype=np.uint64)
+    return np.ascontiguousarray(flat), offs
+
+
+class OracleSystem:
+    """The oracle's System: CPU prover (src/prover.rs) and restated verifier (src/verifier.rs)."""
+
+    def __init__(self, L, kind, log_blowup=1, log_final_poly_len=0, max_log_arity=1, num_queries=100, commit_pow_bits=0,
+                 query_pow_bits=0):
+        self.L = L
+        self.h = L.orc_system_create(kind.encode(), log_blowup, log_final_poly_len, max_log_arity, num_queries,
+                                     commit_pow_bits, query_pow_bits)
+        assert self.h, "orc_system_create failed"
+
+    def prove(self, traces, claims):
+        """traces: one (h x w) array per circuit (h = 0: inactive). Returns (proof bytes, stage ms[6])."""
+        mats = [np.ascontiguousarray(t, dtype=np.uint64) for t in traces]
+        n = len(mats)
+        ptrs = (C.c_void_p * n)(*[m.ctypes.data if m.size else None for m in mats])
+        hs = np.array([m.shape[0] for m in mats], dtype=np.uint64)
+        flat, offs = flatten_claims(claims)
+        out, ln = C.c_void_p(), C.c_uint64()
+        ms = (C.c_double * 6)()
+        rc = self.L.orc_prove(self.h, ptrs, hs, flat, offs, len(claims), C.byref(out), C.byref(ln), ms)
+        if rc != 0:
+            raise RuntimeError(self.L.orc_last_error().decode())
+        data = C.string_at(out.value, ln.value)
+        self.L.orc_bytes_free(out)
+        return data, list(ms)
+
+    def verify(self, claims, proof_bytes):
+        flat, offs = flatten_claims(claims)
+        buf = np.frombuffer(proof_bytes, dtype=np.uint8).copy() if len(proof_bytes) else np.zeros(1, dtype=np.uint8)
+        return VERIFY_ERRORS.get(self.L.orc_verify(self.h, flat, offs, len(claims), buf, len(proof_bytes)), "Error")
+
+    def preprocessed_commit(self):
+        out = np.zeros(32, dtype=np.uint8)
+        return bytes(out) if self.L.orc_preprocessed_commit(self.h, out) else None
+
+    def close(self):
+        if self.h:
+            self.L.orc_system_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
