@@ -57,6 +57,10 @@ int msgpu_memcpy_h2d(msgpu_ctx* ctx, void* dst_dev, const void* src_host, size_t
 int msgpu_memcpy_d2h(msgpu_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 int msgpu_host_alloc(size_t bytes, void** hptr); /* pinned host memory */
 int msgpu_host_free(void* hptr);
+/* H2D copy of n field elements that also verifies the ABI's precondition on the device: every value must be
+ * canonical (< p). Returns MSGPU_ERR_INVALID otherwise (a typed `Goldilocks` can never be out of range in the
+ * reference; raw u64 buffers can). */
+int msgpu_upload_canonical(msgpu_ctx* ctx, void* dst_dev, const uint64_t* src_host, uint64_t n);
 
 /* ---- TwoAdicSubgroupDft slot (reference: `type Dft = Radix2DitParallel<Val>`, src/types.rs:200;
  *      used at src/prover.rs:440,650,716) ------------------------------------------------------- */
@@ -167,6 +171,18 @@ int msgpu_claims_accumulator(msgpu_ctx* ctx, const uint64_t* claims, uint64_t n_
  * acc, next_acc) as base coordinates. Returns a device matrix of (n << log_blowup) rows x 2q columns from
  * msgpu_malloc (pass it to msgpu_commit_ldes_dev with take_ownership = 1).
  * quotient_values_out (optional, HOST, n*q*2 values) receives the quotient evaluations in natural order. */
+/* Device-resident claims for one proof. Uploads n_claims x claim_len HOST values (verified canonical on the device) and
+ * returns in digest32 the BLAKE3 of
+ *     transcript_prefix || for each claim: le64(claim_len) || le64(value_0) || ... || le64(value_{claim_len-1})
+ * i.e. of the challenger's observation buffer after the claims loop of src/prover.rs:369-372, so the host transcript
+ * (`HashChallenger` flush) does not have to materialise 40 bytes per claim. The handle then serves the initial
+ * accumulator (src/prover.rs:381-387) without a second copy. */
+typedef struct msgpu_claims msgpu_claims;
+int msgpu_claims_upload(msgpu_ctx* ctx, const uint64_t* claims, uint64_t n_claims, uint64_t claim_len,
+                        const uint8_t* transcript_prefix, uint64_t prefix_len, msgpu_claims** out, uint8_t* digest32);
+int msgpu_claims_accumulate(msgpu_claims* cl, const uint64_t* beta2, const uint64_t* gamma2, uint64_t* out2);
+void msgpu_claims_free(msgpu_claims* cl);
+
 int msgpu_quotient(msgpu_ctx* ctx, const msgpu_program* prog, const msgpu_pdata* pd_pre, uint64_t idx_pre,
                    const msgpu_pdata* pd_s1, uint64_t idx_s1, const msgpu_pdata* pd_s2, uint64_t idx_s2, uint32_t log_n,
                    uint32_t log_quotient_degree, uint32_t log_blowup, const uint64_t* publics8, const uint64_t* alpha2,
@@ -206,6 +222,13 @@ int msgpu_fri_read_current(msgpu_open* op, uint64_t* out);
 uint64_t msgpu_fri_num_layers(const msgpu_open* op);
 const msgpu_pdata* msgpu_fri_layer_pdata(const msgpu_open* op, uint64_t layer);
 void msgpu_open_free(msgpu_open* op);
+
+/* ---- transcript helper ---------------------------------------------------------------------------
+ * Unkeyed BLAKE3-256 of a HOST byte string, hashed on the device (chunk chaining values in parallel, then the
+ * binary parent tree). The reference's challenger is `HashChallenger<u8, Blake3, 32>` (src/types.rs:28-29); its
+ * flush hashes the whole observation buffer, which holds 40 bytes per claim (src/prover.rs:368-373): 42 MB at
+ * 2^20 claims. The digest is by definition the same as the CPU's. */
+int msgpu_blake3_hash(msgpu_ctx* ctx, const uint8_t* data, uint64_t len, uint8_t* out32);
 
 /* ---- test hooks --------------------------------------------------------------------------------- */
 /* raw 7-round BLAKE3 compression of a 16-word state and 16 message words (known-answer vector of

@@ -27,6 +27,8 @@ SIGNATURES = {
     "msgpu_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "msgpu_host_alloc": (C.c_int, [C.c_size_t, c_vpp]),
     "msgpu_host_free": (C.c_int, [C.c_void_p]),
+    "msgpu_upload_canonical": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "msgpu_blake3_hash": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "msgpu_dft_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "msgpu_dft_batch_bitrev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "msgpu_idft_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
@@ -57,6 +59,9 @@ SIGNATURES = {
                                      C.c_void_p, C.c_void_p]),
     "msgpu_claims_accumulator": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                            C.c_void_p]),
+    "msgpu_claims_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, c_vpp, C.c_void_p]),
+    "msgpu_claims_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "msgpu_claims_free": (None, [C.c_void_p]),
     "msgpu_quotient": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
                                  C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, c_vpp, C.c_void_p]),
     "msgpu_shifted_quotient_slices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),

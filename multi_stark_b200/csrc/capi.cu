@@ -2,6 +2,7 @@
 // turns them into error codes + a thread-local message; nothing unwinds across the ABI.
 #include "capi_common.hpp"
 #include "mmcs.hpp"
+#include "../host/blake3_host.hpp"
 #include <cstring>
 
 namespace msg {
@@ -151,6 +152,40 @@ int msgpu_host_alloc(size_t bytes, void** hptr) {
 }
 int msgpu_host_free(void* hptr) {
     return guard([&] { MSG_CUDA(cudaFreeHost(hptr)); });
+}
+
+int msgpu_upload_canonical(msgpu_ctx* h, void* dst, const uint64_t* src, uint64_t n) {
+    return guard([&] {
+        Ctx& c = h->c;
+        if (n == 0) return;
+        MSG_CUDA(cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyHostToDevice, c.stream));
+        DevBuf flag(c, 4);
+        MSG_CUDA(cudaMemsetAsync(flag.p, 0, 4, c.stream));
+        check_canonical(c, (const u64*)dst, n, (u32*)flag.p);
+        u32 bad = 0;
+        MSG_CUDA(cudaMemcpyAsync(&bad, flag.p, 4, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+        MSG_REQUIRE(bad == 0, "upload: value is not a canonical field element (>= p)");
+    });
+}
+
+int msgpu_blake3_hash(msgpu_ctx* h, const uint8_t* data, uint64_t len, uint8_t* out32) {
+    return guard([&] {
+        Ctx& c = h->c;
+        MSG_REQUIRE(out32 && (data || len == 0), "blake3_hash: null argument");
+        if (len <= 1024) {  // a single chunk: not worth a launch
+            msh::Digest d = msh::blake3_hash(data, (size_t)len);
+            memcpy(out32, d.data(), 32);
+            return;
+        }
+        StageScope ss(c, "transcript");
+        DevBuf buf(c, len + 64);
+        uint8_t* out_dev = (uint8_t*)buf.p + ((len + 15) / 16) * 16;
+        MSG_CUDA(cudaMemcpyAsync(buf.p, data, len, cudaMemcpyHostToDevice, c.stream));
+        b3_hash_long(c, (const uint8_t*)buf.p, len, out_dev);
+        MSG_CUDA(cudaMemcpyAsync(out32, out_dev, 32, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+    });
 }
 
 int msgpu_profile_begin(msgpu_ctx* h) {

@@ -122,6 +122,11 @@ void b3_hash_rows(Ctx& c, const std::vector<MatRef>& mats, uint8_t* digests);
 // next[i] = H(prev[2i] || prev[2i+1]), optionally followed by H(that || inject[i])
 void b3_compress_layer(Ctx& c, const uint8_t* prev, const uint8_t* inject, uint8_t* next, u64 next_len);
 
+// BLAKE3 of one long (> 1024 bytes) device-resident byte string; out_dev receives 32 bytes
+void b3_hash_long(Ctx& c, const uint8_t* data_dev, u64 len, uint8_t* out_dev);
+// sets *flag_dev |= 1 if any v[i] >= p
+void check_canonical(Ctx& c, const u64* v, u64 n, u32* flag_dev);
+
 inline unsigned ilog2(u64 n) {
     unsigned l = 0;
     while ((1ull << l) < n) l++;

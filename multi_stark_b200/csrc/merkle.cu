@@ -152,6 +152,105 @@ __global__ void k_compress_raw(const u32* st, const u32* msg, u32* out) {
     for (int i = 0; i < 16; i++) out[i] = o[i];
 }
 
+// ---- BLAKE3 of one long byte string (the transcript's observation buffer) -----------------------------------
+// chunk chaining values: one thread per 1024-byte chunk, 16 chained blocks (the last chunk may be short)
+__global__ void __launch_bounds__(128) k_b3_chunk_cvs(const uint4* data, u64 len, u64 nchunks, u32* cvs) {
+    u64 ci = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= nchunks) return;
+    const u64 cstart = ci * 1024;
+    const u32 cbytes = (u32)min((u64)1024, len - cstart);
+    const u32 nblocks = cbytes == 0 ? 1u : (cbytes + 63u) / 64u;
+    u32 cv[8];
+    b3::set_iv(cv);
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(data);
+    for (u32 b = 0; b < nblocks; b++) {
+        u32 m[16];
+        const u32 blen = min(64u, cbytes - b * 64u);
+        if (blen == 64) {
+            const uint4* src = data + (cstart + b * 64) / 16;
+            uint4 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3];
+            m[0] = v0.x; m[1] = v0.y; m[2] = v0.z; m[3] = v0.w; m[4] = v1.x; m[5] = v1.y; m[6] = v1.z; m[7] = v1.w;
+            m[8] = v2.x; m[9] = v2.y; m[10] = v2.z; m[11] = v2.w; m[12] = v3.x; m[13] = v3.y; m[14] = v3.z; m[15] = v3.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                u32 w = 0;
+                for (int k = 0; k < 4; k++) {
+                    u32 off = b * 64u + i * 4u + k;
+                    if (off < cbytes) w |= (u32)bytes[cstart + off] << (8 * k);
+                }
+                m[i] = w;
+            }
+        }
+        u32 flags = (b == 0 ? b3::CHUNK_START : 0u) | (b + 1 == nblocks ? b3::CHUNK_END : 0u);
+        b3::compress(cv, m, (u32)ci, (u32)(ci >> 32), blen, flags);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) cvs[ci * 8 + i] = cv[i];
+}
+// one level of the BLAKE3 tree: adjacent pairs merge, an odd last node moves up unchanged (this reproduces the
+// left-heavy tree: the left subtree always holds the largest power of two of chunks)
+__global__ void __launch_bounds__(128) k_b3_parent_level(const u32* in, u64 n_in, u32* out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 n_out = (n_in + 1) / 2;
+    if (i >= n_out) return;
+    u32 cv[8];
+    if (2 * i + 1 < n_in) {
+        u32 m[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) m[k] = in[(2 * i) * 8 + k];
+        b3::set_iv(cv);
+        b3::compress(cv, m, 0, 0, 64, b3::PARENT | (n_in == 2 ? b3::ROOT : 0u));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) cv[k] = in[(2 * i) * 8 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) out[i * 8 + k] = cv[k];
+}
+
+// data_dev: 16-byte aligned device copy of the message (len > 1024). out_dev: 32 bytes.
+void b3_hash_long(Ctx& c, const uint8_t* data_dev, u64 len, uint8_t* out_dev) {
+    MSG_REQUIRE(len > 1024, "b3_hash_long: message fits one chunk");
+    u64 nchunks = (len + 1023) / 1024;
+    u32* a = (u32*)c.alloc(nchunks * 32);
+    u32* b = (u32*)c.alloc((nchunks + 1) / 2 * 32);
+    {
+        KLaunch kl(c, "k_b3_chunk_cvs");
+        k_b3_chunk_cvs<<<(unsigned)((nchunks + 127) / 128), 128, 0, c.stream>>>((const uint4*)data_dev, len, nchunks, a);
+    }
+    MSG_CUDA(cudaGetLastError());
+    u64 n = nchunks;
+    while (n > 1) {
+        u64 n_out = (n + 1) / 2;
+        {
+            KLaunch kl(c, "k_b3_parent_level");
+            k_b3_parent_level<<<(unsigned)((n_out + 127) / 128), 128, 0, c.stream>>>(a, n, b);
+        }
+        MSG_CUDA(cudaGetLastError());
+        std::swap(a, b);
+        n = n_out;
+    }
+    MSG_CUDA(cudaMemcpyAsync(out_dev, a, 32, cudaMemcpyDeviceToDevice, c.stream));
+    c.free(a);
+    c.free(b);
+}
+
+__global__ void __launch_bounds__(256) k_check_canonical(const u64* v, u64 n, u32* flag) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    for (; i < n; i += (u64)gridDim.x * blockDim.x) bad |= v[i] >= GLD_P;
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+void check_canonical(Ctx& c, const u64* v, u64 n, u32* flag_dev) {
+    u64 blocks = std::min<u64>((n + 255) / 256, (u64)c.sm_count * 8);
+    {
+        KLaunch kl(c, "k_check_canonical");
+        k_check_canonical<<<(unsigned)std::max<u64>(blocks, 1), 256, 0, c.stream>>>(v, n, flag_dev);
+    }
+    MSG_CUDA(cudaGetLastError());
+}
+
 void b3_hash_rows(Ctx& c, const std::vector<MatRef>& mats, uint8_t* digests) {
     MSG_REQUIRE(!mats.empty(), "hash_rows: no matrices");
     u64 height = mats[0].height;

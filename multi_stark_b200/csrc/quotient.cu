@@ -16,6 +16,8 @@
 // committed LDEs are read where they lie: the quotient domain GENERATOR * H_{nq} is the first nq stored
 // rows of every LDE in bit-reversed order, so the "current row" stream is fully coalesced.
 #include "capi_common.hpp"
+#include "../host/blake3_host.hpp"
+#include <cstring>
 #include "mmcs.hpp"
 #include <algorithm>
 #include <cstring>
@@ -648,6 +650,48 @@ static void view_of(const msgpu_pdata* pd, u64 idx, u64 nq, u32 width, const u64
 
 using namespace msg;
 
+struct msgpu_claims {
+    Ctx* ctx;
+    u64* d;
+    u64 n, len;
+};
+
+namespace msg {
+// msg[prefix_len + 8*j ..] = le64(word j), word j of claim i = j / (len+1): position 0 is the length, then the values
+__global__ void __launch_bounds__(256) k_encode_claims(const u64* claims, u64 n_words, u32 len, uint8_t* msg) {
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_words) return;
+    u64 claim = j / (len + 1);
+    u32 k = (u32)(j % (len + 1));
+    u64 v = k == 0 ? (u64)len : claims[claim * len + (k - 1)];
+    uint8_t* o = msg + 8 * j;
+#pragma unroll
+    for (int b = 0; b < 8; b++) o[b] = (uint8_t)(v >> (8 * b));
+}
+}  // namespace msg
+
+static void claims_sum(Ctx& c, const u64* d_claims, u64 n_claims, u64 claim_len, const uint64_t* beta2, const uint64_t* gamma2,
+                       uint64_t* out2) {
+    StageScope ss(c, "stage2");
+    out2[0] = out2[1] = 0;
+    if (n_claims == 0) return;
+    u64 nblocks = (n_claims + kScanPerBlock - 1) / kScanPerBlock;
+    DevBuf part(c, nblocks * 16);
+    {
+        KLaunch kl(c, "k_claims");
+        k_claims<<<(unsigned)nblocks, kScanThreads, 0, c.stream>>>(d_claims, n_claims, (u32)claim_len, gl::e2{beta2[0], beta2[1]},
+                                                                   gl::e2{gamma2[0], gamma2[1]}, part.u());
+    }
+    MSG_CUDA(cudaGetLastError());
+    std::vector<u64> hp(nblocks * 2);
+    MSG_CUDA(cudaMemcpyAsync(hp.data(), part.p, nblocks * 16, cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    msh::Fp2 acc;
+    for (u64 b = 0; b < nblocks; b++) acc += msh::Fp2(msh::Fp(hp[2 * b]), msh::Fp(hp[2 * b + 1]));
+    out2[0] = acc.c[0].v;
+    out2[1] = acc.c[1].v;
+}
+
 extern "C" {
 
 int msgpu_program_create(msgpu_ctx* h, const msgpu_graph_desc* desc, msgpu_program** out) {
@@ -726,27 +770,64 @@ int msgpu_claims_accumulator(msgpu_ctx* h, const uint64_t* claims, uint64_t n_cl
                              const uint64_t* beta2, const uint64_t* gamma2, uint64_t* out2) {
     return guard([&] {
         Ctx& c = h->c;
-        StageScope ss(c, "stage2");
-        out2[0] = out2[1] = 0;
-        if (n_claims == 0) return;
         MSG_REQUIRE(claim_len < (1ull << 31), "claims: claim too long");
-        u64 nblocks = (n_claims + kScanPerBlock - 1) / kScanPerBlock;
-        DevBuf d(c, n_claims * std::max<u64>(claim_len, 1) * 8), part(c, nblocks * 16);
-        if (claim_len) MSG_CUDA(cudaMemcpyAsync(d.p, claims, n_claims * claim_len * 8, cudaMemcpyHostToDevice, c.stream));
+        DevBuf d(c, n_claims * std::max<u64>(claim_len, 1) * 8);
+        if (claim_len && n_claims) MSG_CUDA(cudaMemcpyAsync(d.p, claims, n_claims * claim_len * 8, cudaMemcpyHostToDevice, c.stream));
+        claims_sum(c, d.u(), n_claims, claim_len, beta2, gamma2, out2);
+    });
+}
+
+int msgpu_claims_upload(msgpu_ctx* h, const uint64_t* claims, uint64_t n_claims, uint64_t claim_len, const uint8_t* prefix,
+                        uint64_t prefix_len, msgpu_claims** out, uint8_t* digest32) {
+    return guard([&] {
+        Ctx& c = h->c;
+        MSG_REQUIRE(out && digest32 && claims && n_claims > 0 && claim_len > 0, "claims_upload: null or empty argument");
+        MSG_REQUIRE(claim_len < (1ull << 31) && n_claims <= (~0ull) / 16 / (claim_len + 1), "claims_upload: too large");
+        StageScope ss(c, "transcript");
+        u64 n_vals = n_claims * claim_len, n_words = n_claims * (claim_len + 1), msg_len = prefix_len + 8 * n_words;
+        DevBuf d(c, n_vals * 8), msg(c, msg_len + 64), flag(c, 4);
+        MSG_CUDA(cudaMemcpyAsync(d.p, claims, n_vals * 8, cudaMemcpyHostToDevice, c.stream));
+        MSG_CUDA(cudaMemsetAsync(flag.p, 0, 4, c.stream));
+        check_canonical(c, d.u(), n_vals, (u32*)flag.p);
+        if (prefix_len) MSG_CUDA(cudaMemcpyAsync(msg.p, prefix, prefix_len, cudaMemcpyHostToDevice, c.stream));
         {
-            KLaunch kl(c, "k_claims");
-            k_claims<<<(unsigned)nblocks, kScanThreads, 0, c.stream>>>(d.u(), n_claims, (u32)claim_len,
-                                                                       gl::e2{beta2[0], beta2[1]}, gl::e2{gamma2[0], gamma2[1]}, part.u());
+            KLaunch kl(c, "k_encode_claims");
+            k_encode_claims<<<(unsigned)((n_words + 255) / 256), 256, 0, c.stream>>>(d.u(), n_words, (u32)claim_len,
+                                                                                     (uint8_t*)msg.p + prefix_len);
         }
         MSG_CUDA(cudaGetLastError());
-        std::vector<u64> hp(nblocks * 2);
-        MSG_CUDA(cudaMemcpyAsync(hp.data(), part.p, nblocks * 16, cudaMemcpyDeviceToHost, c.stream));
-        c.sync();
-        msh::Fp2 acc;
-        for (u64 b = 0; b < nblocks; b++) acc += msh::Fp2(msh::Fp(hp[2 * b]), msh::Fp(hp[2 * b + 1]));
-        out2[0] = acc.c[0].v;
-        out2[1] = acc.c[1].v;
+        u32 bad = 0;
+        if (msg_len > 1024) {
+            uint8_t* out_dev = (uint8_t*)msg.p + ((msg_len + 15) / 16) * 16;
+            b3_hash_long(c, (const uint8_t*)msg.p, msg_len, out_dev);
+            MSG_CUDA(cudaMemcpyAsync(digest32, out_dev, 32, cudaMemcpyDeviceToHost, c.stream));
+            MSG_CUDA(cudaMemcpyAsync(&bad, flag.p, 4, cudaMemcpyDeviceToHost, c.stream));
+            c.sync();
+        } else {
+            std::vector<uint8_t> hm(msg_len);
+            MSG_CUDA(cudaMemcpyAsync(hm.data(), msg.p, msg_len, cudaMemcpyDeviceToHost, c.stream));
+            MSG_CUDA(cudaMemcpyAsync(&bad, flag.p, 4, cudaMemcpyDeviceToHost, c.stream));
+            c.sync();
+            msh::Digest dg = msh::blake3_hash(hm.data(), hm.size());
+            memcpy(digest32, dg.data(), 32);
+        }
+        MSG_REQUIRE(bad == 0, "claims_upload: claim value is not a canonical field element (>= p)");
+        *out = new msgpu_claims{&c, (u64*)d.release(), n_claims, claim_len};
     });
+}
+int msgpu_claims_accumulate(msgpu_claims* cl, const uint64_t* beta2, const uint64_t* gamma2, uint64_t* out2) {
+    return guard([&] {
+        MSG_REQUIRE(cl && beta2 && gamma2 && out2, "claims_accumulate: null argument");
+        claims_sum(*cl->ctx, cl->d, cl->n, cl->len, beta2, gamma2, out2);
+    });
+}
+void msgpu_claims_free(msgpu_claims* cl) {
+    if (!cl) return;
+    try {
+        cl->ctx->free(cl->d);
+    } catch (...) {
+    }
+    delete cl;
 }
 
 int msgpu_quotient(msgpu_ctx* h, const msgpu_program* prog, const msgpu_pdata* pd_pre, uint64_t idx_pre,

@@ -111,23 +111,15 @@ int msh_prove(msh_prover* p, const uint64_t* const* traces, const uint64_t* heig
               uint64_t n_claims, uint8_t** proof_out, uint64_t* proof_len, double* stage_ms) {
     try {
         const SystemShape& shape = p->sys->shape;
-        std::vector<Matrix> mats;
-        for (size_t i = 0; i < shape.circuits.size(); i++) {
-            size_t w = shape.circuits[i].main_width, n = (size_t)heights[i] * w;
-            Matrix m(heights[i], w);
-            for (size_t k = 0; k < n; k++) {
-                if (traces[i][k] >= GL_P) throw std::runtime_error("trace value is not canonical");
-                m.values[k].v = traces[i][k];
-            }
-            mats.push_back(std::move(m));
-        }
-        std::vector<const Matrix*> ptrs;
-        for (auto& m : mats) ptrs.push_back(&m);
-        std::vector<std::vector<Fp>> cl(n_claims);
-        for (uint64_t i = 0; i < n_claims; i++)
-            for (uint64_t k = offsets[i]; k < offsets[i + 1]; k++) cl[i].push_back(Fp(claims[k]));
+        std::vector<MatrixView> views;
+        for (size_t i = 0; i < shape.circuits.size(); i++)
+            views.push_back(MatrixView((const Fp*)traces[i], (size_t)heights[i], shape.circuits[i].main_width));
+        ClaimsView cl;
+        cl.values = (const Fp*)claims;
+        cl.offsets = offsets;
+        cl.n = (size_t)n_claims;
         ProveTimings tm;
-        Proof proof = p->prover->prove(cl, ptrs, &tm);
+        Proof proof = p->prover->prove(cl, views, &tm);
         std::vector<u8> bytes = proof_to_bytes(proof);
         *proof_out = (uint8_t*)malloc(bytes.size());
         memcpy(*proof_out, bytes.data(), bytes.size());

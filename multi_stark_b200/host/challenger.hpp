@@ -13,6 +13,7 @@
 #pragma once
 #include "goldilocks.hpp"
 #include "blake3_host.hpp"
+#include <functional>
 #include <vector>
 
 namespace msh {
@@ -48,8 +49,11 @@ class Challenger {
         output_.clear();
         input_.push_back(b);
     }
-    void observe(Fp v) {
-        for (int b = 0; b < 8; b++) observe_byte((u8)(v.v >> (8 * b)));
+    void observe(Fp v) {  // 8 x observe_byte
+        output_.clear();
+        u8 le[8];
+        for (int b = 0; b < 8; b++) le[b] = (u8)(v.v >> (8 * b));
+        input_.insert(input_.end(), le, le + 8);
     }
     void observe_usize(size_t x) { observe(Fp((u64)x)); }
     void observe(const Fp2& v) {  // observe_algebra_element
@@ -57,8 +61,12 @@ class Challenger {
         observe(v.c[1]);
     }
     void observe(const Digest& d) {
-        for (u8 b : d) observe_byte(b);
+        output_.clear();
+        input_.insert(input_.end(), d.begin(), d.end());
     }
+    // BLAKE3 of a long input buffer may be computed elsewhere (the device: gpu_backend.hpp); same digest by definition.
+    using BigHash = std::function<Digest(const u8*, size_t)>;
+    void set_big_hash(BigHash f, size_t threshold) { big_hash_ = std::move(f); big_threshold_ = threshold; }
     void observe_slice(const Fp* v, size_t n) {
         for (size_t i = 0; i < n; i++) observe(v[i]);
     }
@@ -105,14 +113,22 @@ class Challenger {
     }
 
     const std::vector<u8>& input_buffer() const { return input_; }
+    // The caller observed further bytes "virtually" and hashed input_buffer() || those bytes elsewhere (the device);
+    // continue exactly as after the flush() that the next sample would have performed.
+    void set_flushed(const Digest& d) {
+        input_.assign(d.begin(), d.end());
+        output_.assign(d.begin(), d.end());
+    }
 
   private:
     void flush() {
-        Digest d = blake3_hash(input_);
+        Digest d = (big_hash_ && input_.size() >= big_threshold_) ? big_hash_(input_.data(), input_.size()) : blake3_hash(input_);
         input_.assign(d.begin(), d.end());
         output_.assign(d.begin(), d.end());
     }
     std::vector<u8> input_, output_;
+    BigHash big_hash_;
+    size_t big_threshold_ = 0;
 };
 
 }  // namespace msh

@@ -75,6 +75,8 @@ struct Fp {
     Fp halve() const { Fp r; r.v = (v & 1) ? (v >> 1) + (GL_P >> 1) + 1 : v >> 1; return r; }
 };
 
+static_assert(sizeof(Fp) == 8, "Fp must be layout-compatible with uint64_t");
+
 // two_adic_generator(bits): generator of the order-2^bits subgroup (p3 TwoAdicField).
 static inline Fp two_adic_generator(unsigned bits) {
     assert(bits <= GL_TWO_ADICITY);
@@ -158,6 +160,36 @@ struct Matrix {
     size_t height() const { return width ? values.size() / width : 0; }
     Fp* row(size_t r) { return values.data() + r * width; }
     const Fp* row(size_t r) const { return values.data() + r * width; }
+};
+
+// Borrowed row-major matrix (the caller's memory; `Fp` is layout-compatible with a canonical uint64_t).
+struct MatrixView {
+    const Fp* data = nullptr;
+    size_t h = 0, width = 0;
+    MatrixView() = default;
+    MatrixView(const Fp* d, size_t height, size_t w) : data(d), h(height), width(w) {}
+    MatrixView(const Matrix& m) : data(m.values.data()), h(m.height()), width(m.width) {}
+    size_t height() const { return h; }
+    const Fp* row(size_t r) const { return data + r * width; }
+    Matrix to_matrix() const { return Matrix(std::vector<Fp>(data, data + h * width), width); }
+};
+
+// Borrowed claims: `values` flat, claim i = values[offsets[i] .. offsets[i+1])  (src/prover.rs:289-294 `claims: &[&[Val]]`).
+struct ClaimsView {
+    const Fp* values = nullptr;
+    const u64* offsets = nullptr;
+    size_t n = 0;
+    size_t size() const { return n; }
+    size_t len(size_t i) const { return (size_t)(offsets[i + 1] - offsets[i]); }
+    const Fp* at(size_t i) const { return values + offsets[i]; }
+    // all claims of one length (the common case: one call shape), 0 if empty or ragged
+    size_t uniform_len() const {
+        if (n == 0) return 0;
+        size_t l = len(0);
+        for (size_t i = 1; i < n; i++)
+            if (len(i) != l) return 0;
+        return l;
+    }
 };
 
 }  // namespace msh

@@ -154,7 +154,8 @@ class GpuBackend : public ProverBackend {
             programs_.push_back(p);
             // the preprocessed trace in natural order stays on the device for the stage-2 construction
             uint64_t* dp = nullptr;
-            if (c.has_preprocessed && !c.preprocessed.values.empty()) dp = upload(c.preprocessed);
+            if (c.has_preprocessed && !c.preprocessed.values.empty())
+                dp = upload((const uint64_t*)c.preprocessed.values.data(), c.preprocessed.values.size());
             pre_dev_.push_back(dp);
         }
     }
@@ -174,43 +175,70 @@ class GpuBackend : public ProverBackend {
         return std::make_shared<GpuPcsHandle>(pd);
     }
 
-    PcsHandlePtr commit_stage1(const std::vector<size_t>& circuits, const std::vector<const Matrix*>& traces, Digest& root) override {
+    PcsHandlePtr commit_stage1(const std::vector<size_t>& circuits, const std::vector<MatrixView>& traces, Digest& root) override {
         end_proof();
         active_ = circuits;
         std::vector<const uint64_t*> ptrs;
         std::vector<uint64_t> hs, ws;
-        for (auto* m : traces) {
-            uint64_t* d = upload(*m);
+        for (auto& m : traces) {
+            uint64_t* d = upload((const uint64_t*)m.data, m.height() * m.width);
             trace_dev_.push_back(d);
-            trace_rows_.push_back(m->height());
+            trace_rows_.push_back(m.height());
             ptrs.push_back(d);
-            hs.push_back(m->height());
-            ws.push_back(m->width);
+            hs.push_back(m.height());
+            ws.push_back(m.width);
         }
         msgpu_pdata* pd = nullptr;
         gpu_check(msgpu_commit_dev(ctx_, ptrs.data(), hs.data(), ws.data(), traces.size(), (uint32_t)shape_.log_blowup(), &pd, root.data()));
         return std::make_shared<GpuPcsHandle>(pd);
     }
 
-    Fp2 claims_accumulator(const std::vector<std::vector<Fp>>& claims, Fp2 beta, Fp2 gamma) override {
-        // the C ABI takes claims of one length per call; group consecutive claims of equal length
+    bool observe_claims(Challenger& ch, const ClaimsView& claims) override {
+        size_t len = claims.uniform_len();
+        if (len == 0 || claims.size() * len < 4096) {  // small or ragged: the host loop is cheaper; the ABI's precondition is checked here
+            size_t total = claims.size() ? (size_t)claims.offsets[claims.size()] : 0;
+            for (size_t k = 0; k < total; k++)
+                if (claims.values[k].v >= GL_P) throw GpuError("claim value is not canonical");
+            return false;
+        }
+        drop_claims();
+        Digest d;
+        const std::vector<u8>& prefix = ch.input_buffer();
+        gpu_check(msgpu_claims_upload(ctx_, (const uint64_t*)claims.at(0), claims.size(), len, prefix.data(), prefix.size(), &claims_dev_,
+                                      d.data()));
+        ch.set_flushed(d);
+        return true;
+    }
+
+    Fp2 claims_accumulator(const ClaimsView& claims, Fp2 beta, Fp2 gamma) override {
         Fp2 acc = Fp2::zero();
         uint64_t b[2] = {beta.c[0].v, beta.c[1].v}, g[2] = {gamma.c[0].v, gamma.c[1].v};
-        size_t i = 0;
-        std::vector<uint64_t> flat;
-        while (i < claims.size()) {
-            size_t len = claims[i].size(), j = i;
-            flat.clear();
-            while (j < claims.size() && claims[j].size() == len) {
-                for (Fp v : claims[j]) flat.push_back(v.v);
-                j++;
-            }
+        if (claims_dev_) {  // already resident (observe_claims)
             uint64_t out[2];
-            gpu_check(msgpu_claims_accumulator(ctx_, flat.data(), j - i, len, b, g, out));
+            gpu_check(msgpu_claims_accumulate(claims_dev_, b, g, out));
+            drop_claims();
+            return Fp2(Fp(out[0]), Fp(out[1]));
+        }
+        // the C ABI takes claims of one length per call; group consecutive claims of equal length
+        size_t i = 0;
+        while (i < claims.size()) {
+            size_t len = claims.len(i), j = i;
+            while (j < claims.size() && claims.len(j) == len) j++;
+            uint64_t out[2];
+            gpu_check(msgpu_claims_accumulator(ctx_, (const uint64_t*)claims.at(i), j - i, len, b, g, out));
             acc += Fp2(Fp(out[0]), Fp(out[1]));
             i = j;
         }
         return acc;
+    }
+
+    Challenger::BigHash big_hash() override {
+        msgpu_ctx* ctx = ctx_;
+        return [ctx](const u8* data, size_t n) {
+            Digest d;
+            gpu_check(msgpu_blake3_hash(ctx, data, n, d.data()));
+            return d;
+        };
     }
 
     PcsHandlePtr commit_stage2(Fp2 beta, Fp2 gamma, Fp2 acc, std::vector<Fp2>& intermediate, Digest& root) override {
@@ -277,6 +305,7 @@ class GpuBackend : public ProverBackend {
     }
 
     void end_proof() override {
+        drop_claims();
         for (auto* d : trace_dev_) msgpu_free(ctx_, d);
         trace_dev_.clear();
         trace_rows_.clear();
@@ -284,14 +313,25 @@ class GpuBackend : public ProverBackend {
     }
 
   private:
-    uint64_t* upload(const Matrix& m) {
+    // H2D copy + check that every value is canonical (the ABI's precondition, verified on the device)
+    uint64_t* upload(const uint64_t* src, size_t n) {
         void* d = nullptr;
-        size_t bytes = std::max<size_t>(m.values.size() * 8, 8);
-        gpu_check(msgpu_malloc(ctx_, bytes, &d));
-        if (!m.values.empty()) gpu_check(msgpu_memcpy_h2d(ctx_, d, m.values.data(), m.values.size() * 8));
+        gpu_check(msgpu_malloc(ctx_, std::max<size_t>(n * 8, 8), &d));
+        if (n) {
+            int rc = msgpu_upload_canonical(ctx_, d, src, n);
+            if (rc != 0) {
+                msgpu_free(ctx_, d);
+                gpu_check(rc);
+            }
+        }
         return (uint64_t*)d;
     }
+    void drop_claims() {
+        if (claims_dev_) msgpu_claims_free(claims_dev_);
+        claims_dev_ = nullptr;
+    }
     msgpu_ctx* ctx_;
+    msgpu_claims* claims_dev_ = nullptr;
     const SystemShape& shape_;
     std::vector<msgpu_program*> programs_;
     std::vector<uint64_t*> pre_dev_;

@@ -24,9 +24,14 @@ struct ProverBackend {
     // Pcs::commit on host matrices over their natural domains (setup: preprocessed traces)
     virtual PcsHandlePtr commit(const std::vector<const Matrix*>& evals, Digest& root) = 0;
     // stage 1: commit the active traces; the backend keeps them (natural order) for the stage-2 construction
-    virtual PcsHandlePtr commit_stage1(const std::vector<size_t>& circuits, const std::vector<const Matrix*>& traces, Digest& root) = 0;
+    virtual PcsHandlePtr commit_stage1(const std::vector<size_t>& circuits, const std::vector<MatrixView>& traces, Digest& root) = 0;
     // sum over claims of 1 / (beta + fingerprint(gamma, claim))  (src/prover.rs:381-387)
-    virtual Fp2 claims_accumulator(const std::vector<std::vector<Fp>>& claims, Fp2 beta, Fp2 gamma) = 0;
+    virtual Fp2 claims_accumulator(const ClaimsView& claims, Fp2 beta, Fp2 gamma) = 0;
+    // Optional: observe every claim (length-prefixed, src/prover.rs:369-372) into the transcript on the backend's side and
+    // leave the challenger flushed (the next transcript operation is always a sample, src/prover.rs:376). false = not done.
+    virtual bool observe_claims(Challenger&, const ClaimsView&) { return false; }
+    // optional accelerator for the transcript's BLAKE3 over a long input buffer (2^20 claims = 42 MB of observations)
+    virtual Challenger::BigHash big_hash() { return nullptr; }
     // stage 2: lookup values from the kept traces, stage-2 traces, their commitment; `intermediate` = running accumulator
     // after each active circuit (src/prover.rs:391-421, src/lookup.rs:472-555)
     virtual PcsHandlePtr commit_stage2(Fp2 beta, Fp2 gamma, Fp2 acc, std::vector<Fp2>& intermediate, Digest& root) = 0;
@@ -63,6 +68,17 @@ class Prover {
 
     // traces[i] = stage-1 trace of circuit i (height 0 = inactive)
     Proof prove(const std::vector<std::vector<Fp>>& claims, const std::vector<const Matrix*>& traces, ProveTimings* tm = nullptr) {
+        std::vector<Fp> flat;
+        std::vector<u64> offsets(1, 0);
+        for (auto& c : claims) { flat.insert(flat.end(), c.begin(), c.end()); offsets.push_back(flat.size()); }
+        ClaimsView cv;
+        cv.values = flat.data(); cv.offsets = offsets.data(); cv.n = claims.size();
+        std::vector<MatrixView> views;
+        for (auto* m : traces) views.push_back(MatrixView(*m));
+        return prove(cv, views, tm);
+    }
+
+    Proof prove(const ClaimsView& claims, const std::vector<MatrixView>& traces, ProveTimings* tm = nullptr) {
         using clk = std::chrono::steady_clock;
         auto t0 = clk::now();
         auto lap = [&](const char* name) {
@@ -72,17 +88,18 @@ class Prover {
         };
         if (traces.size() != shape_.circuits.size()) throw std::runtime_error("expected one trace per circuit");
         Challenger ch = Challenger::for_config(shape_.commitment, shape_.fri);
+        if (auto bh = be_.big_hash()) ch.set_big_hash(bh, size_t(1) << 16);
         shape_.observe_shape(ch);
         Proof proof;
         std::vector<size_t> active_indices;
         for (size_t i = 0; i < traces.size(); i++) {
-            bool a = traces[i]->height() > 0;
+            bool a = traces[i].height() > 0;
             proof.active.push_back(a);
             ch.observe(Fp(a ? 1 : 0));
             if (a) active_indices.push_back(i);
-            if (a && shape_.circuits[i].has_preprocessed && shape_.circuits[i].preprocessed_height != traces[i]->height())
+            if (a && shape_.circuits[i].has_preprocessed && shape_.circuits[i].preprocessed_height != traces[i].height())
                 throw std::runtime_error("main trace height must equal preprocessed trace height");
-            if (a && traces[i]->width != shape_.circuits[i].main_width) throw std::runtime_error("trace width does not match the circuit");
+            if (a && traces[i].width != shape_.circuits[i].main_width) throw std::runtime_error("trace width does not match the circuit");
         }
         if (active_indices.empty()) throw std::runtime_error("cannot prove with every circuit deactivated (all traces empty)");
         std::vector<int> active_pos(traces.size(), -1);
@@ -90,9 +107,10 @@ class Prover {
 
         // stark/stage1_commit
         std::vector<unsigned> log_degrees;
-        std::vector<const Matrix*> active_traces;
+        std::vector<MatrixView> active_traces;
         for (size_t ci : active_indices) {
-            log_degrees.push_back(log2_strict(traces[ci]->height()));
+            if (traces[ci].height() & (traces[ci].height() - 1)) throw std::runtime_error("trace height must be a power of two");
+            log_degrees.push_back(log2_strict(traces[ci].height()));
             active_traces.push_back(traces[ci]);
         }
         PcsHandlePtr s1 = be_.commit_stage1(active_indices, active_traces, proof.stage_1_trace);
@@ -101,10 +119,11 @@ class Prover {
         ch.observe(proof.stage_1_trace);
         for (unsigned ld : log_degrees) ch.observe_usize(ld);
         ch.observe_usize(claims.size());
-        for (auto& claim : claims) {
-            ch.observe_usize(claim.size());
-            ch.observe_slice(claim.data(), claim.size());
-        }
+        if (!be_.observe_claims(ch, claims))
+            for (size_t i = 0; i < claims.size(); i++) {
+                ch.observe_usize(claims.len(i));
+                ch.observe_slice(claims.at(i), claims.len(i));
+            }
         Fp2 beta = ch.sample_ext();
         ch.observe(beta);
         Fp2 gamma = ch.sample_ext();

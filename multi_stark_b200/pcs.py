@@ -33,9 +33,13 @@ class GpuContext:
         check(self.L.msgpu_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
         self.h = h
         self.device = device
+        self._pinned = []
 
     def close(self):
         if getattr(self, "h", None):
+            for p in self._pinned:
+                self.L.msgpu_host_free(p)
+            self._pinned = []
             self.L.msgpu_ctx_destroy(self.h)
             self.h = None
 
@@ -73,6 +77,39 @@ class GpuContext:
 
     def free(self, ptr):
         check(self.L.msgpu_free(self.h, C.c_void_p(ptr)))
+
+    def pinned_empty(self, shape, dtype=np.uint64):
+        """numpy array over page-locked host memory (msgpu_host_alloc): H2D copies from it run at full PCIe rate.
+        The memory lives until the context is closed."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        check(self.L.msgpu_host_alloc(max(n, 8), C.byref(p)))
+        self._pinned.append(p)
+        buf = (C.c_uint8 * max(n, 8)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def pinned_copy(self, arr):
+        out = self.pinned_empty(arr.shape, arr.dtype)
+        out[...] = arr
+        return out
+
+    def blake3_hash(self, data):
+        """msgpu_blake3_hash: BLAKE3-256 of a host byte string, hashed on the device (the transcript's long flushes)."""
+        buf = np.frombuffer(bytes(data), dtype=np.uint8) if len(data) else np.zeros(1, dtype=np.uint8)
+        out = np.zeros(32, dtype=np.uint8)
+        check(self.L.msgpu_blake3_hash(self.h, buf.ctypes.data_as(C.c_void_p), len(data), out.ctypes.data_as(C.c_void_p)))
+        return bytes(out)
+
+    def upload_canonical(self, arr):
+        """msgpu_upload_canonical: H2D copy that rejects values >= p."""
+        a = np.ascontiguousarray(arr, dtype=np.uint64)
+        p = self.malloc(max(a.nbytes, 8))
+        try:
+            check(self.L.msgpu_upload_canonical(self.h, C.c_void_p(p), a.ctypes.data_as(C.c_void_p), a.size))
+        except Exception:
+            self.free(p)
+            raise
+        return p
 
     def upload(self, arr):
         a = np.ascontiguousarray(arr)

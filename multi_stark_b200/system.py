@@ -172,6 +172,11 @@ class Prover:
         claims: sequence of 1-D uint64 arrays. Returns `Proof::to_bytes`."""
         mats = [np.ascontiguousarray(t, dtype=np.uint64) for t in traces]
         n = len(mats)
+        if n != self.system.num_circuits:
+            raise _ffi.MsgpuError(-1, "expected one trace per circuit")
+        for m, info in zip(mats, self.system.circuits):
+            if m.ndim != 2 or (m.shape[0] and m.shape[1] != info["main_width"]):
+                raise _ffi.MsgpuError(-1, "trace width does not match the circuit")
         ptrs = (C.c_void_p * n)(*[m.ctypes.data if m.size else None for m in mats])
         hs = (C.c_uint64 * n)(*[m.shape[0] for m in mats])
         if isinstance(claims, np.ndarray) and claims.ndim == 2:

@@ -245,17 +245,20 @@ class CpuBackend : public ProverBackend {
     PcsHandlePtr commit(const std::vector<const Matrix*>& evals, Digest& root) override {
         return cpu_commit(evals, (unsigned)shape_.log_blowup(), root);
     }
-    PcsHandlePtr commit_stage1(const std::vector<size_t>& circuits, const std::vector<const Matrix*>& traces, Digest& root) override {
+    PcsHandlePtr commit_stage1(const std::vector<size_t>& circuits, const std::vector<MatrixView>& traces, Digest& root) override {
         active_ = circuits;
-        traces_ = traces;
-        return cpu_commit(traces, (unsigned)shape_.log_blowup(), root);
+        traces_.clear();
+        for (auto& v : traces) traces_.push_back(v.to_matrix());
+        std::vector<const Matrix*> ptrs;
+        for (auto& m : traces_) ptrs.push_back(&m);
+        return cpu_commit(ptrs, (unsigned)shape_.log_blowup(), root);
     }
-    Fp2 claims_accumulator(const std::vector<std::vector<Fp>>& claims, Fp2 beta, Fp2 gamma) override {
+    Fp2 claims_accumulator(const ClaimsView& claims, Fp2 beta, Fp2 gamma) override {
         // src/prover.rs:381-387 (one inversion per claim; the sum is order-independent in exact arithmetic)
         std::vector<Fp2> msgs(claims.size()), inv(claims.size());
         long long n = (long long)claims.size();
 #pragma omp parallel for schedule(static)
-        for (long long i = 0; i < n; i++) msgs[i] = beta + fingerprint(gamma, claims[i].data(), claims[i].size());
+        for (long long i = 0; i < n; i++) msgs[i] = beta + fingerprint(gamma, claims.at((size_t)i), claims.len((size_t)i));
         const long long CH = 4096;
         long long nch = (n + CH - 1) / CH;
 #pragma omp parallel for schedule(static)
@@ -266,7 +269,7 @@ class CpuBackend : public ProverBackend {
     }
     PcsHandlePtr commit_stage2(Fp2 beta, Fp2 gamma, Fp2 acc, std::vector<Fp2>& intermediate, Digest& root) override {
         std::vector<LookupValues> lvs;
-        for (size_t p = 0; p < active_.size(); p++) lvs.push_back(compute_lookup_values(shape_.circuits[active_[p]], *traces_[p]));
+        for (size_t p = 0; p < active_.size(); p++) lvs.push_back(compute_lookup_values(shape_.circuits[active_[p]], traces_[p]));
         std::vector<const LookupValues*> ptrs;
         for (auto& l : lvs) ptrs.push_back(&l);
         std::vector<Matrix> s2;
@@ -303,7 +306,7 @@ class CpuBackend : public ProverBackend {
   private:
     const SystemShape& shape_;
     std::vector<size_t> active_;
-    std::vector<const Matrix*> traces_;
+    std::vector<Matrix> traces_;
 };
 
 }  // namespace orc

@@ -134,3 +134,25 @@ def test_commit_full_size_root_of_roots(gpu):
             j >>= 1
         assert d == bytes(root)
     pd.free()
+
+
+@pytest.mark.parametrize("n", [0, 1, 63, 64, 65, 1023, 1024, 1025, 2047, 2048, 2049, 3072, 4097, 5 * 1024, 7 * 1024 + 3,
+                               (1 << 16) + 1, (1 << 20) + 777, 3 * (1 << 20)])
+def test_blake3_long_hash_matches_official(gpu, n):
+    """msgpu_blake3_hash (the transcript's long flushes) against the official BLAKE3 implementation, across chunk
+    and subtree boundaries (odd chunk counts exercise the left-heavy tree)."""
+    ms, ctx = gpu
+    rng = np.random.default_rng(n)
+    data = rng.integers(0, 256, size=n, dtype=np.uint8).tobytes()
+    assert ctx.blake3_hash(data) == pyb3.blake3(data).digest()
+
+
+def test_upload_canonical_rejects_out_of_range(gpu):
+    ms, ctx = gpu
+    good = np.array([0, 1, ms.P - 1], dtype=np.uint64)
+    ctx.free(ctx.upload_canonical(good))
+    for bad in (ms.P, 2**64 - 1):
+        a = np.zeros(5000, dtype=np.uint64)
+        a[4321] = bad
+        with pytest.raises(ms.MsgpuError):
+            ctx.upload_canonical(a)
