@@ -184,6 +184,63 @@ def sample_stages(stages, log_sample):
     return [[m if m.shape[0] <= n else m[:n] for m in st] for st in stages]
 
 
+
+def prove_params(args):
+    """BASELINE configs[0]/[1]: log_blowup as given, 100 queries, final poly len 1, binary folding, PoW 0/0 (deterministic)."""
+    return dict(log_blowup=args.log_blowup, log_final_poly_len=0, max_log_arity=1, num_queries=100, commit_pow_bits=0,
+                query_pow_bits=0)
+
+
+def cpu_prove_time(args, log_rows, reps=1):
+    """The oracle's CPU prover (restatement of src/prover.rs:289-603 over restated Plonky3 semantics) on all host cores."""
+    import multi_stark_b200.system as mss
+    orc, L = load_oracle()
+    S = orc.OracleSystem(L, "u32_add", **prove_params(args))
+    byte, add, claims = mss.u32_add_workload(1 << log_rows)
+    best, stages = None, None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        proof, ms_stages = S.prove([byte, add], claims)
+        dt = (time.perf_counter() - t0) * 1e3
+        if best is None or dt < best:
+            best, stages = dt, ms_stages
+    ok = S.verify(claims, proof)
+    S.close()
+    names = ["stark/stage1_commit", "stark/claims", "stark/stage2_commit", "stark/quotient", "stark/fri_open", "stark/prove"]
+    return {"rows": 1 << log_rows, "ms": best, "stages_ms": dict(zip(names, stages)), "cores": int(L.orc_num_threads()),
+            "kind": "port", "verified": ok == "Ok", "proof_bytes": len(proof)}
+
+
+def gpu_prove_leg(args, ms, ctx, steps, warmup, verify):
+    """prove() end to end through the public API: HOST (pinned) traces and claims in, Proof::to_bytes out."""
+    system = ms.System("u32_add", **prove_params(args))
+    prover = ms.Prover(ctx, system)  # System::new: programs + preprocessed commitment (setup, untimed like Criterion's setup)
+    byte, add, claims = ms.u32_add_workload(1 << args.log_rows)
+    byte, add, claims = ctx.pinned_copy(byte), ctx.pinned_copy(add), ctx.pinned_copy(claims)
+    for _ in range(warmup):
+        proof = prover.prove([byte, add], claims)
+    times, stage_acc = [], {}
+    l0 = ctx.launches
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        proof = prover.prove([byte, add], claims)
+        times.append((time.perf_counter() - t0) * 1e3)
+        for k, v in prover.last_stage_ms.items():
+            stage_acc.setdefault(k, []).append(v)
+    launches = (ctx.launches - l0) // max(steps, 1)
+    out = {"rows": 1 << args.log_rows, "ms": float(np.median(times)), "ms_min": float(np.min(times)), "steps": steps,
+           "stages_ms": {k: float(np.median(v)) for k, v in stage_acc.items()}, "proof_bytes": len(proof),
+           "h2d_bytes": int(byte.nbytes + add.nbytes + claims.nbytes), "gpu_launches": int(launches),
+           "timing": "host wall clock around the call (host buffers in, proof bytes out)"}
+    if verify:
+        orc, L = load_oracle()
+        S = orc.OracleSystem(L, "u32_add", **prove_params(args))
+        out["verified"] = S.verify(claims, proof) == "Ok"
+        S.close()
+    prover.close()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -202,6 +259,7 @@ def run_reference(args):
     ms = 1e3 * float(np.mean(times))
     value = elems / (ms / 1e3) / 1e9
     desc = "first 2^%d of 2^%d rows of each trace matrix, %d steps" % (log_sample, args.log_rows, args.steps)
+    prove = None if args.no_prove else cpu_prove_time(args, min(args.log_rows, args.cpu_prove_log_rows))
     print(json.dumps({
         "impl": "reference", "metric": "lde_merkle_gelem_per_s", "value": value, "unit": "Gelem/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -211,6 +269,7 @@ def run_reference(args):
                          "note": "C++/OpenMP restatement of the reference path (oracle/); the Rust reference cannot be "
                                  "built here (no cargo, Plonky3 un-vendored)"},
         "e2e": {"value": value, "unit": "Gelem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "prove": prove,
     }))
 
 
@@ -225,13 +284,15 @@ def workload_config(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-rows", type=int, default=20)
     ap.add_argument("--log-blowup", type=int, default=1)
     ap.add_argument("--cpu-log-rows", type=int, default=18, help="rows of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-prove-log-rows", type=int, default=16, help="rows of the CPU prove() baseline")
+    ap.add_argument("--no-prove", action="store_true", help="skip the prove() leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -314,9 +375,15 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    t_s = time.perf_counter()
+    while len(sampler.lines) < 1 and time.perf_counter() - t_s < 3.0:  # nvidia-smi needs ~0.5 s to print its first sample
+        step_resident()
     ms_res, launches, prof, _ = timed(step_resident, args.steps, profile=True)
-    clocks = sampler.stop()
     ms_e2e, _, _, _ = timed(step_e2e, args.steps)
+    t_s = time.perf_counter()
+    while len(sampler.lines) < 8 and time.perf_counter() - t_s < 2.0:  # same kernels, untimed: enough samples under load
+        step_resident()
+    clocks = sampler.stop()
 
     elems = committed_elements(stages, B)
     ms_step = ms_res / args.steps
@@ -363,6 +430,19 @@ def main():
             pd.free()
             assert bytes(got) == want, "GPU root differs from the oracle"
 
+    prove = None
+    if not args.no_prove:
+        barrier()
+        prove = gpu_prove_leg(args, ms, ctx, steps=max(3, min(args.steps, 10)), warmup=2, verify=(rank == 0))
+        if world > 1:
+            t = torch.tensor([prove["ms"]], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            prove["ms_max_over_ranks"] = float(t.item())
+            prove["proofs_per_s_all_ranks"] = world * 1e3 / float(t.item())
+        if cpu is not None:
+            prove["cpu"] = cpu_prove_time(args, min(args.log_rows, args.cpu_prove_log_rows))
+        barrier()
+
     if rank == 0:
         print(json.dumps({
             "metric": "lde_merkle_gelem_per_s", "value": value, "unit": "Gelem/s", "n_gpus": world, "steps": args.steps,
@@ -370,7 +450,7 @@ def main():
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": "Gelem/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "prove": prove,
         }))
     ctx.close()
     if world > 1:

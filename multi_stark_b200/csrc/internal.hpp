@@ -122,6 +122,8 @@ void b3_hash_rows(Ctx& c, const std::vector<MatRef>& mats, uint8_t* digests);
 // next[i] = H(prev[2i] || prev[2i+1]), optionally followed by H(that || inject[i])
 void b3_compress_layer(Ctx& c, const uint8_t* prev, const uint8_t* inject, uint8_t* next, u64 next_len);
 
+// `levels` node layers in one launch (each CTA reduces 2^levels adjacent digests through shared memory)
+void b3_merkle_subtrees(Ctx& c, const uint8_t* in, u64 len, u32 levels, uint8_t* const* out, const uint8_t* const* inject);
 // BLAKE3 of one long (> 1024 bytes) device-resident byte string; out_dev receives 32 bytes
 void b3_hash_long(Ctx& c, const uint8_t* data_dev, u64 len, uint8_t* out_dev);
 // sets *flag_dev |= 1 if any v[i] >= p

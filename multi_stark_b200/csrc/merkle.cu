@@ -144,6 +144,55 @@ __global__ void __launch_bounds__(256) k_compress_layer(const uint4* prev, const
     next[2 * i + 1] = make_uint4(d[4], d[5], d[6], d[7]);
 }
 
+// Several node layers per launch: a CTA owns `chunk` adjacent digests of the input layer and reduces them to one,
+// level by level through shared memory, writing every intermediate layer to its place in the tree (the prover data
+// keeps all layers for the opening proofs). Level l output i = H(in[2i] || in[2i+1]), then H(that || inject_l[i]) when
+// matrices of that height are injected.
+constexpr int kMaxFusedLevels = 12;
+struct SubtreeParams {
+    const uint4* in;                        // input layer (global)
+    uint4* out[kMaxFusedLevels];            // output layers 1..levels (global, whole-layer base pointers)
+    const uint4* inject[kMaxFusedLevels];   // injected leaf digests per output layer or null
+    u32 levels;                             // chunk = 1 << levels
+};
+__device__ __forceinline__ void ld_digest(const uint4* p, u32 d[8]) {
+    uint4 a = p[0], b = p[1];
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
+__device__ __forceinline__ void st_digest(uint4* p, const u32 d[8]) {
+    p[0] = make_uint4(d[0], d[1], d[2], d[3]);
+    p[1] = make_uint4(d[4], d[5], d[6], d[7]);
+}
+__global__ void __launch_bounds__(256) k_merkle_subtree(SubtreeParams p) {
+    extern __shared__ uint4 sm_t[];
+    const u32 chunk = 1u << p.levels;
+    uint4* bufA = sm_t;                    // chunk/2 digests
+    uint4* bufB = sm_t + chunk;            // chunk/4 digests (2 uint4 per digest)
+    const u64 cta = blockIdx.x;
+    for (u32 l = 0; l < p.levels; l++) {
+        const u32 nodes = chunk >> (l + 1);
+        const uint4* src = l == 0 ? p.in + cta * chunk * 2 : ((l & 1) ? bufA : bufB);
+        uint4* dst = (l & 1) ? bufB : bufA;
+        const u64 gbase = cta * nodes;
+        for (u32 i = threadIdx.x; i < nodes; i += blockDim.x) {
+            u32 a[8], b[8], d[8];
+            ld_digest(src + 4 * i, a);
+            ld_digest(src + 4 * i + 2, b);
+            b3::hash_pair(a, b, d);
+            if (p.inject[l]) {
+                u32 x[8], d2[8];
+                ld_digest(p.inject[l] + 2 * (gbase + i), x);
+                b3::hash_pair(d, x, d2);
+#pragma unroll
+                for (int k = 0; k < 8; k++) d[k] = d2[k];
+            }
+            st_digest(dst + 2 * i, d);
+            st_digest(p.out[l] + 2 * (gbase + i), d);
+        }
+        __syncthreads();
+    }
+}
+
 // raw compression for the known-answer test
 __global__ void k_compress_raw(const u32* st, const u32* msg, u32* out) {
     u32 s[16], m[16], o[16];
@@ -301,6 +350,30 @@ void b3_compress_layer(Ctx& c, const uint8_t* prev, const uint8_t* inject, uint8
         KLaunch kl(c, "k_compress_layer");
         k_compress_layer<<<(unsigned)blocks, 256, 0, c.stream>>>((const uint4*)prev, (const uint4*)inject, (uint4*)next,
                                                                  next_len);
+    }
+    MSG_CUDA(cudaGetLastError());
+}
+
+// Reduces the layer `in` (len digests) by `levels` levels. out[l] / inject[l]: output layer l+1 and its injected digests.
+void b3_merkle_subtrees(Ctx& c, const uint8_t* in, u64 len, u32 levels, uint8_t* const* out, const uint8_t* const* inject) {
+    MSG_REQUIRE(levels >= 1 && levels <= (u32)kMaxFusedLevels && (len >> levels) >= 1, "merkle: bad fused level count");
+    SubtreeParams p{};
+    p.in = (const uint4*)in;
+    p.levels = levels;
+    for (u32 l = 0; l < levels; l++) {
+        p.out[l] = (uint4*)out[l];
+        p.inject[l] = (const uint4*)inject[l];
+    }
+    size_t smem = ((size_t)1 << levels) * 24;  // chunk/2 + chunk/4 digests
+    static bool attr = false;
+    if (!attr) {
+        MSG_CUDA(cudaFuncSetAttribute(k_merkle_subtree, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 << kMaxFusedLevels));
+        attr = true;
+    }
+    u32 threads = (u32)std::min<u64>(256, std::max<u64>(32, (1ull << levels) / 2));
+    {
+        KLaunch kl(c, "k_merkle_subtree");
+        k_merkle_subtree<<<(unsigned)(len >> levels), threads, smem, c.stream>>>(p);
     }
     MSG_CUDA(cudaGetLastError());
 }

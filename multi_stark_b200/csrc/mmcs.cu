@@ -39,28 +39,37 @@ void mmcs_build(Ctx& c, msgpu_pdata* pd) {
         group.push_back(MatRef{m.ptr, m.height, m.width});
     }
     b3_hash_rows(c, group, pd->digests);
-    uint8_t* inj = nullptr;
-    u64 inj_cap = 0;
-    for (size_t l = 1; l < pd->layer_len.size(); l++) {
+    // leaf digests of the shorter matrices, per layer they are injected into
+    size_t n_layers = pd->layer_len.size();
+    std::vector<uint8_t*> inj(n_layers, nullptr);
+    for (size_t l = 1; l < n_layers; l++) {
         u64 next_len = pd->layer_len[l];
         group.clear();
         while (pos < order.size() && pd->mats[order[pos]].height == next_len) {
             auto& m = pd->mats[order[pos++]];
             group.push_back(MatRef{m.ptr, m.height, m.width});
         }
-        const uint8_t* injp = nullptr;
         if (!group.empty()) {
-            if (inj_cap < next_len) {
-                if (inj) c.free(inj);
-                inj = (uint8_t*)c.alloc(next_len * 32);
-                inj_cap = next_len;
-            }
-            b3_hash_rows(c, group, inj);
-            injp = inj;
+            inj[l] = (uint8_t*)c.alloc(next_len * 32);
+            b3_hash_rows(c, group, inj[l]);
         }
-        b3_compress_layer(c, pd->digests + pd->layer_off[l - 1] * 32, injp, pd->digests + pd->layer_off[l] * 32, next_len);
     }
-    if (inj) c.free(inj);
+    // node layers: 10 per launch while the layer is large, then everything that is left in one CTA
+    size_t l = 0;
+    while (l + 1 < n_layers) {
+        u64 len = pd->layer_len[l];
+        u32 levels = len > 4096 ? 10 : ilog2(len);
+        uint8_t* outs[16];
+        const uint8_t* injs[16];
+        for (u32 k = 0; k < levels; k++) {
+            outs[k] = pd->digests + pd->layer_off[l + 1 + k] * 32;
+            injs[k] = inj[l + 1 + k];
+        }
+        b3_merkle_subtrees(c, pd->digests + pd->layer_off[l] * 32, len, levels, outs, injs);
+        l += levels;
+    }
+    for (auto* p : inj)
+        if (p) c.free(p);
     MSG_REQUIRE(pos == order.size(), "commit: internal error, matrix not placed in the tree");
     MSG_CUDA(cudaMemcpyAsync(pd->root, pd->digests + pd->layer_off.back() * 32, 32, cudaMemcpyDeviceToHost, c.stream));
     c.sync();
