@@ -122,6 +122,50 @@ __device__ __forceinline__ u64 pow(u64 a, u64 e) {
 __device__ __forceinline__ u64 inv(u64 a) { return pow(a, GLD_P - 2); }
 __device__ __forceinline__ u64 halve(u64 a) { return (a & 1) ? (a >> 1) + (GLD_P >> 1) + 1 : a >> 1; }
 
+// ---- lean canonical arithmetic for the NTT butterflies (canonical in, canonical out) ---------------------------
+// Instruction counts (sm_100a SASS): add 7, sub 5, mul 26 (4 IMAD.WIDE + carries + reduction), against 14 / 5 / 34 of
+// the general-purpose forms above.
+namespace gf {
+__device__ __forceinline__ u64 sub(u64 a, u64 b) { return sub_lazy(a, b); }
+// a + b = a - (p - b): one borrow fix-up makes the result canonical (p - b is in (0, p], which sub_lazy tolerates)
+__device__ __forceinline__ u64 add(u64 a, u64 b) { return sub_lazy(a, GLD_P - b); }
+// 128-bit (hi:lo) -> canonical. 2^64 = 2^32 - 1 =: eps, 2^96 = -1 (mod p).
+__device__ __forceinline__ u64 reduce128(u64 lo, u64 hi) {
+    u32 l0 = (u32)lo, l1 = (u32)(lo >> 32), h0 = (u32)hi, h1 = (u32)(hi >> 32);
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 t0, t1, m, k, z, r0, r1;\n\t"
+        ".reg .u64 rr;\n\t"
+        "sub.cc.u32 t0, %1, %4;\n\t"          // t = lo - h1 (- eps on borrow)
+        "subc.cc.u32 t1, %2, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 t0, t0, m;\n\t"
+        "subc.u32 t1, t1, 0;\n\t"
+        "mad.lo.cc.u32 r0, %3, 0xffffffff, t0;\n\t"   // r = t + h0 * eps (+ eps on carry)
+        "madc.hi.cc.u32 r1, %3, 0xffffffff, t1;\n\t"
+        "addc.u32 k, 0, 0;\n\t"
+        "mov.b64 rr, {r0, r1};\n\t"
+        "mad.wide.u32 rr, k, 0xffffffff, rr;\n\t"
+        "mov.b64 {r0, r1}, rr;\n\t"
+        "add.cc.u32 z, r0, 0xffffffff;\n\t"   // r >= p  <=>  r + eps carries; then r - p = r + eps (mod 2^64)
+        "addc.cc.u32 z, r1, 0;\n\t"
+        "addc.u32 k, 0, 0;\n\t"
+        "mad.wide.u32 %0, k, 0xffffffff, rr;\n\t"
+        "}"
+        : "=l"(r)
+        : "r"(l0), "r"(l1), "r"(h0), "r"(h1));
+    return r;
+}
+__device__ __forceinline__ u64 mul(u64 a, u64 b) {
+    unsigned __int128 pr = (unsigned __int128)a * b;
+    return reduce128((u64)pr, (u64)(pr >> 64));
+}
+// 2^e mod p for 0 <= e < 96 (folds to a constant when e is known at compile time)
+__host__ __device__ constexpr u64 pow2_mod_p(int e) {
+    return e < 64 ? (1ull << e) : ((1ull << (e - 32)) - (1ull << (e - 64)));  // 2^64 = 2^32 - 1
+}
+}  // namespace gf
+
 // ---- extension field F_p[X]/(X^2 - 7) -------------------------------------------------------
 struct e2 {
     u64 a, b;  // a + b X

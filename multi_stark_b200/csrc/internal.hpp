@@ -45,7 +45,8 @@ struct Ctx {
     bool own_stream = false;
     unsigned long long launches = 0;  // kernels of this library launched so far
     int sm_count = 148;
-    u64* tw_small[2] = {nullptr, nullptr};  // w_1024^{i} / w_1024^{-i}, i < 512
+    u64* tw_full[2] = {nullptr, nullptr};  // w_1024^{i} / w_1024^{-i}, i < 1024
+    std::map<std::tuple<u32, u32, u32, u64>, u64*> ntt_tables;  // per-size inter-pass twiddles / coset scales (ntt.cu)
     std::map<std::tuple<u64, u64, u32>, DevPow> pow_cache;
     std::map<std::tuple<u32, u32, u64>, gl::PowTable*> coset_cache;  // (log_n, added_bits, shift) -> device array [B]
     std::vector<void*> owned;  // table allocations freed with the context

@@ -5,113 +5,199 @@
 // .bit_reverse_rows()` inside `TwoAdicFriPcs::commit` (src/prover.rs:350,419; src/system.rs:193).
 //
 // Data layout: row-major n x w matrices of canonical u64, exactly the reference's RowMajorMatrix.
-// A transform of size n = 2^L over the rows is split into passes of at most 10 bits. Each pass
-// stages a tile of T (= 2^tb) points x up to 16 adjacent u64 (128 B of one row, or whole rows of
-// several adjacent blocks) in shared memory, runs the tb butterfly stages as register-resident
-// radix-16/8/4/2 rounds, applies the inter-pass twiddle and writes back:
+// A transform of size n = 2^L over the rows is split into passes of at most 10 bits. A pass works on
+// tiles of T = 2^tb points x 16 adjacent u64 (128-byte row segments, so every global access is a full
+// coalesced line) and runs the tb butterfly stages as radix-16 / radix-16 / radix-4 rounds:
+//
+//   round = one register-resident size-R DFT per thread whose internal twiddles are all POWERS OF TWO
+//           (p3's two_adic_generator(k) is 2^96, 2^48, 2^120, 2^156 for k = 1..4, and 2^96 = -1), i.e.
+//           multiplications by compile-time constants with zero limbs and free sign flips, followed by ONE
+//           general multiplication per element by w_T^{off * r} (Cooley-Tukey / Gentleman-Sande with the
+//           twiddles pulled out of the butterflies): 15 general multiplications per 16 elements instead of 32.
+//   The first round loads straight from global memory into registers and the last round stores straight
+//   from registers to global memory (with the inter-pass twiddle folded in), so a tile touches shared
+//   memory only between rounds. Thread -> (column, row group) is fixed for the whole kernel: no integer
+//   division in any loop.
 //
 //  * k_ntt_strided: decimation-in-frequency pass over bits [lo, lo+tb) of the row index, natural
 //    order in, bit-reversed order out, in place (the 4-step decomposition with the transpose absorbed
 //    into index arithmetic). A chain of these is a DFT whose output is stored bit-reversed, which is
 //    the storage the reference gets from `dft_batch(..).bit_reverse_rows()`.
 //  * k_ntt_block: first pass of the coset evaluation. It reads the bit-reversed coefficients that the
-//    inverse transform left behind (contiguous blocks, fully coalesced), multiplies row j by
-//    shift_s^j / n, runs a decimation-in-time tile (bit-reversed in, natural out) and scatters whole
-//    128-byte row segments to their bit-reversed block. The zero-padded forward transform of size
-//    n*B is never materialised: output block rev(s) of n rows is the size-n coset transform with
-//    shift * w_{nB}^s, so the LDE reads n rows and writes n*B.
+//    inverse transform left behind (contiguous blocks), multiplies row j by shift_s^j / n, runs a
+//    decimation-in-time tile (bit-reversed in, natural out) and scatters whole 128-byte row segments to
+//    their bit-reversed block. The zero-padded forward transform of size n*B is never materialised: output
+//    block rev(s) of n rows is the size-n coset transform with shift * w_{nB}^s,
+//    so the LDE reads n rows and writes n*B.
+//  Inter-pass twiddles and coset scales come from per-size tables built once per context (n entries each,
+//  L2-resident while a pass streams): one load + one multiplication per element.
 #include "internal.hpp"
 
 namespace msg {
 
-constexpr int kPitch = 17;        // u64 per tile row (16 data + 1 pad: conflict-free column writes)
-constexpr int kMaxXt = 16;        // tile columns
+constexpr int kPitch = 17;        // u64 per tile row (16 data + 1 pad)
+constexpr int kXt = 16;           // tile columns
 constexpr int kMaxLogT = 10;      // tile points
-constexpr int kTwSmallLog = 10;
+constexpr int kTwLog = 10;        // w_1024 table, full period
 
-// ------------------------------------------------------------------------------------------------
-// Register radix rounds over a shared-memory tile [T][kPitch].
-// ------------------------------------------------------------------------------------------------
-template <int RB, bool DIT>
-__device__ __forceinline__ void radix_round(u64* tile, const u64* twl, u32 log_t, u32 s0, u32 ncols, u32 tid,
-                                            u32 nthr) {
+using gl::gf::add;
+using gl::gf::mul;
+using gl::gf::sub;
+
+// two_adic_generator(k) = 2^root_exp(k) for k <= 4 (checked against the host field in tests); inverse = 2^(192 - e)
+__host__ __device__ constexpr int root_exp(int logr, bool inv) {
+    int e = logr == 1 ? 96 : logr == 2 ? 48 : logr == 3 ? 120 : logr == 4 ? 156 : 0;
+    return inv ? (192 - e) % 192 : e;
+}
+
+// (u - x) * 2^e, e in [0, 192) known at compile time after unrolling
+__device__ __forceinline__ u64 sub_mul_pow2(u64 u, u64 x, int e) {
+    if (e == 0) return sub(u, x);
+    if (e == 96) return sub(x, u);
+    if (e < 96) return mul(sub(u, x), gl::gf::pow2_mod_p(e));
+    return mul(sub(x, u), gl::gf::pow2_mod_p(e - 96));
+}
+
+// size-2^RB DFT in registers, natural order in, bit-reversed order out (decimation in frequency)
+template <int RB, bool INV>
+__device__ __forceinline__ void dif_regs(u64 (&v)[1 << RB]) {
     constexpr int R = 1 << RB;
-    const u32 stride = 1u << s0;
-    const u32 items = ((1u << log_t) >> RB) * ncols;
-    for (u32 item = tid; item < items; item += nthr) {
-        u32 q = item % ncols, g = item / ncols;
-        u32 off = g & (stride - 1), blk = g >> s0;
-        u32 row0 = (blk << (s0 + RB)) + off;
-        u64* base = tile + (size_t)row0 * kPitch + q;
-        u64 v[R];
 #pragma unroll
-        for (int m = 0; m < R; m++) v[m] = base[(size_t)(m << s0) * kPitch];
+    for (int s = 0; s < RB; s++) {
+        const int half = R >> (s + 1);
+        const int lg = RB - s;
 #pragma unroll
-        for (int s = 0; s < RB; s++) {
-            const int lb = DIT ? s : RB - 1 - s;
-            const int half = 1 << lb;
-            const u32 shift = log_t - 1 - s0 - lb;
+        for (int blk = 0; blk < R; blk += 2 * half) {
 #pragma unroll
             for (int el = 0; el < half; el++) {
-                u64 t = twl[(((u32)el << s0) + off) << shift];
+                const int i = blk + el, j = i + half;
+                const int e = (root_exp(lg, INV) * el) % 192;
+                u64 u = v[i], x = v[j];
+                v[i] = add(u, x);
+                v[j] = sub_mul_pow2(u, x, e);
+            }
+        }
+    }
+}
+// bit-reversed order in, natural order out (decimation in time)
+template <int RB, bool INV>
+__device__ __forceinline__ void dit_regs(u64 (&v)[1 << RB]) {
+    constexpr int R = 1 << RB;
 #pragma unroll
-                for (int m0 = 0; m0 < R; m0 += 2 * half) {
-                    int i = m0 + el, j = i + half;
-                    if (DIT) {
-                        u64 x = gl::mul(v[j], t), u = v[i];
-                        v[i] = gl::add(u, x);
-                        v[j] = gl::sub(u, x);
-                    } else {
-                        u64 u = v[i], x = v[j];
-                        v[i] = gl::add(u, x);
-                        v[j] = gl::mul(gl::sub(u, x), t);
-                    }
+    for (int s = 0; s < RB; s++) {
+        const int half = 1 << s;
+        const int lg = s + 1;
+#pragma unroll
+        for (int blk = 0; blk < R; blk += 2 * half) {
+#pragma unroll
+            for (int el = 0; el < half; el++) {
+                const int i = blk + el, j = i + half;
+                const int e = (root_exp(lg, INV) * el) % 192;
+                u64 u = v[i], x = v[j];
+                if (e == 0) {
+                    v[i] = add(u, x);
+                    v[j] = sub(u, x);
+                } else if (e == 96) {
+                    v[i] = sub(u, x);
+                    v[j] = add(u, x);
+                } else if (e < 96) {
+                    u64 y = mul(x, gl::gf::pow2_mod_p(e));
+                    v[i] = add(u, y);
+                    v[j] = sub(u, y);
+                } else {
+                    u64 y = mul(x, gl::gf::pow2_mod_p(e - 96));
+                    v[i] = sub(u, y);
+                    v[j] = add(u, y);
                 }
             }
         }
+    }
+}
+
+__host__ __device__ constexpr int rev_small(int x, int bits) {
+    int r = 0;
+    for (int i = 0; i < bits; i++) r |= ((x >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+
+// Round sizes of a tb-bit tile: 4, 4, rest.
+__host__ __device__ constexpr int round_bits(int tb, int k) {
+    int r1 = tb < 4 ? tb : 4, rem = tb - r1;
+    int r2 = rem < 4 ? rem : 4;
+    return k == 0 ? r1 : k == 1 ? r2 : rem - r2;
+}
+
+// One round of RB bits at bit offset S0 of a TB-bit tile. Slot m of item (blk, off) is tile row
+// (blk << (S0 + RB)) + off + (m << S0). DIF: DFT then slot m *= w^{off * rev(m)}; DIT: the mirror image.
+// ld(row) / st(row, value) move one element of this thread's column (registers <-> global or shared memory).
+template <int TB, int RB, int S0, bool INV, bool DIT, class Ld, class St>
+__device__ __forceinline__ void tile_round(const u64* __restrict__ tw, u32 trow, u32 nrows_thr, Ld ld, St st) {
+    constexpr int R = 1 << RB;
+    constexpr u32 items = 1u << (TB - RB);
+    for (u32 g = trow; g < items; g += nrows_thr) {
+        const u32 off = g & ((1u << S0) - 1), blk = g >> S0;
+        const u32 row0 = (blk << (S0 + RB)) + off;
+        u64 v[R];
 #pragma unroll
-        for (int m = 0; m < R; m++) base[(size_t)(m << s0) * kPitch] = v[m];
+        for (int m = 0; m < R; m++) v[m] = ld(row0 + ((u32)m << S0));
+        if (DIT) {
+            if (S0 > 0) {
+#pragma unroll
+                for (int m = 1; m < R; m++)
+                    v[m] = mul(v[m], __ldg(tw + ((off * (u32)rev_small(m, RB)) << (kTwLog - S0 - RB))));
+            }
+            dit_regs<RB, INV>(v);
+        } else {
+            dif_regs<RB, INV>(v);
+            if (S0 > 0) {
+#pragma unroll
+                for (int m = 1; m < R; m++)
+                    v[m] = mul(v[m], __ldg(tw + ((off * (u32)rev_small(m, RB)) << (kTwLog - S0 - RB))));
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < R; m++) st(row0 + ((u32)m << S0), v[m]);
     }
 }
 
-template <bool DIT>
-__device__ __forceinline__ void radix_dispatch(int rb, u64* tile, const u64* twl, u32 log_t, u32 s0, u32 ncols,
-                                               u32 tid, u32 nthr) {
-    switch (rb) {
-        case 4: radix_round<4, DIT>(tile, twl, log_t, s0, ncols, tid, nthr); break;
-        case 3: radix_round<3, DIT>(tile, twl, log_t, s0, ncols, tid, nthr); break;
-        case 2: radix_round<2, DIT>(tile, twl, log_t, s0, ncols, tid, nthr); break;
-        default: radix_round<1, DIT>(tile, twl, log_t, s0, ncols, tid, nthr); break;
+// All rounds of a TB-bit tile for this thread's column q. gld(row) reads the input element of tile row `row`,
+// gst(row, v) consumes the output element. DIF: natural rows in, bit-reversed rows out. DIT: the converse.
+template <int TB, bool INV, bool DIT, class GLd, class GSt>
+__device__ __forceinline__ void tile_pass(u64* tile, const u64* __restrict__ tw, u32 q, u32 trow, u32 nrows_thr, GLd gld, GSt gst) {
+    constexpr int B0 = round_bits(TB, 0), B1 = round_bits(TB, 1), B2 = round_bits(TB, 2);
+    auto sld = [&](u32 row) { return tile[(size_t)row * kPitch + q]; };
+    auto sst = [&](u32 row, u64 v) { tile[(size_t)row * kPitch + q] = v; };
+    if constexpr (!DIT) {
+        // round 0 works on the top bits
+        if constexpr (B1 == 0) {
+            tile_round<TB, B0, TB - B0, INV, false>(tw, trow, nrows_thr, gld, gst);
+        } else if constexpr (B2 == 0) {
+            tile_round<TB, B0, TB - B0, INV, false>(tw, trow, nrows_thr, gld, sst);
+            __syncthreads();
+            tile_round<TB, B1, 0, INV, false>(tw, trow, nrows_thr, sld, gst);
+        } else {
+            tile_round<TB, B0, TB - B0, INV, false>(tw, trow, nrows_thr, gld, sst);
+            __syncthreads();
+            tile_round<TB, B1, B2, INV, false>(tw, trow, nrows_thr, sld, sst);
+            __syncthreads();
+            tile_round<TB, B2, 0, INV, false>(tw, trow, nrows_thr, sld, gst);
+        }
+    } else {
+        // round 0 works on the low bits
+        if constexpr (B1 == 0) {
+            tile_round<TB, B0, 0, INV, true>(tw, trow, nrows_thr, gld, gst);
+        } else if constexpr (B2 == 0) {
+            tile_round<TB, B0, 0, INV, true>(tw, trow, nrows_thr, gld, sst);
+            __syncthreads();
+            tile_round<TB, B1, B0, INV, true>(tw, trow, nrows_thr, sld, gst);
+        } else {
+            tile_round<TB, B0, 0, INV, true>(tw, trow, nrows_thr, gld, sst);
+            __syncthreads();
+            tile_round<TB, B1, B0, INV, true>(tw, trow, nrows_thr, sld, sst);
+            __syncthreads();
+            tile_round<TB, B2, B0 + B1, INV, true>(tw, trow, nrows_thr, sld, gst);
+        }
     }
-}
-
-// natural order in -> bit-reversed order out (rows of the tile)
-__device__ __forceinline__ void tile_dif(u64* tile, const u64* twl, u32 log_t, u32 ncols) {
-    int hi = (int)log_t;
-    while (hi > 0) {
-        int rb = hi >= 4 ? 4 : hi;
-        if (hi > 4 && hi < 8) rb = (hi + 1) / 2;  // 7 -> 4+3, 6 -> 3+3, 5 -> 3+2
-        radix_dispatch<false>(rb, tile, twl, log_t, (u32)(hi - rb), ncols, threadIdx.x, blockDim.x);
-        __syncthreads();
-        hi -= rb;
-    }
-}
-// bit-reversed order in -> natural order out
-__device__ __forceinline__ void tile_dit(u64* tile, const u64* twl, u32 log_t, u32 ncols) {
-    int lo = 0;
-    while (lo < (int)log_t) {
-        int rem = (int)log_t - lo;
-        int rb = rem >= 4 ? 4 : rem;
-        if (rem > 4 && rem < 8) rb = (rem + 1) / 2;
-        radix_dispatch<true>(rb, tile, twl, log_t, (u32)lo, ncols, threadIdx.x, blockDim.x);
-        __syncthreads();
-        lo += rb;
-    }
-}
-
-__device__ __forceinline__ void load_local_twiddles(u64* twl, const u64* tw_small, u32 log_t) {
-    u32 half = (1u << log_t) >> 1;
-    for (u32 i = threadIdx.x; i < half; i += blockDim.x) twl[i] = __ldg(tw_small + ((size_t)i << (kTwSmallLog - log_t)));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -122,80 +208,49 @@ __device__ __forceinline__ void load_local_twiddles(u64* twl, const u64* tw_smal
 struct StridedParams {
     const u64* src;
     u64* dst;
-    const u64* tw_small;
-    gl::PowTable tw;
-    u64 I;        // inner elements per point: S * w
-    u64 a_total;  // number of (independent) outer blocks
-    u32 log_t, w, xt;
-    u32 nchunks;  // wide mode: column chunks per outer block; 0 selects narrow mode
-    u32 aa;       // narrow mode (I <= xt): outer blocks per tile
-    int has_tw;
+    const u64* tw;    // w_1024^{+-i}, i < 1024
+    const u64* twp;   // inter-pass twiddles [b][r] = w_M^{+-b * rev(r)}, or null
+    u64 I;            // inner elements per point: S * w
+    u64 a_total;      // number of (independent) outer blocks
+    u32 w;
+    u32 nchunks;      // wide mode: column chunks per outer block; 0 selects narrow mode
+    u32 aa;           // narrow mode (I <= 16): outer blocks per tile
 };
 
+template <int TB, bool INV>
 __global__ void __launch_bounds__(1024) k_ntt_strided(StridedParams p) {
     extern __shared__ u64 smem[];
-    const u32 T = 1u << p.log_t;
-    u64* tile = smem;
-    u64* twl = smem + (size_t)T * kPitch;
-    const u32 tid = threadIdx.x, nthr = blockDim.x;
-    load_local_twiddles(twl, p.tw_small, p.log_t);
-
-    u32 ncols;
-    u64 base;  // element offset of (row 0, col 0)
-    u64 x0 = 0;
+    constexpr u32 T = 1u << TB;
+    const u32 q = threadIdx.x & (kXt - 1), trow = threadIdx.x >> 4, nrows_thr = blockDim.x >> 4;
+    // this thread's column: element offset of tile row 0, validity, and the row index b of the inter-pass twiddle
+    u64 col;
+    u32 b;
+    bool valid;
     if (p.nchunks) {
-        u64 a = blockIdx.x / p.nchunks;
-        x0 = (u64)(blockIdx.x % p.nchunks) * p.xt;
-        ncols = (u32)min((u64)p.xt, p.I - x0);
-        base = a * T * p.I + x0;
-        const u32 total = T * ncols;
-        for (u32 e = tid; e < total; e += nthr) {
-            u32 q = e % ncols, j = e / ncols;
-            tile[(size_t)j * kPitch + q] = p.src[base + (u64)j * p.I + q];
-        }
+        const u64 a = blockIdx.x / p.nchunks;
+        const u64 x = (u64)(blockIdx.x % p.nchunks) * kXt + q;
+        valid = x < p.I;
+        col = a * T * p.I + x;
+        b = (u32)(x / p.w);
     } else {
-        u64 a0 = (u64)blockIdx.x * p.aa;
-        u32 na = (u32)min((u64)p.aa, p.a_total - a0);
-        u32 I = (u32)p.I;
-        ncols = na * I;
-        base = a0 * T * I;
-        const u32 per_a = T * I, total = na * per_a;
-        for (u32 e = tid; e < total; e += nthr) {
-            u32 aq = e / per_a, rem = e % per_a;
-            u32 j = rem / I, x = rem % I;
-            tile[(size_t)j * kPitch + aq * I + x] = p.src[base + e];
-        }
+        const u32 I = (u32)p.I;
+        const u32 aq = q / I, x = q % I;
+        const u64 a = (u64)blockIdx.x * p.aa + aq;
+        valid = aq < p.aa && a < p.a_total;
+        col = a * T * I + x;
+        b = x / p.w;
     }
-    __syncthreads();
-    tile_dif(tile, twl, p.log_t, ncols);
-
-    if (p.nchunks) {
-        const u32 total = T * ncols;
-        for (u32 e = tid; e < total; e += nthr) {
-            u32 q = e % ncols, j = e / ncols;
-            u64 v = tile[(size_t)j * kPitch + q];
-            if (p.has_tw) {
-                u64 b = (x0 + q) / p.w;
-                u64 k1 = gl::rev_bits(j, p.log_t);
-                v = gl::mul(v, gl::pow_lookup(p.tw, b * k1));
-            }
-            p.dst[base + (u64)j * p.I + q] = v;
-        }
-    } else {
-        u32 I = (u32)p.I;
-        const u32 per_a = T * I, total = (ncols / I) * per_a;
-        for (u32 e = tid; e < total; e += nthr) {
-            u32 aq = e / per_a, rem = e % per_a;
-            u32 j = rem / I, x = rem % I;
-            u64 v = tile[(size_t)j * kPitch + aq * I + x];
-            if (p.has_tw) {
-                u64 b = x / p.w;
-                u64 k1 = gl::rev_bits(j, p.log_t);
-                v = gl::mul(v, gl::pow_lookup(p.tw, b * k1));
-            }
-            p.dst[base + e] = v;
-        }
-    }
+    const u64* __restrict__ src = p.src + col;
+    u64* __restrict__ dst = p.dst + col;
+    const u64 I = p.I;
+    const u64* __restrict__ twp = p.twp ? p.twp + (size_t)b * T : nullptr;
+    auto gld = [&](u32 row) -> u64 { return valid ? src[(u64)row * I] : 0ull; };
+    auto gst = [&](u32 row, u64 v) {
+        if (!valid) return;
+        if (twp) v = mul(v, __ldg(twp + row));
+        dst[(u64)row * I] = v;
+    };
+    tile_pass<TB, INV, false>(smem, p.tw, q, trow, nrows_thr, gld, gst);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -207,71 +262,50 @@ __global__ void __launch_bounds__(1024) k_ntt_strided(StridedParams p) {
 struct BlockParams {
     const u64* src;
     u64* dst;
-    const u64* tw_small;
-    const gl::PowTable* scale;  // [B] device array, indexed by output block
-    gl::PowTable tw;
-    u64 S;                // n / T
+    const u64* tw;      // w_1024^i
+    const u64* scale;   // [beta][b][t] = (shift_beta)^{rev_T(t)*S + b} / n
+    const u64* twb;     // [b][s] = w_n^{b*s}, or null when S == 1
+    u64 S;              // n / T
     u64 out_block_elems;  // n * w
-    u32 log_n, log_t, w, xt;
-    u32 nchunks;  // w > xt: column chunks per b; 0: whole rows, nbq low indices per tile
+    u32 log_n, w;
+    u32 nchunks;  // w > 16: column chunks per b; 0: whole rows, nbq low indices per tile
     u32 nbq;
-    int has_tw;
 };
 
+template <int TB>
 __global__ void __launch_bounds__(1024) k_ntt_block(BlockParams p) {
     extern __shared__ u64 smem[];
-    const u32 T = 1u << p.log_t;
-    u64* tile = smem;
-    u64* twl = smem + (size_t)T * kPitch;
-    const u32 tid = threadIdx.x, nthr = blockDim.x;
-    load_local_twiddles(twl, p.tw_small, p.log_t);
-    const gl::PowTable sc = p.scale[blockIdx.y];
-    const u32 hi_bits = p.log_n - p.log_t;
+    constexpr u32 T = 1u << TB;
+    const u32 q = threadIdx.x & (kXt - 1), trow = threadIdx.x >> 4, nrows_thr = blockDim.x >> 4;
+    const u32 hi_bits = p.log_n - TB;
     const u32 w = p.w;
-    u32 ncols;
-    u64 b0;
-    u32 c0 = 0;
+    u64 b;
+    u32 c;
+    bool valid;
     if (p.nchunks == 0) {
-        b0 = (u64)blockIdx.x * p.nbq;
-        u32 nb = (u32)min((u64)p.nbq, p.S - b0);
-        ncols = nb * w;
-        const u32 per_b = T * w, total = nb * per_b;
-        for (u32 e = tid; e < total; e += nthr) {
-            u32 bq = e / per_b, rem = e % per_b;
-            u32 t = rem / w, c = rem % w;
-            u64 b = b0 + bq;
-            u64 blk = gl::rev_bits((u32)b, hi_bits);
-            u64 v = p.src[(blk * T + t) * w + c];
-            u64 j = (u64)gl::rev_bits(t, p.log_t) * p.S + b;
-            tile[(size_t)t * kPitch + bq * w + c] = gl::mul(v, gl::pow_lookup(sc, j));
-        }
+        const u32 bq = q / w;
+        c = q % w;
+        b = (u64)blockIdx.x * p.nbq + bq;
+        valid = bq < p.nbq && b < p.S;
     } else {
-        b0 = blockIdx.x / p.nchunks;
-        c0 = (blockIdx.x % p.nchunks) * p.xt;
-        ncols = min(p.xt, w - c0);
-        u64 blk = gl::rev_bits((u32)b0, hi_bits);
-        const u32 total = T * ncols;
-        for (u32 e = tid; e < total; e += nthr) {
-            u32 q = e % ncols, t = e / ncols;
-            u64 v = p.src[(blk * T + t) * w + c0 + q];
-            u64 j = (u64)gl::rev_bits(t, p.log_t) * p.S + b0;
-            tile[(size_t)t * kPitch + q] = gl::mul(v, gl::pow_lookup(sc, j));
-        }
+        b = blockIdx.x / p.nchunks;
+        c = (blockIdx.x % p.nchunks) * kXt + q;
+        valid = c < w;
     }
-    __syncthreads();
-    tile_dit(tile, twl, p.log_t, ncols);
-
-    u64* out = p.dst + (u64)blockIdx.y * p.out_block_elems;
-    const u32 total = T * ncols;
-    for (u32 e = tid; e < total; e += nthr) {
-        u32 q = e % ncols, s = e / ncols;
-        u64 v = tile[(size_t)s * kPitch + q];
-        u64 b = p.nchunks ? b0 : b0 + q / w;
-        if (p.has_tw) v = gl::mul(v, gl::pow_lookup(p.tw, b * (u64)s));
-        u64 drow = (u64)gl::rev_bits(s, p.log_t) * p.S;
-        // (drow + b0) * w + c0 + q addresses (b, c) because q = bq * w + c in whole-row mode
-        out[(drow + b0) * w + c0 + q] = v;
-    }
+    if (!valid) b = 0;
+    const u64 blk = gl::rev_bits((u32)b, hi_bits);
+    const u64* __restrict__ src = p.src + blk * T * w + c;
+    const u64* __restrict__ sc = p.scale + ((size_t)blockIdx.y * p.S + b) * T;
+    const u64* __restrict__ twb = p.twb ? p.twb + (size_t)b * T : nullptr;
+    u64* __restrict__ dst = p.dst + (u64)blockIdx.y * p.out_block_elems + b * w + c;
+    const u64 dstride = p.S * w;
+    auto gld = [&](u32 t) -> u64 { return valid ? mul(src[(u64)t * w], __ldg(sc + t)) : 0ull; };
+    auto gst = [&](u32 s, u64 v) {
+        if (!valid) return;
+        if (twb) v = mul(v, __ldg(twb + s));
+        dst[(u64)gl::rev_bits(s, TB) * dstride] = v;
+    };
+    tile_pass<TB, false, true>(smem, p.tw, q, trow, nrows_thr, gld, gst);
 }
 
 // dst[beta][j][c] = src[j][c] * tab[beta](j)
@@ -294,6 +328,34 @@ __global__ void k_bitrev_rows_scale(const u64* src, u64* dst, u64 n, u64 w, u32 
     }
 }
 
+// ---- table builders ----------------------------------------------------------------------------------
+// out[b * T + r] = g^{b * rev_tb(r)}
+__global__ void k_fill_twp(u64* out, u64 total, u32 tb, gl::PowTable g) {
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (u64)gridDim.x * blockDim.x) {
+        u64 b = e >> tb;
+        u32 r = (u32)(e & ((1u << tb) - 1));
+        out[e] = gl::pow_lookup(g, b * gl::rev_bits(r, tb));
+    }
+}
+// out[b * T + s] = g^{b * s}
+__global__ void k_fill_twb(u64* out, u64 total, u32 tb, gl::PowTable g) {
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (u64)gridDim.x * blockDim.x) {
+        u64 b = e >> tb;
+        u32 s = (u32)(e & ((1u << tb) - 1));
+        out[e] = gl::pow_lookup(g, b * s);
+    }
+}
+// out[(beta * S + b) * T + t] = tab[beta](rev_tb(t) * S + b)
+__global__ void k_fill_scale(u64* out, u64 n, u32 tb, u64 S, const gl::PowTable* tabs, u32 nb) {
+    u64 total = n * nb;
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (u64)gridDim.x * blockDim.x) {
+        u32 t = (u32)(e & ((1u << tb) - 1));
+        u64 rest = e >> tb;
+        u64 b = rest % S, beta = rest / S;
+        out[e] = gl::pow_lookup(tabs[beta], (u64)gl::rev_bits(t, tb) * S + b);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host drivers
 // ------------------------------------------------------------------------------------------------
@@ -306,59 +368,131 @@ static std::vector<u32> plan_passes(u32 log_n) {
     return tb;
 }
 
-static size_t tile_smem(u32 log_t) { return ((size_t)(1u << log_t) * kPitch + ((1u << log_t) >> 1)) * sizeof(u64); }
-static u32 tile_threads(u32 log_t, u32 ncols) {
-    u32 t = ((1u << log_t) * ncols) / 16;
-    if (t < 64) t = 64;
+static size_t tile_smem(u32 log_t) { return log_t <= 4 ? 0 : (size_t)(1u << log_t) * kPitch * sizeof(u64); }
+static u32 tile_threads(u32 log_t) {
+    u32 rows = log_t >= 4 ? (1u << (log_t - 4)) : 1u;  // one thread row per radix-16 item
+    u32 t = rows * kXt;
+    if (t < 32) t = 32;
     if (t > 1024) t = 1024;
-    return (t + 31) / 32 * 32;
+    return t;
 }
 
-static void ensure_smem_attr() {
-    static bool done = false;
-    if (done) return;
-    MSG_CUDA(cudaFuncSetAttribute(k_ntt_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(kMaxLogT)));
-    MSG_CUDA(cudaFuncSetAttribute(k_ntt_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(kMaxLogT)));
-    done = true;
+template <int TB>
+static void launch_strided_tb(const StridedParams& p, bool inverse, u64 blocks, cudaStream_t st) {
+    static bool attr[2] = {false, false};
+    if (inverse) {
+        if (!attr[1]) {
+            MSG_CUDA(cudaFuncSetAttribute(k_ntt_strided<TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(kMaxLogT)));
+            attr[1] = true;
+        }
+        k_ntt_strided<TB, true><<<(unsigned)blocks, tile_threads(TB), tile_smem(TB), st>>>(p);
+    } else {
+        if (!attr[0]) {
+            MSG_CUDA(cudaFuncSetAttribute(k_ntt_strided<TB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(kMaxLogT)));
+            attr[0] = true;
+        }
+        k_ntt_strided<TB, false><<<(unsigned)blocks, tile_threads(TB), tile_smem(TB), st>>>(p);
+    }
+}
+template <int TB>
+static void launch_block_tb(const BlockParams& p, dim3 grid, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        MSG_CUDA(cudaFuncSetAttribute(k_ntt_block<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(kMaxLogT)));
+        attr = true;
+    }
+    k_ntt_block<TB><<<grid, tile_threads(TB), tile_smem(TB), st>>>(p);
+}
+
+#define MSG_TB_SWITCH(tb, CALL)                               \
+    switch (tb) {                                             \
+        case 1: { constexpr int TBV = 1; CALL; } break;       \
+        case 2: { constexpr int TBV = 2; CALL; } break;       \
+        case 3: { constexpr int TBV = 3; CALL; } break;       \
+        case 4: { constexpr int TBV = 4; CALL; } break;       \
+        case 5: { constexpr int TBV = 5; CALL; } break;       \
+        case 6: { constexpr int TBV = 6; CALL; } break;       \
+        case 7: { constexpr int TBV = 7; CALL; } break;       \
+        case 8: { constexpr int TBV = 8; CALL; } break;       \
+        case 9: { constexpr int TBV = 9; CALL; } break;       \
+        case 10: { constexpr int TBV = 10; CALL; } break;     \
+        default: throw Error(-3, "ntt: bad tile size");       \
+    }
+
+// inter-pass twiddle table of a DIF pass: [b][r] = w_{2^log_big}^{+-b * rev_tb(r)}, b < 2^(log_big - tb)
+static const u64* twp_table(Ctx& c, u32 log_big, u32 tb, bool inverse) {
+    auto key = std::make_tuple(0u, log_big, tb, (u64)inverse);
+    auto it = c.ntt_tables.find(key);
+    if (it != c.ntt_tables.end()) return it->second;
+    msh::Fp g = msh::two_adic_generator(log_big);
+    if (inverse) g = g.inverse();
+    gl::PowTable tab = c.pow_table(g.v, 1, log_big).view();
+    u64 total = 1ull << log_big;
+    u64* d;
+    MSG_CUDA(cudaMalloc(&d, total * 8));
+    c.owned.push_back(d);
+    k_fill_twp<<<(unsigned)std::min<u64>((total + 255) / 256, (u64)c.sm_count * 16), 256, 0, c.stream>>>(d, total, tb, tab);
+    MSG_CUDA(cudaGetLastError());
+    c.ntt_tables[key] = d;
+    return d;
+}
+// output twiddle table of the block pass: [b][s] = w_n^{b * s}
+static const u64* twb_table(Ctx& c, u32 log_n, u32 tb) {
+    auto key = std::make_tuple(1u, log_n, tb, (u64)0);
+    auto it = c.ntt_tables.find(key);
+    if (it != c.ntt_tables.end()) return it->second;
+    gl::PowTable tab = c.pow_table(msh::two_adic_generator(log_n).v, 1, log_n).view();
+    u64 total = 1ull << log_n;
+    u64* d;
+    MSG_CUDA(cudaMalloc(&d, total * 8));
+    c.owned.push_back(d);
+    k_fill_twb<<<(unsigned)std::min<u64>((total + 255) / 256, (u64)c.sm_count * 16), 256, 0, c.stream>>>(d, total, tb, tab);
+    MSG_CUDA(cudaGetLastError());
+    c.ntt_tables[key] = d;
+    return d;
+}
+// coset scales of the block pass: [beta][b][t] = (shift * w_{nB}^{rev(beta)})^{rev_tb(t) * S + b} / n
+static const u64* scale_table(Ctx& c, u32 log_n, u32 tb, u32 added_bits, u64 shift) {
+    auto key = std::make_tuple(2u + (added_bits << 8), log_n, tb, shift);
+    auto it = c.ntt_tables.find(key);
+    if (it != c.ntt_tables.end()) return it->second;
+    const gl::PowTable* tabs = c.coset_tables(log_n, added_bits, shift);
+    u64 n = 1ull << log_n, total = n << added_bits;
+    u64* d;
+    MSG_CUDA(cudaMalloc(&d, total * 8));
+    c.owned.push_back(d);
+    k_fill_scale<<<(unsigned)std::min<u64>((total + 255) / 256, (u64)c.sm_count * 16), 256, 0, c.stream>>>(d, n, tb, n >> tb, tabs,
+                                                                                                         1u << added_bits);
+    MSG_CUDA(cudaGetLastError());
+    c.ntt_tables[key] = d;
+    return d;
 }
 
 // One DIF pass over bits [lo_bit, lo_bit + tb) of a size-2^log_m transform, for `count` transforms
 // stored back to back (count * 2^log_m rows in total).
 static void launch_strided(Ctx& c, const u64* src, u64* dst, u32 log_m, u64 count, u64 w, u32 lo_bit, u32 tb, bool inverse) {
-    ensure_smem_attr();
     StridedParams p{};
     p.src = src;
     p.dst = dst;
-    p.tw_small = c.tw_small[inverse ? 1 : 0];
-    p.log_t = tb;
+    p.tw = c.tw_full[inverse ? 1 : 0];
     p.w = (u32)w;
-    p.xt = kMaxXt;
     u64 S = 1ull << lo_bit;
     p.I = S * w;
     p.a_total = count << (log_m - lo_bit - tb);
-    p.has_tw = lo_bit > 0;
-    if (p.has_tw) {
-        u32 log_big = lo_bit + tb;
-        msh::Fp g = msh::two_adic_generator(log_big);
-        if (inverse) g = g.inverse();
-        p.tw = c.pow_table(g.v, 1, log_big).view();
-    }
+    p.twp = lo_bit > 0 ? twp_table(c, lo_bit + tb, tb, inverse) : nullptr;
     u64 blocks;
-    u32 ncols_max;
-    if (p.I > (u64)p.xt) {
-        p.nchunks = (u32)((p.I + p.xt - 1) / p.xt);
+    if (p.I > (u64)kXt) {
+        p.nchunks = (u32)((p.I + kXt - 1) / kXt);
         blocks = p.a_total * p.nchunks;
-        ncols_max = p.xt;
     } else {
         p.nchunks = 0;
-        p.aa = (u32)(p.xt / p.I);
+        p.aa = (u32)(kXt / p.I);
         blocks = (p.a_total + p.aa - 1) / p.aa;
-        ncols_max = (u32)std::min<u64>(p.aa, p.a_total) * (u32)p.I;
     }
     MSG_REQUIRE(blocks < (1ull << 31), "ntt: grid too large");
     {
         KLaunch kl(c, "k_ntt_strided");
-        k_ntt_strided<<<(unsigned)blocks, tile_threads(tb, ncols_max), tile_smem(tb), c.stream>>>(p);
+        MSG_TB_SWITCH(tb, launch_strided_tb<TBV>(p, inverse, blocks, c.stream));
     }
     MSG_CUDA(cudaGetLastError());
 }
@@ -387,42 +521,40 @@ void ntt_coset_lde(Ctx& c, const u64* src, u64* dst, u64* tmp, u64 n, u64 w, u32
     if (w == 0) return;
     u32 log_n = ilog2(n);
     MSG_REQUIRE(log_n + added_bits <= msh::GL_TWO_ADICITY, "lde: extended height exceeds the two-adicity of the field");
-    ensure_smem_attr();
+    if (log_n == 0) {  // constant polynomials: every coset evaluation is the value itself
+        for (u64 beta = 0; beta < (1ull << added_bits); beta++)
+            MSG_CUDA(cudaMemcpyAsync(dst + beta * w, src, w * 8, cudaMemcpyDeviceToDevice, c.stream));
+        return;
+    }
     // 1. inverse transform (unnormalised): coefficients in bit-reversed order
     ntt_dft_bitrev(c, src, tmp, n, w, true);
     // 2. first forward pass per coset from the bit-reversed coefficients
     auto plan = plan_passes(log_n);
-    u32 tb = plan.empty() ? 0 : plan.back();
+    u32 tb = plan.back();
     BlockParams p{};
     p.src = tmp;
     p.dst = dst;
-    p.tw_small = c.tw_small[0];
-    p.scale = c.coset_tables(log_n, added_bits, shift);
+    p.tw = c.tw_full[0];
+    p.scale = scale_table(c, log_n, tb, added_bits, shift);
     p.log_n = log_n;
-    p.log_t = tb;
     p.w = (u32)w;
-    p.xt = kMaxXt;
     p.S = n >> tb;
     p.out_block_elems = n * w;
-    p.has_tw = p.S > 1;
-    if (p.has_tw) p.tw = c.pow_table(msh::two_adic_generator(log_n).v, 1, log_n).view();
+    p.twb = p.S > 1 ? twb_table(c, log_n, tb) : nullptr;
     u64 blocks;
-    u32 ncols_max;
-    if (w <= (u64)p.xt) {
+    if (w <= (u64)kXt) {
         p.nchunks = 0;
-        p.nbq = (u32)(p.xt / w);
+        p.nbq = (u32)(kXt / w);
         blocks = (p.S + p.nbq - 1) / p.nbq;
-        ncols_max = (u32)std::min<u64>(p.nbq, p.S) * (u32)w;
     } else {
-        p.nchunks = (u32)((w + p.xt - 1) / p.xt);
+        p.nchunks = (u32)((w + kXt - 1) / kXt);
         blocks = p.S * p.nchunks;
-        ncols_max = p.xt;
     }
     MSG_REQUIRE(blocks < (1ull << 31), "lde: grid too large");
     dim3 grid((unsigned)blocks, 1u << added_bits);
     {
         KLaunch kl(c, "k_ntt_block");
-        k_ntt_block<<<grid, tile_threads(tb, ncols_max), tile_smem(tb), c.stream>>>(p);
+        MSG_TB_SWITCH(tb, launch_block_tb<TBV>(p, grid, c.stream));
     }
     MSG_CUDA(cudaGetLastError());
     // 3. remaining forward passes: every block rev_T(k1) of S rows is an independent size-S DFT
@@ -550,17 +682,23 @@ const gl::PowTable* Ctx::lde_coeff_tables(u32 log_n, u32 added_bits) {
 }
 
 void ctx_init_tables(Ctx& c) {
-    const size_t half = (size_t)1 << (kTwSmallLog - 1);
-    std::vector<u64> f(half), inv(half);
-    msh::Fp w = msh::two_adic_generator(kTwSmallLog), wi = w.inverse();
-    msh::Fp a = msh::Fp::one(), b = msh::Fp::one();
-    for (size_t i = 0; i < half; i++) { f[i] = a.v; inv[i] = b.v; a *= w; b *= wi; }
-    for (int d = 0; d < 2; d++) {
-        MSG_CUDA(cudaMalloc(&c.tw_small[d], half * 8));
-        c.owned.push_back(c.tw_small[d]);
+    // the register DFTs hard-code two_adic_generator(k) = 2^root_exp(k): verify against the host field
+    for (int k = 1; k <= 4; k++) {
+        int e = root_exp(k, false);
+        msh::Fp want = msh::two_adic_generator(k), got = msh::Fp(2).pow((msh::u64)e);
+        if (want != got) throw Error(-3, "ntt: two-adic generator is not the expected power of two");
     }
-    MSG_CUDA(cudaMemcpyAsync(c.tw_small[0], f.data(), half * 8, cudaMemcpyHostToDevice, c.stream));
-    MSG_CUDA(cudaMemcpyAsync(c.tw_small[1], inv.data(), half * 8, cudaMemcpyHostToDevice, c.stream));
+    const size_t full = (size_t)1 << kTwLog;
+    std::vector<u64> f(full), inv(full);
+    msh::Fp w = msh::two_adic_generator(kTwLog), wi = w.inverse();
+    msh::Fp a = msh::Fp::one(), b = msh::Fp::one();
+    for (size_t i = 0; i < full; i++) { f[i] = a.v; inv[i] = b.v; a *= w; b *= wi; }
+    for (int d = 0; d < 2; d++) {
+        MSG_CUDA(cudaMalloc(&c.tw_full[d], full * 8));
+        c.owned.push_back(c.tw_full[d]);
+    }
+    MSG_CUDA(cudaMemcpyAsync(c.tw_full[0], f.data(), full * 8, cudaMemcpyHostToDevice, c.stream));
+    MSG_CUDA(cudaMemcpyAsync(c.tw_full[1], inv.data(), full * 8, cudaMemcpyHostToDevice, c.stream));
     MSG_CUDA(cudaStreamSynchronize(c.stream));
 }
 
