@@ -164,6 +164,22 @@ __device__ __forceinline__ u64 mul(u64 a, u64 b) {
 __host__ __device__ constexpr u64 pow2_mod_p(int e) {
     return e < 64 ? (1ull << e) : ((1ull << (e - 32)) - (1ull << (e - 64)));  // 2^64 = 2^32 - 1
 }
+// x * 2^e mod p for 0 < e < 96 with shifts instead of a multiplication: x << (e % 32) is three 32-bit limbs y0, y1, y2 at
+// limb position q = e / 32, and 2^64 = eps, 2^96 = -1, 2^128 = -2^32. x may be any u64; the result is canonical.
+// `e` must be a compile-time constant after inlining (11 to 17 instructions against 22 for a constant multiplier).
+__device__ __forceinline__ u64 mul_pow2(u64 x, int e) {
+    const int q = e / 32, r = e % 32;
+    const u32 x0 = (u32)x, x1 = (u32)(x >> 32);
+    u32 y0, y1, y2;
+    if (r == 0) {
+        y0 = x0; y1 = x1; y2 = 0;
+    } else {
+        y0 = x0 << r; y1 = __funnelshift_l(x0, x1, r); y2 = x1 >> (32 - r);
+    }
+    if (q == 2) return sub_lazy((u64)y0 * GLD_EPS, ((u64)y2 << 32) | y1);          // y0 eps - (y1 + y2 2^32)
+    if (q == 0) return sub_lazy(((u64)y1 << 32) | y0, GLD_P - (u64)y2 * GLD_EPS);  // (y0 + y1 2^32) + y2 eps
+    return sub_lazy(sub_lazy((u64)y0 << 32, (u64)y2), GLD_P - (u64)y1 * GLD_EPS);  // y0 2^32 - y2 + y1 eps
+}
 }  // namespace gf
 
 // ---- extension field F_p[X]/(X^2 - 7) -------------------------------------------------------

@@ -35,8 +35,10 @@
 
 namespace msg {
 
-constexpr int kPitch = 17;        // u64 per tile row (16 data + 1 pad)
-constexpr int kXt = 16;           // tile columns
+constexpr int kXt = 4;            // tile columns (64-byte row segments); two 512-thread CTAs per SM overlap their load /
+                                  // compute / store phases, which one 1024-thread CTA with 16 columns cannot
+constexpr int kLogXt = 2;
+constexpr int kPitch = kXt + 1;   // u64 per tile row (+1 pad)
 constexpr int kMaxLogT = 10;      // tile points
 constexpr int kTwLog = 10;        // w_1024 table, full period
 
@@ -54,8 +56,8 @@ __host__ __device__ constexpr int root_exp(int logr, bool inv) {
 __device__ __forceinline__ u64 sub_mul_pow2(u64 u, u64 x, int e) {
     if (e == 0) return sub(u, x);
     if (e == 96) return sub(x, u);
-    if (e < 96) return mul(sub(u, x), gl::gf::pow2_mod_p(e));
-    return mul(sub(x, u), gl::gf::pow2_mod_p(e - 96));
+    if (e < 96) return gl::gf::mul_pow2(sub(u, x), e);
+    return gl::gf::mul_pow2(sub(x, u), e - 96);
 }
 
 // size-2^RB DFT in registers, natural order in, bit-reversed order out (decimation in frequency)
@@ -101,11 +103,11 @@ __device__ __forceinline__ void dit_regs(u64 (&v)[1 << RB]) {
                     v[i] = sub(u, x);
                     v[j] = add(u, x);
                 } else if (e < 96) {
-                    u64 y = mul(x, gl::gf::pow2_mod_p(e));
+                    u64 y = gl::gf::mul_pow2(x, e);
                     v[i] = add(u, y);
                     v[j] = sub(u, y);
                 } else {
-                    u64 y = mul(x, gl::gf::pow2_mod_p(e - 96));
+                    u64 y = gl::gf::mul_pow2(x, e - 96);
                     v[i] = sub(u, y);
                     v[j] = add(u, y);
                 }
@@ -213,33 +215,21 @@ struct StridedParams {
     u64 I;            // inner elements per point: S * w
     u64 a_total;      // number of (independent) outer blocks
     u32 w;
-    u32 nchunks;      // wide mode: column chunks per outer block; 0 selects narrow mode
-    u32 aa;           // narrow mode (I <= 16): outer blocks per tile
 };
 
 template <int TB, bool INV>
-__global__ void __launch_bounds__(1024) k_ntt_strided(StridedParams p) {
+__global__ void __launch_bounds__(64 * kXt, 1024 / (64 * kXt)) k_ntt_strided(StridedParams p) {
     extern __shared__ u64 smem[];
     constexpr u32 T = 1u << TB;
-    const u32 q = threadIdx.x & (kXt - 1), trow = threadIdx.x >> 4, nrows_thr = blockDim.x >> 4;
+    const u32 q = threadIdx.x & (kXt - 1), trow = threadIdx.x >> kLogXt, nrows_thr = blockDim.x >> kLogXt;
     // this thread's column: element offset of tile row 0, validity, and the row index b of the inter-pass twiddle
-    u64 col;
-    u32 b;
-    bool valid;
-    if (p.nchunks) {
-        const u64 a = blockIdx.x / p.nchunks;
-        const u64 x = (u64)(blockIdx.x % p.nchunks) * kXt + q;
-        valid = x < p.I;
-        col = a * T * p.I + x;
-        b = (u32)(x / p.w);
-    } else {
-        const u32 I = (u32)p.I;
-        const u32 aq = q / I, x = q % I;
-        const u64 a = (u64)blockIdx.x * p.aa + aq;
-        valid = aq < p.aa && a < p.a_total;
-        col = a * T * I + x;
-        b = x / p.w;
-    }
+    // Virtual column v enumerates (outer block a, inner index x): tiles take kXt consecutive virtual columns, so lanes
+    // are idle only in the very last tile even when the row length is not a multiple of kXt.
+    const u64 v = (u64)blockIdx.x * kXt + q;
+    const bool valid = v < p.a_total * p.I;
+    const u64 a = valid ? v / p.I : 0, x = valid ? v % p.I : 0;
+    const u64 col = a * T * p.I + x;
+    const u32 b = (u32)(x / p.w);
     const u64* __restrict__ src = p.src + col;
     u64* __restrict__ dst = p.dst + col;
     const u64 I = p.I;
@@ -268,31 +258,20 @@ struct BlockParams {
     u64 S;              // n / T
     u64 out_block_elems;  // n * w
     u32 log_n, w;
-    u32 nchunks;  // w > 16: column chunks per b; 0: whole rows, nbq low indices per tile
-    u32 nbq;
 };
 
 template <int TB>
-__global__ void __launch_bounds__(1024) k_ntt_block(BlockParams p) {
+__global__ void __launch_bounds__(64 * kXt, 1024 / (64 * kXt)) k_ntt_block(BlockParams p) {
     extern __shared__ u64 smem[];
     constexpr u32 T = 1u << TB;
-    const u32 q = threadIdx.x & (kXt - 1), trow = threadIdx.x >> 4, nrows_thr = blockDim.x >> 4;
+    const u32 q = threadIdx.x & (kXt - 1), trow = threadIdx.x >> kLogXt, nrows_thr = blockDim.x >> kLogXt;
     const u32 hi_bits = p.log_n - TB;
     const u32 w = p.w;
-    u64 b;
-    u32 c;
-    bool valid;
-    if (p.nchunks == 0) {
-        const u32 bq = q / w;
-        c = q % w;
-        b = (u64)blockIdx.x * p.nbq + bq;
-        valid = bq < p.nbq && b < p.S;
-    } else {
-        b = blockIdx.x / p.nchunks;
-        c = (blockIdx.x % p.nchunks) * kXt + q;
-        valid = c < w;
-    }
-    if (!valid) b = 0;
+    // virtual column v = b * w + c over the S low indices b and the w matrix columns c
+    const u64 v = (u64)blockIdx.x * kXt + q;
+    const bool valid = v < p.S * w;
+    const u64 b = valid ? v / w : 0;
+    const u32 c = valid ? (u32)(v % w) : 0;
     const u64 blk = gl::rev_bits((u32)b, hi_bits);
     const u64* __restrict__ src = p.src + blk * T * w + c;
     const u64* __restrict__ sc = p.scale + ((size_t)blockIdx.y * p.S + b) * T;
@@ -373,7 +352,7 @@ static u32 tile_threads(u32 log_t) {
     u32 rows = log_t >= 4 ? (1u << (log_t - 4)) : 1u;  // one thread row per radix-16 item
     u32 t = rows * kXt;
     if (t < 32) t = 32;
-    if (t > 1024) t = 1024;
+    if (t > 64 * kXt) t = 64 * kXt;
     return t;
 }
 
@@ -480,15 +459,7 @@ static void launch_strided(Ctx& c, const u64* src, u64* dst, u32 log_m, u64 coun
     p.I = S * w;
     p.a_total = count << (log_m - lo_bit - tb);
     p.twp = lo_bit > 0 ? twp_table(c, lo_bit + tb, tb, inverse) : nullptr;
-    u64 blocks;
-    if (p.I > (u64)kXt) {
-        p.nchunks = (u32)((p.I + kXt - 1) / kXt);
-        blocks = p.a_total * p.nchunks;
-    } else {
-        p.nchunks = 0;
-        p.aa = (u32)(kXt / p.I);
-        blocks = (p.a_total + p.aa - 1) / p.aa;
-    }
+    u64 blocks = (p.a_total * p.I + kXt - 1) / kXt;
     MSG_REQUIRE(blocks < (1ull << 31), "ntt: grid too large");
     {
         KLaunch kl(c, "k_ntt_strided");
@@ -541,15 +512,7 @@ void ntt_coset_lde(Ctx& c, const u64* src, u64* dst, u64* tmp, u64 n, u64 w, u32
     p.S = n >> tb;
     p.out_block_elems = n * w;
     p.twb = p.S > 1 ? twb_table(c, log_n, tb) : nullptr;
-    u64 blocks;
-    if (w <= (u64)kXt) {
-        p.nchunks = 0;
-        p.nbq = (u32)(kXt / w);
-        blocks = (p.S + p.nbq - 1) / p.nbq;
-    } else {
-        p.nchunks = (u32)((w + kXt - 1) / kXt);
-        blocks = p.S * p.nchunks;
-    }
+    u64 blocks = (p.S * w + kXt - 1) / kXt;
     MSG_REQUIRE(blocks < (1ull << 31), "lde: grid too large");
     dim3 grid((unsigned)blocks, 1u << added_bits);
     {
