@@ -125,6 +125,12 @@ int msgpu_pdata_read_layer(msgpu_ctx* ctx, const msgpu_pdata* pd, uint64_t layer
 int msgpu_open_batch(msgpu_ctx* ctx, const msgpu_pdata* pd, const uint64_t* indices, uint64_t n_idx,
                      uint64_t* opened_out, uint8_t* proof_out);
 
+/* The query phase of Pcs::open in one launch: tree k (an input commitment or a FRI commit-phase layer) is opened at
+ * indices[q] >> shifts[k] for every query q. Per tree, outputs have the layout of msgpu_open_batch and follow each other:
+ * opened_out gets n_idx * total_width_k values per tree, proof_out n_idx * depth_k * 32 bytes per tree. */
+int msgpu_open_batch_multi(msgpu_ctx* ctx, const msgpu_pdata* const* pds, const uint32_t* shifts, uint64_t n_trees,
+                           const uint64_t* indices, uint64_t n_idx, uint64_t* opened_out, uint8_t* proof_out);
+
 /* ---- compiled constraint programs (reference `ConstraintGraph`, src/graph.rs:35-76) --------------------
  * The host compiles a circuit (src/graph.rs:120-188) and hands the flat node vector over; the library
  * lowers it to bytecode with liveness-based slot allocation for the device interpreter. */

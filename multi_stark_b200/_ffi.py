@@ -53,6 +53,7 @@ SIGNATURES = {
     "msgpu_pdata_layer_len": (C.c_uint64, [C.c_void_p, C.c_uint64]),
     "msgpu_pdata_read_layer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "msgpu_open_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "msgpu_open_batch_multi": (C.c_int, [C.c_void_p, c_vpp, c_u32p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "msgpu_program_create": (C.c_int, [C.c_void_p, C.c_void_p, c_vpp]),
     "msgpu_program_free": (None, [C.c_void_p]),
     "msgpu_stage2_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,

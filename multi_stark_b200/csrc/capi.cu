@@ -391,6 +391,14 @@ int msgpu_open_batch(msgpu_ctx* h, const msgpu_pdata* pd, const uint64_t* indice
     return guard([&] { mmcs_open_batch(h->c, pd, (const u64*)indices, n_idx, (u64*)opened_out, proof_out); });
 }
 
+int msgpu_open_batch_multi(msgpu_ctx* h, const msgpu_pdata* const* pds, const uint32_t* shifts, uint64_t n_trees,
+                           const uint64_t* indices, uint64_t n_idx, uint64_t* opened_out, uint8_t* proof_out) {
+    return guard([&] {
+        MSG_REQUIRE(pds && shifts && indices, "open_batch_multi: null argument");
+        mmcs_open_multi(h->c, pds, (const u32*)shifts, n_trees, (const u64*)indices, n_idx, (u64*)opened_out, proof_out);
+    });
+}
+
 int msgpu_blake3_compress_raw(msgpu_ctx* h, const uint32_t* state16, const uint32_t* msg16, uint32_t* out16) {
     return guard([&] {
         Ctx& c = h->c;

@@ -3,9 +3,34 @@
 // open_batch}` as configured by the reference at src/types.rs:82-84,199-207.
 #include "mmcs.hpp"
 #include <algorithm>
+#include <cstring>
 #include <numeric>
 
 namespace msg {
+
+struct OpenMat {
+    const u64* ptr;
+    u32 width;
+    u32 shift;    // log_max_height - log_height
+    u64 out_off;  // column offset inside one query's opened block
+};
+
+// device-resident descriptors for the query kernels: OpenMat[n_mats] then u64 layer_off[n_layers]
+static void build_open_desc(Ctx& c, msgpu_pdata* pd) {
+    u32 log_max = ilog2(pd->max_height);
+    std::vector<OpenMat> om;
+    u64 off = 0;
+    for (auto& m : pd->mats) {
+        om.push_back(OpenMat{m.ptr, (u32)m.width, log_max - ilog2(m.height), off});
+        off += m.width;
+    }
+    size_t sz_mats = om.size() * sizeof(OpenMat), sz_off = pd->layer_off.size() * 8;
+    std::vector<uint8_t> host(sz_mats + sz_off);
+    memcpy(host.data(), om.data(), sz_mats);
+    memcpy(host.data() + sz_mats, pd->layer_off.data(), sz_off);
+    pd->d_desc = c.alloc(host.size());
+    MSG_CUDA(cudaMemcpyAsync(pd->d_desc, host.data(), host.size(), cudaMemcpyHostToDevice, c.stream));  // pageable: staged before return
+}
 
 void mmcs_build(Ctx& c, msgpu_pdata* pd) {
     StageScope stage_scope(c, "merkle");
@@ -71,90 +96,95 @@ void mmcs_build(Ctx& c, msgpu_pdata* pd) {
     for (auto* p : inj)
         if (p) c.free(p);
     MSG_REQUIRE(pos == order.size(), "commit: internal error, matrix not placed in the tree");
+    build_open_desc(c, pd);
     MSG_CUDA(cudaMemcpyAsync(pd->root, pd->digests + pd->layer_off.back() * 32, 32, cudaMemcpyDeviceToHost, c.stream));
     c.sync();
 }
 
-struct OpenMat {
-    const u64* ptr;
-    u32 width;
-    u32 shift;    // log_max_height - log_height
-    u64 out_off;  // column offset inside one query's opened block
+struct MultiTree {
+    const OpenMat* mats;
+    const u64* layer_off;
+    const uint4* digests;
+    u32 nmats, shift, depth, pad;
+    u64 tw;           // total width of the tree's matrices
+    u64 opened_base;  // u64 offset of this tree's block in the opened output
+    u64 proof_base;   // uint4 offset of this tree's block in the proof output
 };
 
-__global__ void k_open_rows(const OpenMat* mats, u32 nmats, const u64* idx, u64 total_width, u64* out) {
+__global__ void __launch_bounds__(128) k_open_multi(const MultiTree* trees, const u64* idx, u64* opened, uint4* proofs) {
+    const MultiTree t = trees[blockIdx.y];
     const u64 q = blockIdx.x;
-    const u64 index = idx[q];
-    for (u32 k = 0; k < nmats; k++) {
-        const OpenMat m = mats[k];
+    const u64 index = idx[q] >> t.shift;
+    u64* o = opened + t.opened_base + q * t.tw;
+    for (u32 k = 0; k < t.nmats; k++) {
+        const OpenMat m = t.mats[k];
         const u64* row = m.ptr + (index >> m.shift) * m.width;
-        u64* o = out + q * total_width + m.out_off;
-        for (u32 cidx = threadIdx.x; cidx < m.width; cidx += blockDim.x) o[cidx] = row[cidx];
+        for (u32 cidx = threadIdx.x; cidx < m.width; cidx += blockDim.x) o[m.out_off + cidx] = row[cidx];
+    }
+    uint4* p = proofs + t.proof_base + q * t.depth * 2;
+    for (u32 e = threadIdx.x; e < t.depth * 2; e += blockDim.x) {
+        u32 lvl = e >> 1, half = e & 1;
+        u64 sib = (index >> lvl) ^ 1;
+        p[e] = t.digests[(t.layer_off[lvl] + sib) * 2 + half];
     }
 }
 
-__global__ void k_open_proof(const uint4* digests, const u64* layer_off, u32 depth, const u64* idx, u64 n_idx, uint4* out) {
-    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u64 total = n_idx * depth * 2;
-    if (t >= total) return;
-    u32 half = (u32)(t & 1);
-    u64 r = t >> 1;
-    u32 lvl = (u32)(r % depth);
-    u64 q = r / depth;
-    u64 sib = (idx[q] >> lvl) ^ 1;
-    out[t] = digests[(layer_off[lvl] + sib) * 2 + half];
+void mmcs_open_multi(Ctx& c, const msgpu_pdata* const* pds, const u32* shifts, u64 n_trees, const u64* indices_host, u64 n_idx,
+                     u64* opened_host, uint8_t* proof_host) {
+    if (n_idx == 0 || n_trees == 0) return;
+    std::vector<MultiTree> mt(n_trees);
+    u64 opened_total = 0, proof_total = 0;
+    for (u64 k = 0; k < n_trees; k++) {
+        const msgpu_pdata* pd = pds[k];
+        MSG_REQUIRE(pd && pd->d_desc, "open_multi: prover data without a tree");
+        u32 depth = ilog2(pd->max_height);
+        for (u64 i = 0; i < n_idx; i++)
+            MSG_REQUIRE((indices_host[i] >> shifts[k]) < pd->max_height, "open_multi: index out of range");
+        MultiTree& t = mt[k];
+        t.mats = (const OpenMat*)pd->d_desc;
+        t.layer_off = (const u64*)((const uint8_t*)pd->d_desc + pd->mats.size() * sizeof(OpenMat));
+        t.digests = (const uint4*)pd->digests;
+        t.nmats = (u32)pd->mats.size();
+        t.shift = shifts[k];
+        t.depth = depth;
+        t.tw = pd->total_width;
+        t.opened_base = opened_total;
+        t.proof_base = proof_total * 2;
+        opened_total += n_idx * pd->total_width;
+        proof_total += n_idx * depth;
+    }
+    size_t sz_t = n_trees * sizeof(MultiTree), sz_idx = n_idx * 8;
+    std::vector<uint8_t> host(sz_t + sz_idx);
+    memcpy(host.data(), mt.data(), sz_t);
+    memcpy(host.data() + sz_t, indices_host, sz_idx);
+    uint8_t* d_in = (uint8_t*)c.alloc(host.size());
+    u64* d_open = (u64*)c.alloc(std::max<u64>(opened_total * 8, 8));
+    uint4* d_proof = (uint4*)c.alloc(std::max<u64>(proof_total * 32, 32));
+    MSG_CUDA(cudaMemcpyAsync(d_in, host.data(), host.size(), cudaMemcpyHostToDevice, c.stream));
+    {
+        KLaunch kl(c, "k_open_multi");
+        k_open_multi<<<dim3((unsigned)n_idx, (unsigned)n_trees), 128, 0, c.stream>>>((const MultiTree*)d_in, (const u64*)(d_in + sz_t), d_open,
+                                                                                      d_proof);
+    }
+    MSG_CUDA(cudaGetLastError());
+    if (opened_total) MSG_CUDA(cudaMemcpyAsync(opened_host, d_open, opened_total * 8, cudaMemcpyDeviceToHost, c.stream));
+    if (proof_total) MSG_CUDA(cudaMemcpyAsync(proof_host, d_proof, proof_total * 32, cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    c.free(d_in);
+    c.free(d_open);
+    c.free(d_proof);
 }
 
 void mmcs_open_batch(Ctx& c, const msgpu_pdata* pd, const u64* indices_host, u64 n_idx, u64* opened_host,
                      uint8_t* proof_host) {
-    if (n_idx == 0) return;
-    u32 log_max = ilog2(pd->max_height);
-    for (u64 i = 0; i < n_idx; i++) MSG_REQUIRE(indices_host[i] < pd->max_height, "open_batch: index out of range");
-    std::vector<OpenMat> om;
-    u64 off = 0;
-    for (auto& m : pd->mats) {
-        om.push_back(OpenMat{m.ptr, (u32)m.width, log_max - ilog2(m.height), off});
-        off += m.width;
-    }
-    u64 tw = pd->total_width;
-    size_t sz_mats = om.size() * sizeof(OpenMat), sz_idx = n_idx * 8, sz_off = pd->layer_off.size() * 8;
-    OpenMat* d_mats = (OpenMat*)c.alloc(sz_mats);
-    u64* d_idx = (u64*)c.alloc(sz_idx);
-    u64* d_off = (u64*)c.alloc(sz_off);
-    u64* d_open = (u64*)c.alloc(std::max<u64>(n_idx * tw * 8, 8));
-    uint8_t* d_proof = (uint8_t*)c.alloc(std::max<u64>(n_idx * log_max * 32, 32));
-    MSG_CUDA(cudaMemcpyAsync(d_mats, om.data(), sz_mats, cudaMemcpyHostToDevice, c.stream));
-    MSG_CUDA(cudaMemcpyAsync(d_idx, indices_host, sz_idx, cudaMemcpyHostToDevice, c.stream));
-    MSG_CUDA(cudaMemcpyAsync(d_off, pd->layer_off.data(), sz_off, cudaMemcpyHostToDevice, c.stream));
-    if (tw) {
-        {
-            KLaunch kl(c, "k_open_rows");
-            k_open_rows<<<(unsigned)n_idx, 128, 0, c.stream>>>(d_mats, (u32)om.size(), d_idx, tw, d_open);
-        }
-        MSG_CUDA(cudaGetLastError());
-        MSG_CUDA(cudaMemcpyAsync(opened_host, d_open, n_idx * tw * 8, cudaMemcpyDeviceToHost, c.stream));
-    }
-    if (log_max) {
-        u64 total = n_idx * log_max * 2;
-        {
-            KLaunch kl(c, "k_open_proof");
-            k_open_proof<<<(unsigned)((total + 127) / 128), 128, 0, c.stream>>>((const uint4*)pd->digests, d_off, log_max,
-                                                                                d_idx, n_idx, (uint4*)d_proof);
-        }
-        MSG_CUDA(cudaGetLastError());
-        MSG_CUDA(cudaMemcpyAsync(proof_host, d_proof, n_idx * log_max * 32, cudaMemcpyDeviceToHost, c.stream));
-    }
-    c.sync();
-    c.free(d_mats);
-    c.free(d_idx);
-    c.free(d_off);
-    c.free(d_open);
-    c.free(d_proof);
+    const u32 shift = 0;
+    mmcs_open_multi(c, &pd, &shift, 1, indices_host, n_idx, opened_host, proof_host);
 }
 
 void pdata_destroy(msgpu_pdata* pd) {
     if (!pd) return;
     Ctx& c = *pd->ctx;
+    if (pd->d_desc) c.free(pd->d_desc);
     for (auto& m : pd->mats)
         if (m.owned && m.ptr) c.free(m.ptr);
     if (pd->digests) c.free(pd->digests);

@@ -17,6 +17,7 @@ struct msgpu_pdata {
     u64 max_height = 0;
     u64 total_width = 0;
     uint8_t root[32];
+    void* d_desc = nullptr;          // device copy of the opening descriptors (OpenMat[] then layer offsets), built with the tree
 };
 
 namespace msg {
@@ -24,5 +25,8 @@ namespace msg {
 void mmcs_build(Ctx& c, msgpu_pdata* pd);
 void mmcs_open_batch(Ctx& c, const msgpu_pdata* pd, const u64* indices_host, u64 n_idx, u64* opened_host,
                      uint8_t* proof_host);
+// Mmcs::open_batch of several trees in one launch: tree k is opened at indices[q] >> shifts[k]
+void mmcs_open_multi(Ctx& c, const msgpu_pdata* const* pds, const u32* shifts, u64 n_trees, const u64* indices_host, u64 n_idx,
+                     u64* opened_host, uint8_t* proof_host);
 void pdata_destroy(msgpu_pdata* pd);
 }  // namespace msg

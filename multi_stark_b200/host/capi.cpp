@@ -3,6 +3,7 @@
 #include "system.hpp"
 #include "program.hpp"
 #include "gpu_backend.hpp"
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -129,6 +130,9 @@ int msh_prove(msh_prover* p, const uint64_t* const* traces, const uint64_t* heig
             double total = 0;
             for (int i = 0; i < 5; i++) { stage_ms[i] = tm.ms[names[i]]; total += stage_ms[i]; }
             stage_ms[5] = total;
+        }
+        if (getenv("MSH_TRACE")) {
+            for (auto& kv : tm.ms) fprintf(stderr, "[msh] %-24s %8.3f ms\n", kv.first.c_str(), kv.second);
         }
         return 0;
     } catch (const std::exception& e) {

@@ -134,6 +134,53 @@ class GpuOpenDevice : public OpenDevice {
         return gpu_open_batch(ctx_, pd, pair_indices);
     }
 
+    void open_queries(const std::vector<size_t>& indices, const std::vector<unsigned>& round_shifts, size_t n_layers,
+                      std::vector<std::vector<BatchOpening>>& rounds_out, std::vector<std::vector<BatchOpening>>& layers_out) override {
+        std::vector<const msgpu_pdata*> trees(pds_.begin(), pds_.end());
+        std::vector<uint32_t> shifts(round_shifts.begin(), round_shifts.end());
+        for (size_t k = 0; k < n_layers; k++) {
+            const msgpu_pdata* pd = msgpu_fri_layer_pdata(op_, k);
+            if (!pd) throw GpuError("open: no such commit-phase layer");
+            trees.push_back(pd);
+            shifts.push_back((uint32_t)(k + 1));
+        }
+        size_t n = indices.size(), open_total = 0, proof_total = 0;
+        std::vector<std::vector<size_t>> widths(trees.size());
+        std::vector<size_t> depth(trees.size()), tw(trees.size());
+        for (size_t t = 0; t < trees.size(); t++) {
+            size_t nm = msgpu_pdata_num_matrices(trees[t]), maxh = 0;
+            for (size_t i = 0; i < nm; i++) {
+                uint64_t r = 0, c = 0;
+                gpu_check(msgpu_pdata_matrix(trees[t], i, nullptr, &r, &c));
+                widths[t].push_back((size_t)c);
+                tw[t] += (size_t)c;
+                maxh = std::max(maxh, (size_t)r);
+            }
+            depth[t] = log2_strict(maxh);
+            open_total += n * tw[t];
+            proof_total += n * depth[t] * 32;
+        }
+        std::vector<uint64_t> idx(indices.begin(), indices.end()), opened(std::max<size_t>(open_total, 1));
+        std::vector<uint8_t> proofs(std::max<size_t>(proof_total, 1));
+        gpu_check(msgpu_open_batch_multi(ctx_, trees.data(), shifts.data(), trees.size(), idx.data(), n, opened.data(), proofs.data()));
+        rounds_out.assign(round_shifts.size(), {});
+        layers_out.assign(n_layers, {});
+        size_t oo = 0, po = 0;
+        for (size_t t = 0; t < trees.size(); t++) {
+            std::vector<BatchOpening>& out = t < round_shifts.size() ? rounds_out[t] : layers_out[t - round_shifts.size()];
+            out.resize(n);
+            for (size_t q = 0; q < n; q++) {
+                for (size_t m = 0; m < widths[t].size(); m++) {
+                    std::vector<Fp> row(widths[t][m]);
+                    for (auto& v : row) v.v = opened[oo++];
+                    out[q].opened_values.push_back(std::move(row));
+                }
+                out[q].opening_proof.resize(depth[t]);
+                for (size_t l = 0; l < depth[t]; l++, po += 32) memcpy(out[q].opening_proof[l].data(), proofs.data() + po, 32);
+            }
+        }
+    }
+
   private:
     msgpu_ctx* ctx_;
     msgpu_open* op_ = nullptr;

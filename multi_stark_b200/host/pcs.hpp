@@ -11,6 +11,8 @@
 // PARITY UNPINNED against real p3 transcripts; the tests check it end to end with a restated verifier.
 #pragma once
 #include "proof.hpp"
+#include <chrono>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -49,6 +51,22 @@ struct OpenDevice {
     virtual std::vector<BatchOpening> open_round(size_t r, const std::vector<size_t>& indices) = 0;
     // Mmcs::open_batch of commit-phase layer `k` at every pair index: opened row = 2 extension values
     virtual std::vector<BatchOpening> open_layer(size_t k, const std::vector<size_t>& pair_indices) = 0;
+    // The whole query phase at once: round r is opened at indices[q] >> round_shifts[r], layer k at indices[q] >> (k + 1).
+    // rounds_out[r][q], layers_out[k][q]. A device backend overrides this with a single launch.
+    virtual void open_queries(const std::vector<size_t>& indices, const std::vector<unsigned>& round_shifts, size_t n_layers,
+                              std::vector<std::vector<BatchOpening>>& rounds_out, std::vector<std::vector<BatchOpening>>& layers_out) {
+        rounds_out.clear();
+        layers_out.clear();
+        std::vector<size_t> reduced(indices.size());
+        for (size_t r = 0; r < round_shifts.size(); r++) {
+            for (size_t q = 0; q < indices.size(); q++) reduced[q] = indices[q] >> round_shifts[r];
+            rounds_out.push_back(open_round(r, reduced));
+        }
+        for (size_t k = 0; k < n_layers; k++) {
+            for (size_t q = 0; q < indices.size(); q++) reduced[q] = indices[q] >> (k + 1);
+            layers_out.push_back(open_layer(k, reduced));
+        }
+    }
 };
 
 inline unsigned log2_exact(size_t n) { return log2_strict(n); }
@@ -70,16 +88,25 @@ inline std::vector<Fp2> idft_ext(const std::vector<Fp2>& evals) {
 
 // TwoAdicFriPcs::open. `rounds_meta[r]` = log2 of the tallest LDE of round r.
 inline void pcs_open(OpenDevice& dev, const std::vector<OpenRound>& rounds, const CommitmentParameters& cp, const FriParameters& fp,
-                     Challenger& ch, std::vector<OpenedValuesForRound>& opened, FriProof& proof) {
+                     Challenger& ch, std::vector<OpenedValuesForRound>& opened, FriProof& proof,
+                     std::map<std::string, double>* tm = nullptr) {
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* name) {
+        auto t1 = std::chrono::steady_clock::now();
+        if (tm) (*tm)[name] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+        t0 = t1;
+    };
     if (fp.max_log_arity != 1) throw std::runtime_error("only max_log_arity = 1 (binary folding) is supported, as in every reference configuration");
     opened = dev.evaluate();
     for (auto& round : opened)
         for (auto& mat : round)
             for (auto& pt : mat)
                 for (auto& y : pt) ch.observe(y);
+    lap("fri/evaluate");
     Fp2 alpha = ch.sample_ext();
     unsigned log_max_height = 0;
     dev.reduce(alpha, log_max_height);
+    lap("fri/reduce");
 
     // commit phase
     proof = FriProof();
@@ -92,6 +119,7 @@ inline void pcs_open(OpenDevice& dev, const std::vector<OpenRound>& rounds, cons
         Fp2 beta = ch.sample_ext();
         dev.fold(beta);
     }
+    lap("fri/commit_phase");
     // final polynomial: undo the bit reversal, inverse DFT, keep final_poly_len coefficients
     std::vector<Fp2> folded = dev.read_current();
     {
@@ -108,31 +136,30 @@ inline void pcs_open(OpenDevice& dev, const std::vector<OpenRound>& rounds, cons
     for (auto& c : proof.final_poly) ch.observe(c);
     proof.query_pow_witness = ch.grind(fp.query_proof_of_work_bits);
 
+    lap("fri/final_poly");
     // query phase: sample all indices (no observation happens in between), then open in batches
     std::vector<size_t> indices(fp.num_queries);
     for (auto& i : indices) i = ch.sample_bits(log_max_height);
     proof.query_proofs.assign(fp.num_queries, QueryProof());
-    for (size_t r = 0; r < rounds.size(); r++) {
-        unsigned log_h = log2_exact(rounds[r].data->max_height());
-        std::vector<size_t> reduced(indices.size());
-        for (size_t q = 0; q < indices.size(); q++) reduced[q] = indices[q] >> (log_max_height - log_h);
-        auto ops = dev.open_round(r, reduced);
-        for (size_t q = 0; q < indices.size(); q++) proof.query_proofs[q].input_proof.push_back(std::move(ops[q]));
-    }
+    std::vector<unsigned> round_shifts;
+    for (size_t r = 0; r < rounds.size(); r++) round_shifts.push_back(log_max_height - log2_exact(rounds[r].data->max_height()));
+    std::vector<std::vector<BatchOpening>> round_ops, layer_ops;
+    dev.open_queries(indices, round_shifts, proof.commit_phase_commits.size(), round_ops, layer_ops);
+    for (size_t r = 0; r < rounds.size(); r++)
+        for (size_t q = 0; q < indices.size(); q++) proof.query_proofs[q].input_proof.push_back(std::move(round_ops[r][q]));
     for (size_t k = 0; k < proof.commit_phase_commits.size(); k++) {
-        std::vector<size_t> pairs(indices.size());
-        for (size_t q = 0; q < indices.size(); q++) pairs[q] = (indices[q] >> k) >> 1;
-        auto ops = dev.open_layer(k, pairs);
         for (size_t q = 0; q < indices.size(); q++) {
             size_t index_i = indices[q] >> k, sib = (index_i ^ 1) & 1;
-            const std::vector<Fp>& row = ops[q].opened_values.at(0);
+            BatchOpening& bo = layer_ops[k][q];
+            const std::vector<Fp>& row = bo.opened_values.at(0);
             CommitPhaseProofStep step;
             step.log_arity = 1;
             step.sibling_values.push_back(Fp2(row[2 * sib], row[2 * sib + 1]));
-            step.opening_proof = std::move(ops[q].opening_proof);
+            step.opening_proof = std::move(bo.opening_proof);
             proof.query_proofs[q].commit_phase_openings.push_back(std::move(step));
         }
     }
+    lap("fri/queries");
 }
 
 }  // namespace msh

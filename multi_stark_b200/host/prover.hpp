@@ -186,7 +186,7 @@ class Prover {
         }
         std::unique_ptr<OpenDevice> dev = be_.open_begin(rounds);
         std::vector<OpenedValuesForRound> opened;
-        pcs_open(*dev, rounds, shape_.commitment, shape_.fri, ch, opened, proof.opening_proof);
+        pcs_open(*dev, rounds, shape_.commitment, shape_.fri, ch, opened, proof.opening_proof, tm ? &tm->ms : nullptr);
         dev.reset();
         proof.stage_1_opened_values = std::move(opened[0]);
         proof.stage_2_opened_values = std::move(opened[1]);
