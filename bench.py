@@ -230,6 +230,7 @@ def gpu_prove_leg(args, ms, ctx, steps, warmup, verify):
     launches = (ctx.launches - l0) // max(steps, 1)
     out = {"rows": 1 << args.log_rows, "ms": float(np.median(times)), "ms_min": float(np.min(times)), "steps": steps,
            "stages_ms": {k: float(np.median(v)) for k, v in stage_acc.items()}, "proof_bytes": len(proof),
+           "digest": __import__("hashlib").sha256(proof).hexdigest(),
            "h2d_bytes": int(byte.nbytes + add.nbytes + claims.nbytes), "gpu_launches": int(launches),
            "timing": "host wall clock around the call (host buffers in, proof bytes out)"}
     if verify:
@@ -301,6 +302,7 @@ def main():
     import torch
     import torch.distributed as dist
     import multi_stark_b200 as ms
+    from multi_stark_b200 import dist as msd
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -360,10 +362,7 @@ def main():
         ms_total = e0.elapsed_time(e1)
         prof = ctx.profile_end() if profile else None
         launches = ctx.launches - l0
-        if world > 1:
-            t = torch.tensor([ms_total], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_total = float(t.item())
+        ms_total = msd.max_over_ranks(ms_total)  # the job takes as long as its slowest rank
         barrier()
         return ms_total, launches, prof, out
 
@@ -435,10 +434,9 @@ def main():
         barrier()
         prove = gpu_prove_leg(args, ms, ctx, steps=max(3, min(args.steps, 10)), warmup=2, verify=(rank == 0))
         if world > 1:
-            t = torch.tensor([prove["ms"]], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            prove["ms_max_over_ranks"] = float(t.item())
-            prove["proofs_per_s_all_ranks"] = world * 1e3 / float(t.item())
+            prove["ms_max_over_ranks"] = msd.max_over_ranks(prove["ms"])
+            prove["proofs_per_s_all_ranks"] = world * 1e3 / prove["ms_max_over_ranks"]
+            prove["proof_digests"] = [d.hex()[:16] for d in msd.gather_digests([bytes.fromhex(prove["digest"])])]
         if cpu is not None:
             prove["cpu"] = cpu_prove_time(args, min(args.log_rows, args.cpu_prove_log_rows))
         barrier()
