@@ -216,6 +216,9 @@ def gpu_prove_leg(args, ms, ctx, steps, warmup, verify):
     system = ms.System("u32_add", **prove_params(args))
     prover = ms.Prover(ctx, system)  # System::new: programs + preprocessed commitment (setup, untimed like Criterion's setup)
     byte, add, claims = ms.u32_add_workload(1 << args.log_rows)
+    rk = int(os.environ.get("RANK", "0"))
+    if rk:  # every rank proves its own instance: the same additions in a rotated row order
+        add, claims = np.roll(add, rk, axis=0), np.roll(claims, rk, axis=0)
     byte, add, claims = ctx.pinned_copy(byte), ctx.pinned_copy(add), ctx.pinned_copy(claims)
     for _ in range(warmup):
         proof = prover.prove([byte, add], claims)
@@ -311,6 +314,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: libmsgpu has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner out of stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     stages = u32_add_workload(args.log_rows, seed=rank)
