@@ -146,6 +146,20 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def step_counters():
+    """ncu counters of one bench step (tools/one_step.py + tools/ncu_inst_counts.py): data-independent instruction counts
+    and DRAM traffic per stage, committed under profiles/."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "step_counters_*.json")))
+    if not files:
+        return None, None
+    try:
+        with open(files[-1]) as f:
+            return json.load(f), os.path.basename(files[-1])
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -412,10 +426,32 @@ def main():
     dom = max(stages_out, key=lambda s: s["ms_per_step"]) if stages_out else None
     roofline = None
     if dom:
+        # integer roofline: both stages are bound by the INT32 pipes, not by HBM. Peak = live microbenchmark
+        # (msgpu_measure_int_peak); instructions per step = ncu counters of the same step (data independent).
+        ipk = ctx.measure_int_peak()
+        counters, counters_file = step_counters()
+        default_shape = args.log_rows == 20 and args.log_blowup == 1
+        for st in stages_out:
+            c = counters["stages"].get(st["stage"]) if counters and default_shape else None
+            if c:
+                rate = c["thread_inst_per_step"] / (st["ms_per_step"] / 1e3) / 1e9
+                st["int_pipe"] = {"thread_inst_per_step": c["thread_inst_per_step"], "achieved_ginst_s": rate,
+                                  "frac_of_mixed_peak": rate / ipk["mixed"]}
+                st["dram_traffic_bytes_per_step"] = c["dram_bytes_per_step"]
+        traffic = dom.get("dram_traffic_bytes_per_step")
         roofline = {"bound": "hbm", "kernel": "%s stage (%d launches/step)" % (dom["stage"], dom["launches_per_step"]),
-                    "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": None,
+                    "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                    "traffic": traffic / dom["launches_per_step"] if traffic else None,
+                    "traffic_note": "dram read+write bytes per launch (ncu, %s); achieved/frac use ALGORITHMIC bytes per launch" % counters_file,
                     "peak_source": peak_src, "algorithmic_bytes_per_step": dom["algorithmic_bytes"],
-                    "share_of_step": dom["ms_per_step"] / ms_step, "stages": stages_out, "kernels": kernels}
+                    "algorithmic_bytes_per_launch": dom["algorithmic_bytes"] / dom["launches_per_step"],
+                    "share_of_step": dom["ms_per_step"] / ms_step,
+                    "binding_resource": "INT32 pipes (ALU + FMA-heavy): see int_pipe; HBM is not the bound for this stage",
+                    "int_pipe": {"unit": "G thread-inst/s", "peak_alu_only": ipk["alu"], "peak_imad_only": ipk["imad"],
+                                 "peak_mixed": ipk["mixed"], "peak_source": "msgpu_measure_int_peak, live, CUDA events",
+                                 "achieved": dom.get("int_pipe", {}).get("achieved_ginst_s"),
+                                 "frac": dom.get("int_pipe", {}).get("frac_of_mixed_peak")},
+                    "stages": stages_out, "kernels": kernels}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -236,6 +236,12 @@ void msgpu_open_free(msgpu_open* op);
  * 2^20 claims. The digest is by definition the same as the CPU's. */
 int msgpu_blake3_hash(msgpu_ctx* ctx, const uint8_t* data, uint64_t len, uint8_t* out32);
 
+/* ---- measurement support ------------------------------------------------------------------------
+ * Integer-pipe peaks of this GPU in G thread-instructions / s, from dependency-free streams timed with CUDA events:
+ * out3[0] ALU pipe only (LOP3 + SHF), out3[1] FMA pipe only (IMAD), out3[2] both pipes 1 : 1. The NTT and BLAKE3
+ * kernels are bound by these pipes; bench.py reports them next to the HBM roofline. */
+int msgpu_measure_int_peak(msgpu_ctx* ctx, double* out3);
+
 /* ---- test hooks --------------------------------------------------------------------------------- */
 /* raw 7-round BLAKE3 compression of a 16-word state and 16 message words (known-answer vector of
  * reference src/test_circuits/blake3.rs:2646-2746); host pointers */

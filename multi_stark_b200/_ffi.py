@@ -77,6 +77,7 @@ SIGNATURES = {
     "msgpu_fri_num_layers": (C.c_uint64, [C.c_void_p]),
     "msgpu_fri_layer_pdata": (C.c_void_p, [C.c_void_p, C.c_uint64]),
     "msgpu_open_free": (None, [C.c_void_p]),
+    "msgpu_measure_int_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "msgpu_blake3_compress_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

@@ -78,6 +78,12 @@ class GpuContext:
     def free(self, ptr):
         check(self.L.msgpu_free(self.h, C.c_void_p(ptr)))
 
+    def measure_int_peak(self):
+        """msgpu_measure_int_peak: {"alu", "imad", "mixed"} in G thread-instructions / s."""
+        out = (C.c_double * 3)()
+        check(self.L.msgpu_measure_int_peak(self.h, out))
+        return {"alu": out[0], "imad": out[1], "mixed": out[2]}
+
     def pinned_empty(self, shape, dtype=np.uint64):
         """numpy array over page-locked host memory (msgpu_host_alloc): H2D copies from it run at full PCIe rate.
         The memory lives until the context is closed."""
