@@ -56,48 +56,83 @@ __global__ void __launch_bounds__(256) k_inv_denoms(u64* invden, u32 log_h, gl::
     }
 }
 
-// partial[cta][c][p] = sum over the CTA's rows of M[i][c] * x_i * invden_p[i]   (i < h, the low coset)
+// Barycentric evaluation on the coset GENERATOR * H_h (the first h stored rows), per column c and point z_p:
+//   P_c(z) = (z^h - g^h) / (h g^h) * sum_i M[i][c] * x_i / (z - x_i),   and  x_i / (z - x_i) = z / (z - x_i) - 1,
+// so only  S1[c] = sum_i M[i][c]  (base field) and  S2[c][p] = sum_i M[i][c] * invden_p[i]  (extension) are needed:
+// the sum is then z * S2 - S1. Terms are accumulated lazily (160-bit, gl::acc_mac) and reduced once per thread.
+// partial[cta][c][0] = (S1, 0), partial[cta][c][1 + p] = S2 over the CTA's rows.
 constexpr int kMaxPts = 4;
 struct BaryParams {
     const u64* M;
     const u64* invden[kMaxPts];
     u64* partial;
-    gl::PowTable xtab;  // GENERATOR * w_h^e
     u64 h;
-    u32 w, log_h, npts, c0, wc;  // this launch covers columns [c0, c0 + wc)
-    u32 rows_per_step;
+    u32 w, c0, wc;  // this launch covers columns [c0, c0 + wc)
+    u32 rows_per_step, tile_rows;
 };
+// Tiles of tile_rows rows are staged through shared memory with back-to-back coalesced loads (enough bytes in flight to
+// keep HBM busy), then thread (column c, row lane) accumulates its rows of the tile.
+template <int NPTS>
 __global__ void __launch_bounds__(256) k_bary_partial(BaryParams p) {
     extern __shared__ u64 sm_b[];
     const u32 t = threadIdx.x;
-    const u32 active = p.rows_per_step * p.wc;
-    gl::e2 acc[kMaxPts];
-    for (u32 k = 0; k < kMaxPts; k++) acc[k] = gl::e2_make(0, 0);
-    const u32 c = t % p.wc, lane_row = t / p.wc;
-    if (t < active) {
-        for (u64 r = (u64)blockIdx.x * p.rows_per_step + lane_row; r < p.h; r += (u64)gridDim.x * p.rows_per_step) {
-            u64 x = gl::pow_lookup(p.xtab, gl::rev_bits((u32)r, p.log_h));
-            u64 mx = gl::mul(p.M[r * p.w + p.c0 + c], x);
-            for (u32 k = 0; k < p.npts; k++) {
-                gl::e2 d = gl::e2_make(p.invden[k][2 * r], p.invden[k][2 * r + 1]);
-                acc[k] = gl::e2_add(acc[k], gl::e2_mul_base(d, mx));
+    const u32 TR = p.tile_rows, wc = p.wc;
+    u64* tile = sm_b;                                                       // [TR][wc]
+    ulonglong2* dd = reinterpret_cast<ulonglong2*>(sm_b + (size_t)TR * wc);  // [TR][NPTS]
+    const u32 active = p.rows_per_step * wc;
+    const u32 c = t % wc, lane_row = t / wc;
+    gl::Acc160 acc[2 * NPTS];
+#pragma unroll
+    for (int k = 0; k < 2 * NPTS; k++) acc[k] = gl::acc_zero();
+    u64 s1 = 0;
+    const bool contiguous = (wc == p.w);
+    for (u64 row0 = (u64)blockIdx.x * TR; row0 < p.h; row0 += (u64)gridDim.x * TR) {
+        const u32 nrows = (u32)min((u64)TR, p.h - row0);
+        if (contiguous) {
+            const u64* src = p.M + row0 * p.w;
+            for (u32 e = t; e < nrows * wc; e += 256) tile[e] = src[e];
+        } else {
+            for (u32 e = t; e < nrows * wc; e += 256) tile[e] = p.M[(row0 + e / wc) * p.w + p.c0 + e % wc];
+        }
+        for (u32 e = t; e < nrows * NPTS; e += 256)
+            dd[e] = *reinterpret_cast<const ulonglong2*>(p.invden[e % NPTS] + 2 * (row0 + e / NPTS));
+        __syncthreads();
+        if (t < active) {
+            for (u32 r = lane_row; r < nrows; r += p.rows_per_step) {
+                const u64 m = tile[r * wc + c];
+                s1 = gl::gf::add(s1, m);
+#pragma unroll
+                for (int k = 0; k < NPTS; k++) {
+                    const ulonglong2 d = dd[r * NPTS + k];
+                    gl::acc_mac(acc[2 * k], m, d.x);
+                    gl::acc_mac(acc[2 * k + 1], m, d.y);
+                }
             }
         }
+        __syncthreads();
     }
-    // reduce over the row lanes of each column
-    u64* sm = sm_b;  // [rows_per_step][wc][npts][2]
-    if (t < active)
-        for (u32 k = 0; k < p.npts; k++) {
-            sm[((lane_row * p.wc + c) * p.npts + k) * 2] = acc[k].a;
-            sm[((lane_row * p.wc + c) * p.npts + k) * 2 + 1] = acc[k].b;
+    // reduce over the row lanes of each column (the tile buffer is free again)
+    constexpr u32 nslots = NPTS + 1;
+    u64* sm = sm_b;  // [rows_per_step][wc][nslots][2]
+    if (t < active) {
+        u64* o = sm + ((size_t)(lane_row * wc + c) * nslots) * 2;
+        o[0] = s1;
+        o[1] = 0;
+#pragma unroll
+        for (int k = 0; k < NPTS; k++) {
+            o[2 * (k + 1)] = gl::acc_reduce(acc[2 * k]);
+            o[2 * (k + 1) + 1] = gl::acc_reduce(acc[2 * k + 1]);
         }
+    }
     __syncthreads();
-    if (t < p.wc) {
-        for (u32 k = 0; k < p.npts; k++) {
+    if (t < wc) {
+        for (u32 k = 0; k < nslots; k++) {
             gl::e2 s = gl::e2_make(0, 0);
-            for (u32 l = 0; l < p.rows_per_step; l++)
-                s = gl::e2_add(s, gl::e2_make(sm[((l * p.wc + t) * p.npts + k) * 2], sm[((l * p.wc + t) * p.npts + k) * 2 + 1]));
-            u64* o = p.partial + (((u64)blockIdx.x * p.wc + t) * p.npts + k) * 2;
+            for (u32 l = 0; l < p.rows_per_step; l++) {
+                const u64* o = sm + ((size_t)(l * wc + t) * nslots + k) * 2;
+                s = gl::e2_add(s, gl::e2_make(o[0], o[1]));
+            }
+            u64* o = p.partial + (((u64)blockIdx.x * wc + t) * nslots + k) * 2;
             o[0] = s.a;
             o[1] = s.b;
         }
@@ -128,12 +163,13 @@ __global__ void __launch_bounds__(kRedRows) k_reduce_openings(ReduceParams p) {
     __syncthreads();
     if (threadIdx.x >= nrows) return;
     const u64* row = tile + (size_t)threadIdx.x * pitch;
-    u64 m0 = 0, m1 = 0;
+    gl::Acc160 a0 = gl::acc_zero(), a1 = gl::acc_zero();
     for (u32 c = 0; c < p.w; c++) {
         u64 v = row[c];
-        m0 = gl::add(m0, gl::mul(v, ap[2 * c]));
-        m1 = gl::add(m1, gl::mul(v, ap[2 * c + 1]));
+        gl::acc_mac(a0, v, ap[2 * c]);
+        gl::acc_mac(a1, v, ap[2 * c + 1]);
     }
+    const u64 m0 = gl::acc_reduce(a0), m1 = gl::acc_reduce(a1);
     const u64 i = row0 + threadIdx.x;
     gl::e2 acc = gl::e2_make(p.ro[2 * i], p.ro[2 * i + 1]);
     for (u32 k = 0; k < p.npts; k++) {
@@ -261,25 +297,29 @@ static void evaluate_all(Ctx& c, msgpu_open* op) {
                     bp.M = m.ptr;
                     bp.h = h;
                     bp.w = (u32)m.width;
-                    bp.log_h = log_h;
-                    bp.npts = npts;
-                    bp.c0 = c0;
+                                    bp.c0 = c0;
                     bp.wc = (u32)std::min<u64>(256, m.width - c0);
                     bp.rows_per_step = 256 / bp.wc;
-                    bp.xtab = lde_x_table(c, log_h);
                     for (u32 k = 0; k < npts; k++) bp.invden[k] = find_invden(op, m.points[p0 + k], m.log_h);
-                    u64 want = (h + bp.rows_per_step - 1) / bp.rows_per_step;
+                    bp.tile_rows = (u32)std::min<u64>(256, std::max<u64>(8, 4096 / bp.wc));
+                    u64 want = (h + bp.tile_rows - 1) / bp.tile_rows;
                     u32 ctas = (u32)std::min<u64>(want, (u64)c.sm_count * 4);
                     Pending pd{&m, nullptr, {}, ctas, npts, c0, bp.wc, p0};
-                    pd.d_partial = (u64*)c.alloc((size_t)ctas * bp.wc * npts * 16);
+                    pd.d_partial = (u64*)c.alloc((size_t)ctas * bp.wc * (npts + 1) * 16);
                     bp.partial = pd.d_partial;
-                    size_t smem = (size_t)bp.rows_per_step * bp.wc * npts * 16;
+                    size_t smem = std::max((size_t)bp.rows_per_step * bp.wc * (npts + 1) * 16,
+                                           (size_t)bp.tile_rows * (bp.wc * 8 + npts * 16));
                     {
                         KLaunch kl(c, "k_bary_partial");
-                        k_bary_partial<<<ctas, 256, smem, c.stream>>>(bp);
+                        switch (npts) {
+                            case 1: k_bary_partial<1><<<ctas, 256, smem, c.stream>>>(bp); break;
+                            case 2: k_bary_partial<2><<<ctas, 256, smem, c.stream>>>(bp); break;
+                            case 3: k_bary_partial<3><<<ctas, 256, smem, c.stream>>>(bp); break;
+                            default: k_bary_partial<4><<<ctas, 256, smem, c.stream>>>(bp); break;
+                        }
                     }
                     MSG_CUDA(cudaGetLastError());
-                    pd.h_partial.resize((size_t)ctas * bp.wc * npts * 2);
+                    pd.h_partial.resize((size_t)ctas * bp.wc * (npts + 1) * 2);
                     MSG_CUDA(cudaMemcpyAsync(pd.h_partial.data(), pd.d_partial, pd.h_partial.size() * 8, cudaMemcpyDeviceToHost, c.stream));
                     pend.push_back(std::move(pd));
                 }
@@ -290,19 +330,22 @@ static void evaluate_all(Ctx& c, msgpu_open* op) {
         c.free(pd.d_partial);
         auto& m = *pd.m;
         u32 log_h = m.log_h - op->log_blowup;
-        // y = sum * (z^h - g^h) / (h * g^h),  g = GENERATOR
+        // y = (z * S2 - S1) * (z^h - g^h) / (h * g^h),  g = GENERATOR
         msh::Fp shift_pow = msh::Fp(msh::GL_GENERATOR).exp_power_of_2(log_h);
         msh::Fp denom_inv = (shift_pow * msh::Fp((msh::u64)1 << log_h)).inverse();
-        for (u32 k = 0; k < pd.npts; k++) {
-            msh::Fp2 z = m.points[pd.p0 + k];
-            msh::Fp2 scale = (z.exp_power_of_2(log_h) - shift_pow) * denom_inv;
-            for (u32 cc = 0; cc < pd.wc; cc++) {
-                msh::Fp2 s;
+        const u32 nslots = pd.npts + 1;
+        for (u32 cc = 0; cc < pd.wc; cc++) {
+            msh::Fp s1;
+            for (u32 b = 0; b < pd.ctas; b++) s1 += msh::Fp(pd.h_partial[(((size_t)b * pd.wc + cc) * nslots) * 2]);
+            for (u32 k = 0; k < pd.npts; k++) {
+                msh::Fp2 z = m.points[pd.p0 + k];
+                msh::Fp2 scale = (z.exp_power_of_2(log_h) - shift_pow) * denom_inv;
+                msh::Fp2 s2;
                 for (u32 b = 0; b < pd.ctas; b++) {
-                    size_t o = (((size_t)b * pd.wc + cc) * pd.npts + k) * 2;
-                    s += msh::Fp2(msh::Fp(pd.h_partial[o]), msh::Fp(pd.h_partial[o + 1]));
+                    size_t o = (((size_t)b * pd.wc + cc) * nslots + k + 1) * 2;
+                    s2 += msh::Fp2(msh::Fp(pd.h_partial[o]), msh::Fp(pd.h_partial[o + 1]));
                 }
-                m.values[pd.p0 + k][pd.c0 + cc] = s * scale;
+                m.values[pd.p0 + k][pd.c0 + cc] = (z * s2 - s1) * scale;
             }
         }
     }
