@@ -71,8 +71,9 @@ __device__ __forceinline__ u64 sub_lazy(u64 a, u64 b) {
     return pack(r0, r1);
 }
 
-// a, b canonical -> canonical.
-__device__ __forceinline__ u64 add(u64 a, u64 b) { return canon(add_lazy(a, b)); }
+// a, b canonical -> canonical: a + b = a - (p - b), one borrow fix-up (7 instructions; p - b is in (0, p], which sub_lazy
+// tolerates)
+__device__ __forceinline__ u64 add(u64 a, u64 b) { return sub_lazy(a, GLD_P - b); }
 // a, b canonical -> canonical (a - b + p < 2^64 and < p after the fix, so sub_lazy is already canonical)
 __device__ __forceinline__ u64 sub(u64 a, u64 b) { return sub_lazy(a, b); }
 __device__ __forceinline__ u64 neg(u64 a) { return a ? GLD_P - a : 0; }
@@ -103,9 +104,14 @@ __device__ __forceinline__ u64 reduce128_lazy(u64 lo, u64 hi) {
         : "r"(l0), "r"(l1), "r"(hl), "r"(hh));
     return pack(r0, r1);
 }
-__device__ __forceinline__ u64 reduce128(u64 lo, u64 hi) { return canon(reduce128_lazy(lo, hi)); }
-// any u64 operands (not necessarily canonical) -> canonical
-__device__ __forceinline__ u64 mul(u64 a, u64 b) { return reduce128(a * b, __umul64hi(a, b)); }
+namespace gf {
+__device__ __forceinline__ u64 reduce128(u64 lo, u64 hi);
+}
+// any u64 operands (not necessarily canonical) -> canonical (26 instructions: one 128-bit product, lean reduction)
+__device__ __forceinline__ u64 mul(u64 a, u64 b) {
+    unsigned __int128 pr = (unsigned __int128)a * b;
+    return gf::reduce128((u64)pr, (u64)(pr >> 64));
+}
 // any u64 operands -> some congruent u64
 __device__ __forceinline__ u64 mul_lazy(u64 a, u64 b) { return reduce128_lazy(a * b, __umul64hi(a, b)); }
 __device__ __forceinline__ u64 sqr(u64 a) { return mul(a, a); }

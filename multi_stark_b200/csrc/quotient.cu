@@ -270,12 +270,13 @@ __global__ void __launch_bounds__(128) k_quotient_eval(QuotParams p) {
     u64 slots[NSLOT];
     run_program<NSLOT>(p.prog, p.n_instr, slots, cx);
 
-    u64 acc0 = 0, acc1 = 0;
+    // alpha-fold with lazy 160-bit accumulation: one reduction per coordinate at the end
+    gl::Acc160 fa0 = gl::acc_zero(), fa1 = gl::acc_zero();
     u32 ci = 0;
     for (u32 j = 0; j < p.n_zeros; j++, ci++) {
         u64 v = slots[p.zero_slots[j]];
-        acc0 = gl::add(acc0, gl::mul(v, __ldg(p.apow + 2 * ci)));
-        acc1 = gl::add(acc1, gl::mul(v, __ldg(p.apow + 2 * ci + 1)));
+        gl::acc_mac(fa0, v, __ldg(p.apow + 2 * ci));
+        gl::acc_mac(fa1, v, __ldg(p.apow + 2 * ci + 1));
     }
     // logUp constraint values (src/lookup.rs:167-208)
     const u64* s2c = cx.rows[2][0];
@@ -283,8 +284,8 @@ __global__ void __launch_bounds__(128) k_quotient_eval(QuotParams p) {
     const gl::e2 beta = gl::e2_make(p.publics[0], p.publics[1]), gamma = gl::e2_make(p.publics[2], p.publics[3]);
     const gl::e2 inj = gl::e2_make(gl::mul(cx.last, p.delta[0]), gl::mul(cx.last, p.delta[1]));
     auto fold = [&](u64 v) {
-        acc0 = gl::add(acc0, gl::mul(v, __ldg(p.apow + 2 * ci)));
-        acc1 = gl::add(acc1, gl::mul(v, __ldg(p.apow + 2 * ci + 1)));
+        gl::acc_mac(fa0, v, __ldg(p.apow + 2 * ci));
+        gl::acc_mac(fa1, v, __ldg(p.apow + 2 * ci + 1));
         ci++;
     };
     if (p.n_lookups == 0) {
@@ -306,8 +307,8 @@ __global__ void __launch_bounds__(128) k_quotient_eval(QuotParams p) {
         }
     }
     const u64 iv = p.inv_zh[i & ((1ull << p.log_q) - 1)];
-    p.out[2 * i] = gl::mul(acc0, iv);
-    p.out[2 * i + 1] = gl::mul(acc1, iv);
+    p.out[2 * i] = gl::mul(gl::acc_reduce(fa0), iv);
+    p.out[2 * i + 1] = gl::mul(gl::acc_reduce(fa1), iv);
 }
 
 // out[r][k*d + c] = S[rev((N - (k*n + r)) mod N)][c] * weights[k]     (src/prover.rs:659-677)
