@@ -5,8 +5,8 @@ src/types.rs:82-85,199-223; src/config.rs:64-123) over the C ABI of libmsgpu.so 
 There is no CPU fallback: importing works without a GPU (so the ABI can be checked), but every
 compute call needs a CUDA device and raises `MsgpuError` otherwise."""
 from ._ffi import MsgpuError, lib, lib_path  # noqa: F401
-from .pcs import GpuContext, GpuDft, GpuMmcs, GpuPcs, ProverData  # noqa: F401
-from .system import Program, Prover, System, claims_accumulator, fib_trace, shifted_quotient_slices, u32_add_workload  # noqa: F401
+from .pcs import Challenger, GpuContext, GpuDft, GpuMmcs, GpuPcs, ProverData, pcs_open  # noqa: F401
+from .system import Program, Prover, System, claims_accumulator, fib_trace, shifted_quotient_slices, u32_add_workload, wide_trace  # noqa: F401
 
 P = 2**64 - 2**32 + 1
 GENERATOR = 7

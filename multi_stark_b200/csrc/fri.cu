@@ -147,30 +147,46 @@ struct ReduceParams {
     u64* ro;
     u64 H;
     u64 aoff[kMaxPts][2], yred[kMaxPts][2];
-    u32 w, npts;
+    u32 w, npts, tile_rows;
 };
-constexpr int kRedRows = 128;
-__global__ void __launch_bounds__(kRedRows) k_reduce_openings(ReduceParams p) {
+constexpr int kRedThreads = 128;
+// A tile of tile_rows rows (power of two <= 128) is staged in shared memory; 128 / tile_rows lanes share a row, each
+// accumulating the columns c = lane (mod lanes) lazily; the lanes' partial dot products are combined with shuffles.
+__global__ void __launch_bounds__(kRedThreads) k_reduce_openings(ReduceParams p) {
     extern __shared__ u64 sm_r[];
+    const u32 TR = p.tile_rows, tpr = kRedThreads / TR;
     const u32 pitch = p.w | 1;
-    u64* tile = sm_r;                          // [kRedRows][pitch]
-    u64* ap = sm_r + (size_t)kRedRows * pitch;  // [w][2]
-    const u64 row0 = (u64)blockIdx.x * kRedRows;
-    const u32 nrows = (u32)min((u64)kRedRows, p.H - row0);
+    u64* tile = sm_r;                     // [TR][pitch]
+    u64* ap = sm_r + (size_t)TR * pitch;  // [w][2]
+    const u64 row0 = (u64)blockIdx.x * TR;
+    const u32 nrows = (u32)min((u64)TR, p.H - row0);
     for (u32 e = threadIdx.x; e < 2 * p.w; e += blockDim.x) ap[e] = p.apow[e];
     const u64* src = p.M + row0 * p.w;
-    for (u32 e = threadIdx.x; e < nrows * p.w; e += blockDim.x) tile[(e / p.w) * pitch + e % p.w] = src[e];
-    __syncthreads();
-    if (threadIdx.x >= nrows) return;
-    const u64* row = tile + (size_t)threadIdx.x * pitch;
-    gl::Acc160 a0 = gl::acc_zero(), a1 = gl::acc_zero();
-    for (u32 c = 0; c < p.w; c++) {
-        u64 v = row[c];
-        gl::acc_mac(a0, v, ap[2 * c]);
-        gl::acc_mac(a1, v, ap[2 * c + 1]);
+    if (p.w == pitch) {
+        for (u32 e = threadIdx.x; e < nrows * p.w; e += blockDim.x) tile[e] = src[e];
+    } else {
+        for (u32 e = threadIdx.x; e < nrows * p.w; e += blockDim.x) tile[(e / p.w) * pitch + e % p.w] = src[e];
     }
-    const u64 m0 = gl::acc_reduce(a0), m1 = gl::acc_reduce(a1);
-    const u64 i = row0 + threadIdx.x;
+    __syncthreads();
+    const u32 r = threadIdx.x / tpr, lane = threadIdx.x % tpr;  // tpr divides 32: a row's lanes sit in one warp
+    const bool live = r < nrows;
+    gl::Acc160 a0 = gl::acc_zero(), a1 = gl::acc_zero();
+    if (live) {
+        const u64* row = tile + (size_t)r * pitch;
+        for (u32 c = lane; c < p.w; c += tpr) {
+            u64 v = row[c];
+            gl::acc_mac(a0, v, ap[2 * c]);
+            gl::acc_mac(a1, v, ap[2 * c + 1]);
+        }
+    }
+    u64 m0 = gl::acc_reduce(a0), m1 = gl::acc_reduce(a1);
+    for (u32 d = 1; d < tpr; d <<= 1) {  // tpr is a power of two <= 32 (tile_rows >= 4) or the row spans whole warps
+        u64 o0 = __shfl_xor_sync(0xffffffffu, m0, d), o1 = __shfl_xor_sync(0xffffffffu, m1, d);
+        m0 = gl::add(m0, o0);
+        m1 = gl::add(m1, o1);
+    }
+    if (!live || lane != 0) return;
+    const u64 i = row0 + r;
     gl::e2 acc = gl::e2_make(p.ro[2 * i], p.ro[2 * i + 1]);
     for (u32 k = 0; k < p.npts; k++) {
         gl::e2 diff = gl::e2_make(gl::sub(p.yred[k][0], m0), gl::sub(p.yred[k][1], m1));
@@ -396,11 +412,16 @@ static void reduce_all(Ctx& c, msgpu_open* op, msh::Fp2 alpha) {
                     rp.yred[k][0] = yred.c[0].v; rp.yred[k][1] = yred.c[1].v;
                     num_reduced[lh] += m.width;
                 }
-                size_t smem = ((size_t)kRedRows * (m.width | 1) + 2 * m.width) * 8;
-                MSG_REQUIRE(smem <= 200 * 1024, "open: matrix too wide for the reduced-openings kernel");
+                // rows per tile: the largest power of two <= 128 whose tile fits 64 KB; at least 4 so that the lanes sharing
+                // a row (128 / tile_rows <= 32) sit in one warp
+                u32 tr = 128;
+                while (tr > 4 && (size_t)tr * (m.width | 1) * 8 > 64 * 1024) tr >>= 1;
+                rp.tile_rows = tr;
+                size_t smem = ((size_t)tr * (m.width | 1) + 2 * m.width) * 8;
+                MSG_REQUIRE(smem <= 200 * 1024, "open: matrix too wide for the reduced-openings kernel (more than ~5000 columns)");
                 {
                     KLaunch kl(c, "k_reduce_openings");
-                    k_reduce_openings<<<(unsigned)((m.height + kRedRows - 1) / kRedRows), kRedRows, smem, c.stream>>>(rp);
+                    k_reduce_openings<<<(unsigned)((m.height + tr - 1) / tr), kRedThreads, smem, c.stream>>>(rp);
                 }
                 MSG_CUDA(cudaGetLastError());
             }

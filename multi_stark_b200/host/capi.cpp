@@ -3,6 +3,7 @@
 #include "system.hpp"
 #include "program.hpp"
 #include "gpu_backend.hpp"
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -72,6 +73,7 @@ void msh_u32add_workload(uint64_t num_adds, uint64_t* byte_trace_out, uint64_t* 
         for (size_t i = 0; i < w.claims.size(); i++)
             for (int k = 0; k < 4; k++) claims_out[4 * i + k] = w.claims[i][k].v;
 }
+void msh_wide_trace(uint64_t row0, uint64_t rows, uint64_t width, uint64_t* out) { circuits::wide_cubic_fill(out, row0, rows, width); }
 void msh_fib_trace(uint64_t rows, uint64_t* out) {
     Matrix m = circuits::fib_cubic_trace(rows);
     for (size_t i = 0; i < m.values.size(); i++) out[i] = m.values[i].v;
@@ -141,5 +143,82 @@ int msh_prove(msh_prover* p, const uint64_t* const* traces, const uint64_t* heig
     }
 }
 void msh_bytes_free(uint8_t* b) { free(b); }
+
+// ---- standalone PCS use (examples/pcs_example.rs): the transcript object and Pcs::open ------------------------------
+struct msh_challenger {
+    Challenger ch;
+    CommitmentParameters cp;
+    FriParameters fp;
+};
+// GoldilocksBlake3Config::initialise_challenger (src/types.rs:118-130,152-154)
+msh_challenger* msh_challenger_create(uint32_t log_blowup, uint32_t log_final_poly_len, uint32_t max_log_arity, uint32_t num_queries,
+                                      uint32_t commit_pow_bits, uint32_t query_pow_bits) {
+    auto c = std::make_unique<msh_challenger>();
+    c->cp.log_blowup = log_blowup;
+    c->fp.log_final_poly_len = log_final_poly_len;
+    c->fp.max_log_arity = max_log_arity;
+    c->fp.num_queries = num_queries;
+    c->fp.commit_proof_of_work_bits = commit_pow_bits;
+    c->fp.query_proof_of_work_bits = query_pow_bits;
+    c->ch = Challenger::for_config(c->cp, c->fp);
+    return c.release();
+}
+void msh_challenger_free(msh_challenger* c) { delete c; }
+void msh_challenger_observe_digest(msh_challenger* c, const uint8_t* d32) {
+    Digest d;
+    memcpy(d.data(), d32, 32);
+    c->ch.observe(d);
+}
+void msh_challenger_observe_values(msh_challenger* c, const uint64_t* v, uint64_t n) {
+    for (uint64_t i = 0; i < n; i++) c->ch.observe(Fp(v[i]));
+}
+void msh_challenger_sample_ext(msh_challenger* c, uint64_t* out2) {
+    Fp2 e = c->ch.sample_ext();
+    out2[0] = e.c[0].v;
+    out2[1] = e.c[1].v;
+}
+
+// Pcs::open (call shape of src/prover.rs:580 and examples/pcs_example.rs:85-90): rounds of prover data with, per matrix,
+// its opening points (n_points / points as in msgpu_open_begin). out = pcs_open_to_bytes (host/pcs.hpp).
+// ms5 (optional): evaluate+begin, reduce, commit phase, final poly, queries.
+int msh_pcs_open(msgpu_ctx* ctx, msh_challenger* c, uint64_t n_rounds, msgpu_pdata* const* pds, const uint64_t* n_points,
+                 const uint64_t* points, uint8_t** out, uint64_t* out_len, double* ms5) {
+    try {
+        std::vector<std::unique_ptr<GpuPcsHandle>> handles;
+        std::vector<OpenRound> rounds;
+        size_t mi = 0, pi = 0;
+        for (uint64_t r = 0; r < n_rounds; r++) {
+            handles.push_back(std::make_unique<GpuPcsHandle>(pds[r], /*owns=*/false));
+            OpenRound rd;
+            rd.data = handles.back().get();
+            for (size_t m = 0; m < handles.back()->num_matrices(); m++) {
+                std::vector<Fp2> pts;
+                for (uint64_t k = 0; k < n_points[mi]; k++, pi++) pts.push_back(Fp2(Fp(points[2 * pi]), Fp(points[2 * pi + 1])));
+                mi++;
+                rd.points.push_back(std::move(pts));
+            }
+            rounds.push_back(std::move(rd));
+        }
+        std::map<std::string, double> tm;
+        auto t0 = std::chrono::steady_clock::now();
+        GpuOpenDevice dev(ctx, rounds, (uint32_t)c->cp.log_blowup);
+        tm["fri/evaluate"] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        std::vector<OpenedValuesForRound> opened;
+        FriProof proof;
+        pcs_open(dev, rounds, c->cp, c->fp, c->ch, opened, proof, &tm);
+        std::vector<u8> bytes = pcs_open_to_bytes(opened, proof);
+        *out = (uint8_t*)malloc(bytes.size());
+        memcpy(*out, bytes.data(), bytes.size());
+        *out_len = bytes.size();
+        if (ms5) {
+            const char* names[5] = {"fri/evaluate", "fri/reduce", "fri/commit_phase", "fri/final_poly", "fri/queries"};
+            for (int i = 0; i < 5; i++) ms5[i] = tm[names[i]];
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
 
 }  // extern "C"

@@ -18,14 +18,17 @@ inline void gpu_check(int code) {
 struct GpuPcsHandle : PcsHandle {
     msgpu_pdata* pd = nullptr;
     std::vector<std::pair<size_t, size_t>> shapes;
-    explicit GpuPcsHandle(msgpu_pdata* p) : pd(p) {
+    bool owns = true;
+    explicit GpuPcsHandle(msgpu_pdata* p, bool owns_ = true) : pd(p), owns(owns_) {
         for (uint64_t i = 0; i < msgpu_pdata_num_matrices(pd); i++) {
             uint64_t r = 0, c = 0;
             gpu_check(msgpu_pdata_matrix(pd, i, nullptr, &r, &c));
             shapes.push_back({(size_t)r, (size_t)c});
         }
     }
-    ~GpuPcsHandle() override { msgpu_pdata_free(pd); }
+    ~GpuPcsHandle() override {
+        if (owns) msgpu_pdata_free(pd);
+    }
     size_t num_matrices() const override { return shapes.size(); }
     size_t matrix_height(size_t i) const override { return shapes[i].first; }
     size_t matrix_width(size_t i) const override { return shapes[i].second; }

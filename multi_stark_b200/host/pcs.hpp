@@ -162,4 +162,14 @@ inline void pcs_open(OpenDevice& dev, const std::vector<OpenRound>& rounds, cons
     lap("fri/queries");
 }
 
+// Standalone `Pcs::open` result as bytes (examples/pcs_example.rs:85-105 prints the sizes of exactly these two objects):
+// u64 round count, every round's opened values ([matrix][point][column], length-prefixed), then the FRI proof.
+inline std::vector<u8> pcs_open_to_bytes(const std::vector<OpenedValuesForRound>& opened, const FriProof& proof) {
+    ByteWriter w;
+    w.u64_(opened.size());
+    for (auto& r : opened) write_opened_round(w, r);
+    write_fri_proof(w, proof);
+    return w.out;
+}
+
 }  // namespace msh

@@ -129,6 +129,42 @@ inline OpenedValuesForRound read_opened_round(ByteReader& r) {
     for (auto& m : out) { m.resize(r.len()); for (auto& p : m) { p.resize(r.len()); for (auto& v : p) v = r.fp2(); } }
     return out;
 }
+inline void read_fri_proof(ByteReader& r, FriProof& f) {
+    f.commit_phase_commits.resize(r.len());
+    for (auto& d : f.commit_phase_commits) d = r.digest();
+    f.commit_pow_witnesses.resize(r.len());
+    for (auto& v : f.commit_pow_witnesses) v = r.fp();
+    f.query_proofs.resize(r.len());
+    for (auto& q : f.query_proofs) {
+        q.input_proof.resize(r.len());
+        for (auto& b : q.input_proof) {
+            b.opened_values.resize(r.len());
+            for (auto& row : b.opened_values) { row.resize(r.len()); for (auto& v : row) v = r.fp(); }
+            b.opening_proof.resize(r.len());
+            for (auto& d : b.opening_proof) d = r.digest();
+        }
+        q.commit_phase_openings.resize(r.len());
+        for (auto& s : q.commit_phase_openings) {
+            s.log_arity = r.u8_();
+            s.sibling_values.resize(r.len());
+            for (auto& v : s.sibling_values) v = r.fp2();
+            s.opening_proof.resize(r.len());
+            for (auto& d : s.opening_proof) d = r.digest();
+        }
+        if (!r.ok) return;
+    }
+    f.final_poly.resize(r.len());
+    for (auto& v : f.final_poly) v = r.fp2();
+    f.query_pow_witness = r.fp();
+}
+inline bool pcs_open_from_bytes(const u8* data, size_t n, std::vector<OpenedValuesForRound>& opened, FriProof& proof) {
+    ByteReader r(data, n);
+    opened.resize(r.len());
+    for (auto& o : opened) o = read_opened_round(r);
+    if (!r.ok) return false;
+    read_fri_proof(r, proof);
+    return r.ok && r.done();
+}
 inline bool proof_from_bytes(const u8* data, size_t n, Proof& p) {
     ByteReader r(data, n);
     p.active.resize(r.len());

@@ -189,17 +189,47 @@ inline Matrix fib_cubic_trace(size_t rows) {
     return m;
 }
 
+// BASELINE configs[2]: a wide synthetic AIR without lookups. `width` columns (even); column 2k is free, column 2k+1 is its
+// cube: width/2 degree-3 constraints (quotient degree 2, so log_blowup >= 1... the reference needs q <= B).
+inline CircuitInputs wide_cubic(size_t width) {
+    if (width < 2 || width % 2) throw std::runtime_error("wide circuit needs an even width >= 2");
+    CircuitInputs in;
+    in.main_width = width;
+    for (u32 k = 0; k < width / 2; k++) {
+        Expr a = Expr::main(2 * k);
+        in.constraints.push_back(Expr::main(2 * k + 1) - a * a * a);
+    }
+    return in;
+}
+// counter-based PRNG (splitmix64 of row * width + col) so that any shard of the trace can be generated independently
+inline u64 splitmix64(u64 x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+inline void wide_cubic_fill(u64* out, size_t row0, size_t rows, size_t width) {
+    for (size_t r = 0; r < rows; r++)
+        for (size_t k = 0; k < width / 2; k++) {
+            Fp a(splitmix64((u64)(row0 + r) * width + 2 * k) % GL_P);
+            out[r * width + 2 * k] = a.v;
+            out[r * width + 2 * k + 1] = (a * a * a).v;
+        }
+}
+
 }  // namespace circuits
 
 // Named systems used by bench.py and the tests (circuit order = matrix order inside every commitment).
 //   "u32_add"  : [byte_table, u32_add]                 benches/multi_stark.rs:260-267
 //   "mixed"    : [fib_cubic, byte_table, u32_add]      selectors + quotient degree 2 next to the lookup circuits
 //   "fib"      : [fib_cubic]
+//   "wide:W"   : [wide_cubic(W)]                       BASELINE configs[2] shape (W = 256)
 inline std::vector<CircuitInputs> named_system_inputs(const std::string& kind) {
     std::vector<CircuitInputs> v;
     if (kind == "u32_add") { v.push_back(circuits::byte_table()); v.push_back(circuits::u32_add()); }
     else if (kind == "mixed") { v.push_back(circuits::fib_cubic()); v.push_back(circuits::byte_table()); v.push_back(circuits::u32_add()); }
     else if (kind == "fib") { v.push_back(circuits::fib_cubic()); }
+    else if (kind.rfind("wide:", 0) == 0) { v.push_back(circuits::wide_cubic((size_t)std::stoul(kind.substr(5)))); }
     else throw std::runtime_error("unknown system kind: " + kind);
     return v;
 }

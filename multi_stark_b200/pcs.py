@@ -311,3 +311,67 @@ class GpuPcs:
         if nq > rows:
             raise ValueError("quotient domain larger than the committed LDE (needs quotient_degree <= blowup)")
         return ptr, nq, cols
+
+
+class Challenger:
+    """The reference's transcript object (`config.initialise_challenger()`, src/types.rs:118-130,152-154) for standalone
+    PCS use as in examples/pcs_example.rs:77-79."""
+
+    def __init__(self, log_blowup=1, log_final_poly_len=0, max_log_arity=1, num_queries=100, commit_pow_bits=0, query_pow_bits=0):
+        self.H = _ffi.host_lib()
+        self.params = dict(log_blowup=log_blowup, log_final_poly_len=log_final_poly_len, max_log_arity=max_log_arity,
+                           num_queries=num_queries, commit_pow_bits=commit_pow_bits, query_pow_bits=query_pow_bits)
+        self.h = self.H.msh_challenger_create(log_blowup, log_final_poly_len, max_log_arity, num_queries, commit_pow_bits,
+                                              query_pow_bits)
+
+    def observe(self, commitment):
+        d = np.frombuffer(bytes(commitment), dtype=np.uint8).copy()
+        assert d.size == 32
+        self.H.msh_challenger_observe_digest(self.h, d.ctypes.data_as(C.c_void_p))
+
+    def observe_values(self, values):
+        v = np.ascontiguousarray(values, dtype=np.uint64)
+        self.H.msh_challenger_observe_values(self.h, v.ctypes.data_as(C.c_void_p), v.size)
+
+    def sample_algebra_element(self):
+        out = np.zeros(2, dtype=np.uint64)
+        self.H.msh_challenger_sample_ext(self.h, out.ctypes.data_as(C.c_void_p))
+        return (int(out[0]), int(out[1]))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.H.msh_challenger_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pcs_open(ctx, rounds, challenger):
+    """`Pcs::open(rounds, &mut challenger)` (src/prover.rs:580, examples/pcs_example.rs:85-90).
+    rounds: list of (ProverData, points) with points[m] = list of extension points (c0, c1) for matrix m.
+    Returns (bytes of opened values + FRI proof, per-phase ms)."""
+    H = _ffi.host_lib()
+    n = len(rounds)
+    pds = (C.c_void_p * n)(*[pd.h for pd, _ in rounds])
+    npts, pts = [], []
+    for pd, points in rounds:
+        assert len(points) == pd.num_matrices
+        for mp in points:
+            npts.append(len(mp))
+            for z in mp:
+                pts += [int(z[0]), int(z[1])]
+    npts_a = np.array(npts, dtype=np.uint64)
+    pts_a = np.array(pts if pts else [0], dtype=np.uint64)
+    out, ln = C.c_void_p(), C.c_uint64()
+    ms5 = (C.c_double * 5)()
+    rc = H.msh_pcs_open(ctx.h, challenger.h, n, pds, npts_a.ctypes.data_as(_ffi.c_u64p), pts_a.ctypes.data_as(_ffi.c_u64p),
+                        C.byref(out), C.byref(ln), ms5)
+    if rc != 0:
+        raise _ffi.MsgpuError(rc, (H.msh_last_error() or b"").decode())
+    data = C.string_at(out.value, ln.value)
+    H.msh_bytes_free(out)
+    return data, dict(zip(["evaluate", "reduce", "commit_phase", "final_poly", "queries"], ms5))

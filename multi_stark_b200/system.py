@@ -13,7 +13,7 @@ INFO_FIELDS = ["main_width", "pre_width", "pre_height", "num_lookups", "stage2_w
 
 
 class System:
-    """A named system (see named_system_inputs in host/system.hpp): "u32_add", "mixed", "fib"."""
+    """A named system (see named_system_inputs in host/system.hpp): "u32_add", "mixed", "fib", "wide:W"."""
 
     def __init__(self, kind, log_blowup=1, log_final_poly_len=0, max_log_arity=1, num_queries=100, commit_pow_bits=0,
                  query_pow_bits=0):
@@ -75,6 +75,15 @@ def fib_trace(rows):
     H = _ffi.host_lib()
     out = np.zeros((rows, 3), dtype=np.uint64)
     H.msh_fib_trace(rows, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def wide_trace(rows, width, row0=0, out=None):
+    """Trace of the "wide:W" system (BASELINE configs[2]): column 2k = splitmix64(row * W + 2k) mod p, column 2k+1 its cube."""
+    H = _ffi.host_lib()
+    if out is None:
+        out = np.zeros((rows, width), dtype=np.uint64)
+    H.msh_wide_trace(row0, rows, width, out.ctypes.data_as(C.c_void_p))
     return out
 
 

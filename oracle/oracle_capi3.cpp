@@ -79,3 +79,96 @@ int orc_verify(void* s, const u64* claims, const u64* offsets, u64 n_claims, con
 }
 
 }  // extern "C"
+
+// ---- examples/pcs_example.rs:28-122 on the CPU: commit -> observe -> sample zeta -> open at [zeta; num_open] -> bytes,
+// and the matching verification (transcript replay + TwoAdicFriPcs::verify). One round, any number of matrices.
+extern "C" {
+
+static void pcs_params(u32 log_blowup, u32 log_final_poly_len, u32 num_queries, u32 commit_pow, u32 query_pow,
+                       CommitmentParameters& cp, FriParameters& fp) {
+    cp.log_blowup = log_blowup;
+    fp.log_final_poly_len = log_final_poly_len;
+    fp.max_log_arity = 1;
+    fp.num_queries = num_queries;
+    fp.commit_proof_of_work_bits = commit_pow;
+    fp.query_proof_of_work_bits = query_pow;
+}
+
+int orc_pcs_example_prove(const u64* const* mats, const u64* heights, const u64* widths, u64 n_mats, u32 log_blowup,
+                          u32 log_final_poly_len, u32 num_queries, u32 commit_pow, u32 query_pow, u32 num_open, u8* root32,
+                          u64* zeta2, u8** out, u64* out_len) {
+    try {
+        CommitmentParameters cp;
+        FriParameters fp;
+        pcs_params(log_blowup, log_final_poly_len, num_queries, commit_pow, query_pow, cp, fp);
+        std::vector<Matrix> ms;
+        for (u64 i = 0; i < n_mats; i++) {
+            Matrix m(heights[i], widths[i]);
+            for (size_t k = 0; k < m.values.size(); k++) m.values[k] = Fp(mats[i][k]);
+            ms.push_back(std::move(m));
+        }
+        std::vector<const Matrix*> ptrs;
+        for (auto& m : ms) ptrs.push_back(&m);
+        Digest root;
+        auto pd = cpu_commit(ptrs, log_blowup, root);
+        memcpy(root32, root.data(), 32);
+        Challenger ch = Challenger::for_config(cp, fp);
+        ch.observe(root);
+        Fp2 zeta = ch.sample_ext();
+        zeta2[0] = zeta.c[0].v;
+        zeta2[1] = zeta.c[1].v;
+        std::vector<OpenRound> rounds(1);
+        rounds[0].data = pd.get();
+        for (u64 i = 0; i < n_mats; i++) rounds[0].points.push_back(std::vector<Fp2>(num_open, zeta));
+        CpuOpenDevice dev(rounds, log_blowup);
+        std::vector<OpenedValuesForRound> opened;
+        FriProof proof;
+        pcs_open(dev, rounds, cp, fp, ch, opened, proof);
+        std::vector<u8> bytes = pcs_open_to_bytes(opened, proof);
+        *out = (u8*)malloc(bytes.size());
+        memcpy(*out, bytes.data(), bytes.size());
+        *out_len = bytes.size();
+        return 0;
+    } catch (const std::exception& e) {
+        g_orc_err = e.what();
+        return -1;
+    }
+}
+
+// 1 = accepted, 0 = rejected, -1 = the bytes do not parse
+int orc_pcs_example_verify(const u8* root32, const u64* heights, const u64* widths, u64 n_mats, u32 log_blowup,
+                           u32 log_final_poly_len, u32 num_queries, u32 commit_pow, u32 query_pow, u32 num_open, const u8* bytes,
+                           u64 len) {
+    try {
+        CommitmentParameters cp;
+        FriParameters fp;
+        pcs_params(log_blowup, log_final_poly_len, num_queries, commit_pow, query_pow, cp, fp);
+        std::vector<OpenedValuesForRound> opened;
+        FriProof proof;
+        if (!pcs_open_from_bytes(bytes, len, opened, proof)) return -1;
+        if (opened.size() != 1 || opened[0].size() != n_mats) return 0;
+        Digest root;
+        memcpy(root.data(), root32, 32);
+        Challenger ch = Challenger::for_config(cp, fp);
+        ch.observe(root);
+        Fp2 zeta = ch.sample_ext();
+        VerifierRound vr;
+        vr.commit = root;
+        for (u64 i = 0; i < n_mats; i++) {
+            if (opened[0][i].size() != num_open) return 0;
+            VerifierMat vm;
+            vm.log_degree = log2_strict(heights[i]);
+            for (u32 k = 0; k < num_open; k++) {
+                if (opened[0][i][k].size() != widths[i]) return 0;
+                vm.points.push_back({zeta, opened[0][i][k]});
+            }
+            vr.mats.push_back(std::move(vm));
+        }
+        return pcs_verify({vr}, proof, cp, fp, ch) ? 1 : 0;
+    } catch (const std::exception& e) {
+        g_orc_err = e.what();
+        return -2;
+    }
+}
+
+}  // extern "C"

@@ -69,6 +69,10 @@ def lib():
         "orc_bytes_free": (None, [C.c_void_p]),
         "orc_preprocessed_commit": (C.c_int, [C.c_void_p, u8p]),
         "orc_verify": (C.c_int, [C.c_void_p, u64p, u64p, C.c_uint64, u8p, C.c_uint64]),
+        "orc_pcs_example_prove": (C.c_int, [C.POINTER(C.c_void_p), u64p, u64p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
+                                            C.c_uint32, C.c_uint32, C.c_uint32, u8p, u64p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+        "orc_pcs_example_verify": (C.c_int, [u8p, u64p, u64p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                             C.c_uint32, C.c_uint32, u8p, C.c_uint64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -211,3 +215,32 @@ class OracleSystem:
             self.close()
         except Exception:
             pass
+
+
+def pcs_example_prove(L, mats, log_blowup=1, log_final_poly_len=0, num_queries=100, commit_pow=0, query_pow=0, num_open=2):
+    """examples/pcs_example.rs on the CPU oracle: returns (root, zeta, bytes of opened values + FRI proof)."""
+    mats = [np.ascontiguousarray(m, dtype=np.uint64) for m in mats]
+    n = len(mats)
+    ptrs = (C.c_void_p * n)(*[m.ctypes.data for m in mats])
+    hs = np.array([m.shape[0] for m in mats], dtype=np.uint64)
+    ws = np.array([m.shape[1] for m in mats], dtype=np.uint64)
+    root = np.zeros(32, dtype=np.uint8)
+    zeta = np.zeros(2, dtype=np.uint64)
+    out, ln = C.c_void_p(), C.c_uint64()
+    rc = L.orc_pcs_example_prove(ptrs, hs, ws, n, log_blowup, log_final_poly_len, num_queries, commit_pow, query_pow, num_open,
+                                 root, zeta, C.byref(out), C.byref(ln))
+    if rc != 0:
+        raise RuntimeError(L.orc_last_error().decode())
+    data = C.string_at(out.value, ln.value)
+    L.orc_bytes_free(out)
+    return bytes(root), (int(zeta[0]), int(zeta[1])), data
+
+
+def pcs_example_verify(L, root, shapes, data, log_blowup=1, log_final_poly_len=0, num_queries=100, commit_pow=0, query_pow=0,
+                       num_open=2):
+    hs = np.array([h for h, _ in shapes], dtype=np.uint64)
+    ws = np.array([w for _, w in shapes], dtype=np.uint64)
+    buf = np.frombuffer(data, dtype=np.uint8).copy() if len(data) else np.zeros(1, dtype=np.uint8)
+    r = np.frombuffer(bytes(root), dtype=np.uint8).copy()
+    return L.orc_pcs_example_verify(r, hs, ws, len(shapes), log_blowup, log_final_poly_len, num_queries, commit_pow, query_pow,
+                                    num_open, buf, len(data))

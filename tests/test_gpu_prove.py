@@ -22,6 +22,8 @@ def gpu():
 def workload(ms, kind, log_rows):
     if kind == "fib":
         return [ms.fib_trace(1 << log_rows)], []
+    if kind.startswith("wide:"):
+        return [ms.wide_trace(1 << log_rows, int(kind[5:]))], []
     byte, add, claims = ms.u32_add_workload(1 << log_rows)
     if kind == "u32_add":
         return [byte, add], list(claims)
@@ -68,6 +70,9 @@ CASES = [
     ("mixed", 7, 2, 0, 15, 0),
     ("mixed", 9, 3, 2, 15, 0),
     ("u32_add", 14, 1, 0, 30, 0),
+    ("wide:8", 5, 1, 0, 10, 0),      # quotient degree 2 at the minimal blowup
+    ("wide:256", 7, 2, 0, 10, 0),    # BASELINE configs[2] shape: 2048-byte rows = two BLAKE3 chunks per leaf
+    ("wide:700", 4, 2, 1, 8, 0),     # 5600-byte rows, 350 constraints
 ]
 
 
