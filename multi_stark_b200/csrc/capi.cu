@@ -3,21 +3,113 @@
 #include "capi_common.hpp"
 #include "mmcs.hpp"
 #include "../host/blake3_host.hpp"
+#include <algorithm>
 #include <cstring>
+#include <iterator>
 
 namespace msg {
 
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& s) { g_last_error = s; }
 
-void* Ctx::alloc(size_t bytes) {
-    void* p = nullptr;
-    if (bytes == 0) bytes = 8;
-    MSG_CUDA(cudaMallocAsync(&p, bytes, stream));
-    return p;
+static constexpr size_t kArenaAlign = 512;            // keeps 128-bit vector accesses and TMA-sized rows aligned
+static constexpr size_t kArenaMinSegment = 64u << 20;  // small requests share 64 MB segments
+
+static void arena_erase_free(Ctx::Arena& a, char* addr, size_t size) {
+    auto range = a.free_by_size.equal_range(size);
+    for (auto it = range.first; it != range.second; ++it)
+        if (it->second == addr) {
+            a.free_by_size.erase(it);
+            return;
+        }
 }
-void Ctx::free(void* p) {
-    if (p) MSG_CUDA(cudaFreeAsync(p, stream));
+
+void* Ctx::alloc(size_t bytes) {
+    Arena& a = arena;
+    size_t need = ((bytes ? bytes : 8) + kArenaAlign - 1) / kArenaAlign * kArenaAlign;
+    auto fit = a.free_by_size.lower_bound(need);
+    if (fit == a.free_by_size.end()) {
+        // no block fits: a new segment, exactly the request for large blocks (a proof repeats its sizes)
+        size_t seg = need >= kArenaMinSegment ? (need + (2u << 20) - 1) / (2u << 20) * (2u << 20) : kArenaMinSegment;
+        void* base = nullptr;
+        cudaError_t e = cudaMalloc(&base, seg);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            MSG_CUDA(cudaStreamSynchronize(stream));
+            arena_trim();
+            e = cudaMalloc(&base, seg);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            throw Error(MSGPU_ERR_CUDA, "out of device memory: " + std::to_string(seg >> 20) + " MB requested, " +
+                                            std::to_string(a.reserved >> 20) + " MB reserved, " + std::to_string(a.in_use >> 20) + " MB in use");
+        }
+        a.segments.push_back({(char*)base, seg});
+        a.reserved += seg;
+        a.blocks[(char*)base] = Arena::Block{seg, true, a.segments.size() - 1};
+        fit = a.free_by_size.insert({seg, (char*)base});
+    }
+    char* addr = fit->second;
+    a.free_by_size.erase(fit);
+    Arena::Block& b = a.blocks[addr];
+    if (b.size - need >= kArenaAlign) {  // split: the tail stays free
+        char* tail = addr + need;
+        a.blocks[tail] = Arena::Block{b.size - need, true, b.segment};
+        a.free_by_size.insert({b.size - need, tail});
+        b.size = need;
+    }
+    b.free = false;
+    a.in_use += b.size;
+    a.peak_in_use = std::max(a.peak_in_use, a.in_use);
+    return addr;
+}
+
+bool Ctx::free(void* p) noexcept {
+    if (!p) return true;
+    Arena& a = arena;
+    auto it = a.blocks.find((char*)p);
+    if (it == a.blocks.end() || it->second.free) return false;  // not a live block of this context
+    it->second.free = true;
+    a.in_use -= it->second.size;
+    // merge with the free neighbours of the same segment
+    auto nxt = std::next(it);
+    if (nxt != a.blocks.end() && nxt->second.free && nxt->second.segment == it->second.segment && it->first + it->second.size == nxt->first) {
+        arena_erase_free(a, nxt->first, nxt->second.size);
+        it->second.size += nxt->second.size;
+        a.blocks.erase(nxt);
+    }
+    if (it != a.blocks.begin()) {
+        auto prv = std::prev(it);
+        if (prv->second.free && prv->second.segment == it->second.segment && prv->first + prv->second.size == it->first) {
+            arena_erase_free(a, prv->first, prv->second.size);
+            prv->second.size += it->second.size;
+            a.blocks.erase(it);
+            it = prv;
+        }
+    }
+    a.free_by_size.insert({it->second.size, it->first});
+    return true;
+}
+
+void Ctx::arena_trim() {
+    Arena& a = arena;
+    for (size_t s = 0; s < a.segments.size(); s++) {
+        char* base = a.segments[s].first;
+        if (!base) continue;
+        auto it = a.blocks.find(base);
+        if (it == a.blocks.end() || !it->second.free || it->second.size != a.segments[s].second) continue;
+        arena_erase_free(a, base, it->second.size);
+        a.blocks.erase(it);
+        cudaFree(base);
+        a.reserved -= a.segments[s].second;
+        a.segments[s] = {nullptr, 0};
+    }
+}
+
+void Ctx::arena_destroy() {
+    for (auto& s : arena.segments)
+        if (s.first) cudaFree(s.first);
+    arena = Arena();
 }
 
 void b3_compress_raw_dev(Ctx& c, const u32* st, const u32* msg, u32* out);
@@ -100,10 +192,6 @@ int msgpu_ctx_create(int device, void* stream, msgpu_ctx** out) {
             cudaDeviceProp prop;
             MSG_CUDA(cudaGetDeviceProperties(&prop, device));
             h->c.sm_count = prop.multiProcessorCount;
-            cudaMemPool_t pool;
-            MSG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-            unsigned long long thr = ~0ull;  // keep freed blocks in the pool: no re-allocation per proof
-            MSG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
             ctx_init_tables(h->c);
         } catch (...) {
             delete h;
@@ -118,6 +206,7 @@ void msgpu_ctx_destroy(msgpu_ctx* h) {
     cudaSetDevice(h->c.device);
     cudaStreamSynchronize(h->c.stream);
     for (void* p : h->c.owned) cudaFree(p);
+    h->c.arena_destroy();
     if (h->c.own_stream) cudaStreamDestroy(h->c.stream);
     delete h;
 }
@@ -133,7 +222,7 @@ int msgpu_malloc(msgpu_ctx* h, size_t bytes, void** dptr) {
     return guard([&] { *dptr = h->c.alloc(bytes); });
 }
 int msgpu_free(msgpu_ctx* h, void* dptr) {
-    return guard([&] { h->c.free(dptr); });
+    return guard([&] { MSG_REQUIRE(h->c.free(dptr), "free: not a live block of this context"); });
 }
 int msgpu_memcpy_h2d(msgpu_ctx* h, void* dst, const void* src, size_t bytes) {
     return guard([&] {
@@ -204,13 +293,22 @@ int msgpu_profile_end(msgpu_ctx* h, char* json_out, size_t cap) {
         // aggregate by (stage, kernel)
         std::map<std::pair<std::string, std::string>, std::pair<double, unsigned long long>> agg;
         std::vector<std::pair<std::string, std::string>> order;
+        const bool timeline = getenv("MSGPU_TIMELINE") != nullptr;  // diagnostics: one line per launch on stderr
         for (auto& r : c.prof) {
             float ms = 0;
             MSG_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+            if (timeline) {
+                float off = 0;
+                cudaEventElapsedTime(&off, c.prof.front().a, r.a);
+                fprintf(stderr, "[timeline] %-9s %-24s host +%9.1f us  gpu +%9.1f us  dur %8.1f us\n", r.stage, r.kernel,
+                        r.host_us - c.prof.front().host_us, off * 1e3, ms * 1e3);
+            }
             auto key = std::make_pair(std::string(r.stage), std::string(r.kernel));
             if (!agg.count(key)) order.push_back(key);
             agg[key].first += ms;
             agg[key].second += 1;
+        }
+        for (auto& r : c.prof) {
             cudaEventDestroy(r.a);
             cudaEventDestroy(r.b);
         }

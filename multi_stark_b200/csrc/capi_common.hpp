@@ -33,7 +33,7 @@ struct DevBuf {  // RAII stream-ordered buffer
     DevBuf(Ctx& c_, size_t bytes) : c(c_) { p = c.alloc(bytes); }
     DevBuf(const DevBuf&) = delete;
     ~DevBuf() {
-        if (p) cudaFreeAsync(p, c.stream);
+        if (p) c.free(p);
     }
     u64* u() const { return (u64*)p; }
     void* release() { void* r = p; p = nullptr; return r; }

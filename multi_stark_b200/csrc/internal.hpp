@@ -1,5 +1,6 @@
 // Internal (non-ABI) declarations shared by the .cu translation units of libmsgpu.
 #pragma once
+#include <chrono>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstddef>
@@ -60,13 +61,31 @@ struct Ctx {
         const char* stage;
         const char* kernel;
         cudaEvent_t a, b;
+        double host_us;  // host clock when the launch was issued (MSGPU_TIMELINE diagnostics)
     };
     bool profiling = false;
     const char* stage = "";
     std::vector<ProfRec> prof;
 
-    void* alloc(size_t bytes);  // stream-ordered
-    void free(void* p);
+    // Device memory: a caching arena over cudaMalloc'd segments. Every launch and copy of a context goes to its one stream, so
+    // a block freed on the host can be handed out again at once (the next user is ordered behind the previous one on the
+    // stream). Steady-state proving therefore makes no driver allocation calls at all: cudaMallocAsync / cudaFreeAsync cost
+    // up to several ms per large block on a busy box (tools/diag_step.py), more than the kernels they feed.
+    struct Arena {
+        struct Block {
+            size_t size;
+            bool free;
+            size_t segment;
+        };
+        std::map<char*, Block> blocks;                 // every block of every segment, by address
+        std::multimap<size_t, char*> free_by_size;     // free blocks
+        std::vector<std::pair<char*, size_t>> segments;
+        size_t reserved = 0, in_use = 0, peak_in_use = 0;
+    } arena;
+    void* alloc(size_t bytes);  // valid for work enqueued on `stream` after the call
+    bool free(void* p) noexcept;  // the block may be reused by later work on `stream`; false = not a live block
+    void arena_trim();          // give wholly free segments back to the driver
+    void arena_destroy();
     void sync() { MSG_CUDA(cudaStreamSynchronize(stream)); }
     DevPow pow_table(u64 g, u64 c, u32 bits);
     const gl::PowTable* coset_tables(u32 log_n, u32 added_bits, u64 shift);
@@ -75,6 +94,9 @@ struct Ctx {
 
 void ctx_init_tables(Ctx& c);
 
+inline double host_now_us() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 // Brackets one kernel launch: counts it and, when profiling, records events around it.
 struct KLaunch {
     Ctx& c;
@@ -85,7 +107,7 @@ struct KLaunch {
             MSG_CUDA(cudaEventCreate(&a));
             MSG_CUDA(cudaEventCreate(&b));
             MSG_CUDA(cudaEventRecord(a, c.stream));
-            c.prof.push_back(Ctx::ProfRec{c.stage, kernel, a, b});
+            c.prof.push_back(Ctx::ProfRec{c.stage, kernel, a, b, host_now_us()});
         }
     }
     ~KLaunch() {
