@@ -102,6 +102,24 @@ int msgpu_commit_dev(msgpu_ctx* ctx, const uint64_t* const* mats, const uint64_t
  * (take_ownership = 1; buffers must come from msgpu_malloc) the matrices. */
 int msgpu_commit_ldes_dev(msgpu_ctx* ctx, uint64_t* const* ldes, const uint64_t* heights, const uint64_t* widths,
                           uint64_t n_mats, int take_ownership, msgpu_pdata** out, uint8_t* root32);
+/* ---- one commitment whose matrices live on several GPUs (partitioning A: circuits -> GPUs) ----
+ * The MMCS hashes, per LDE height, the rows of all matrices of that height into one leaf digest and injects the shorter
+ * classes on the way up (p3-merkle-tree, src/types.rs:82-84). When every height class lives on ONE rank, a rank can hash
+ * its classes alone (msgpu_commit_local_dev) and only the 32-byte-per-row class digests travel to the rank that builds
+ * the node layers (msgpu_tree_from_digests); the root and all openings are then bit-identical to a single-GPU commit.
+ * commit_local: `mats` are DEVICE pointers to this rank's matrices in commit order: evaluations (inputs_are_ldes = 0,
+ * not modified) or finished LDEs from msgpu_malloc that the prover data adopts (inputs_are_ldes = 1). The result has no
+ * tree: it serves msgpu_quotient, msgpu_open_begin and the ROW part of msgpu_open_batch_multi (0 sibling digests). */
+int msgpu_commit_local_dev(msgpu_ctx* ctx, uint64_t* const* mats, const uint64_t* heights, const uint64_t* widths,
+                           uint64_t n_mats, uint32_t log_blowup, int inputs_are_ldes, msgpu_pdata** out);
+uint64_t msgpu_pdata_num_classes(const msgpu_pdata* pd);
+/* height class k (tallest first) of a local part: its LDE height and the device pointer of its 32 * height digest bytes */
+int msgpu_pdata_class_digests(const msgpu_pdata* pd, uint64_t k, uint64_t* lde_height, uint8_t** dev_ptr);
+/* node layers over the class digests of ALL ranks (device pointers, distinct power-of-two heights, any order; not
+ * modified). The result has no matrices: msgpu_open_batch_multi on it yields the sibling paths only. */
+int msgpu_tree_from_digests(msgpu_ctx* ctx, uint64_t n_classes, const uint64_t* lde_heights, const uint8_t* const* digests_dev,
+                            msgpu_pdata** out, uint8_t* root32);
+uint64_t msgpu_pdata_max_height(const msgpu_pdata* pd);
 /* Mmcs::commit on HOST matrices as they are (no LDE): used for the FRI layers' ExtensionMmcs rows
  * and by the parity tests of the tree shape (cases of src/types.rs:246-282). */
 int msgpu_mmcs_commit(msgpu_ctx* ctx, const uint64_t* const* mats, const uint64_t* heights, const uint64_t* widths,
@@ -221,6 +239,11 @@ int msgpu_open_values(msgpu_open* op, uint64_t* out);
 int msgpu_open_reduce(msgpu_open* op, const uint64_t* alpha2, uint64_t* n_inputs, uint32_t* log_max_height);
 /* HOST copy of FRI input k (tallest first): 2 * len u64; len_out receives its length. Test hook. */
 int msgpu_open_read_input(msgpu_open* op, uint64_t k, uint64_t* out, uint64_t* len_out);
+/* sharded opening: DEVICE pointer of FRI input k (to send it to the rank that runs the commit phase), and on that rank a new
+ * input of `len` extension elements to receive a peer's reduced openings into (before the first fri_commit_round; one
+ * input per height) */
+int msgpu_open_input_dev(msgpu_open* op, uint64_t k, uint64_t** dev_ptr, uint64_t* len_out);
+int msgpu_open_add_input(msgpu_open* op, uint64_t len, uint64_t** dev_ptr);
 int msgpu_fri_current_len(msgpu_open* op, uint64_t* len);
 int msgpu_fri_commit_round(msgpu_open* op, uint8_t* root32);
 int msgpu_fri_fold(msgpu_open* op, const uint64_t* beta2);

@@ -6,7 +6,8 @@ There is no CPU fallback: importing works without a GPU (so the ABI can be check
 compute call needs a CUDA device and raises `MsgpuError` otherwise."""
 from ._ffi import MsgpuError, lib, lib_path  # noqa: F401
 from .pcs import Challenger, GpuContext, GpuDft, GpuMmcs, GpuPcs, ProverData, pcs_open  # noqa: F401
-from .system import Program, Prover, System, claims_accumulator, fib_trace, shifted_quotient_slices, u32_add_workload, wide_trace  # noqa: F401
+from .system import (Program, Prover, System, claims_accumulator, fib_trace, multi_workload, shifted_quotient_slices,  # noqa: F401
+                     u32_add_workload, wide_trace)
 
 P = 2**64 - 2**32 + 1
 GENERATOR = 7

@@ -44,6 +44,11 @@ SIGNATURES = {
     "msgpu_commit": (C.c_int, [C.c_void_p, c_vpp, c_u64p, c_u64p, C.c_uint64, C.c_uint32, c_vpp, C.c_void_p]),
     "msgpu_commit_dev": (C.c_int, [C.c_void_p, c_vpp, c_u64p, c_u64p, C.c_uint64, C.c_uint32, c_vpp, C.c_void_p]),
     "msgpu_commit_ldes_dev": (C.c_int, [C.c_void_p, c_vpp, c_u64p, c_u64p, C.c_uint64, C.c_int, c_vpp, C.c_void_p]),
+    "msgpu_commit_local_dev": (C.c_int, [C.c_void_p, c_vpp, c_u64p, c_u64p, C.c_uint64, C.c_uint32, C.c_int, c_vpp]),
+    "msgpu_pdata_num_classes": (C.c_uint64, [C.c_void_p]),
+    "msgpu_pdata_class_digests": (C.c_int, [C.c_void_p, C.c_uint64, c_u64p, c_vpp]),
+    "msgpu_tree_from_digests": (C.c_int, [C.c_void_p, C.c_uint64, c_u64p, c_vpp, c_vpp, C.c_void_p]),
+    "msgpu_pdata_max_height": (C.c_uint64, [C.c_void_p]),
     "msgpu_mmcs_commit": (C.c_int, [C.c_void_p, c_vpp, c_u64p, c_u64p, C.c_uint64, c_vpp, C.c_void_p]),
     "msgpu_pdata_free": (None, [C.c_void_p]),
     "msgpu_pdata_num_matrices": (C.c_uint64, [C.c_void_p]),
@@ -70,6 +75,8 @@ SIGNATURES = {
     "msgpu_open_values": (C.c_int, [C.c_void_p, C.c_void_p]),
     "msgpu_open_reduce": (C.c_int, [C.c_void_p, C.c_void_p, c_u64p, c_u32p]),
     "msgpu_open_read_input": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, c_u64p]),
+    "msgpu_open_input_dev": (C.c_int, [C.c_void_p, C.c_uint64, c_vpp, c_u64p]),
+    "msgpu_open_add_input": (C.c_int, [C.c_void_p, C.c_uint64, c_vpp]),
     "msgpu_fri_current_len": (C.c_int, [C.c_void_p, c_u64p]),
     "msgpu_fri_commit_round": (C.c_int, [C.c_void_p, C.c_void_p]),
     "msgpu_fri_fold": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -128,6 +135,8 @@ HOST_SIGNATURES = {
     "msh_circuit_graph": (C.c_void_p, [C.c_void_p, C.c_uint32]),
     "msh_circuit_preprocessed": (None, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "msh_u32add_workload": (None, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "msh_u32add_workload_seeded": (None, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "msh_dist_prover_create": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "msh_fib_trace": (None, [C.c_uint64, C.c_void_p]),
     "msh_wide_trace": (None, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "msh_prover_create": (C.c_void_p, [C.c_void_p, C.c_void_p]),

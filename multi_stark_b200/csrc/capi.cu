@@ -414,6 +414,68 @@ int msgpu_commit_dev(msgpu_ctx* h, const uint64_t* const* mats, const uint64_t* 
         *out = pd;
     });
 }
+// ---- sharded commitments: one MMCS whose matrices live on several GPUs --------------------------------------------------
+int msgpu_commit_local_dev(msgpu_ctx* h, uint64_t* const* mats, const uint64_t* heights, const uint64_t* widths, uint64_t n_mats,
+                           uint32_t log_blowup, int inputs_are_ldes, msgpu_pdata** out) {
+    return guard([&] {
+        Ctx& c = h->c;
+        MSG_REQUIRE(n_mats > 0 && out, "commit_local: no matrices given");
+        msgpu_pdata* pd = new msgpu_pdata();
+        pd->ctx = &c;
+        try {
+            for (u64 i = 0; i < n_mats; i++) {
+                check_shape(heights[i], widths[i]);
+                if (inputs_are_ldes) {  // adopted (buffers from msgpu_malloc), as msgpu_commit_ldes_dev with take_ownership = 1
+                    pd->mats.push_back(msgpu_pdata::Mat{(u64*)mats[i], heights[i], widths[i], false});
+                    continue;
+                }
+                u64 hh = heights[i], w = widths[i], out_h = hh << log_blowup;
+                msgpu_pdata::Mat m{(u64*)c.alloc(out_h * w * 8), out_h, w, true};
+                pd->mats.push_back(m);
+                if (w == 0) continue;
+                StageScope stage_scope(c, "lde");
+                DevBuf tmp(c, hh * w * 8);
+                ntt_coset_lde(c, (const u64*)mats[i], m.ptr, tmp.u(), hh, w, log_blowup, msh::GL_GENERATOR);
+            }
+            mmcs_build_local(c, pd);
+        } catch (...) {
+            pdata_destroy(pd);
+            throw;
+        }
+        for (auto& m : pd->mats) m.owned = true;
+        *out = pd;
+    });
+}
+uint64_t msgpu_pdata_num_classes(const msgpu_pdata* pd) { return pd->class_leaves.size(); }
+int msgpu_pdata_class_digests(const msgpu_pdata* pd, uint64_t k, uint64_t* lde_height, uint8_t** dev_ptr) {
+    return guard([&] {
+        MSG_REQUIRE(k < pd->class_leaves.size(), "class_digests: no such height class");
+        if (lde_height) *lde_height = pd->class_leaves[k].first;
+        if (dev_ptr) *dev_ptr = pd->class_leaves[k].second;
+    });
+}
+int msgpu_tree_from_digests(msgpu_ctx* h, uint64_t n_classes, const uint64_t* lde_heights, const uint8_t* const* digests_dev,
+                            msgpu_pdata** out, uint8_t* root32) {
+    return guard([&] {
+        Ctx& c = h->c;
+        MSG_REQUIRE(n_classes > 0 && lde_heights && digests_dev && out && root32, "tree_from_digests: null argument");
+        std::vector<std::pair<u64, const uint8_t*>> classes;
+        for (u64 k = 0; k < n_classes; k++) classes.push_back({lde_heights[k], digests_dev[k]});
+        std::sort(classes.begin(), classes.end(), [](auto& a, auto& b) { return a.first > b.first; });
+        msgpu_pdata* pd = new msgpu_pdata();
+        pd->ctx = &c;
+        try {
+            mmcs_build_from_classes(c, pd, classes);
+        } catch (...) {
+            pdata_destroy(pd);
+            throw;
+        }
+        memcpy(root32, pd->root, 32);
+        *out = pd;
+    });
+}
+uint64_t msgpu_pdata_max_height(const msgpu_pdata* pd) { return pd->max_height; }
+
 int msgpu_mmcs_commit(msgpu_ctx* h, const uint64_t* const* mats, const uint64_t* heights, const uint64_t* widths,
                       uint64_t n_mats, msgpu_pdata** out, uint8_t* root32) {
     return guard([&] {

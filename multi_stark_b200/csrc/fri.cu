@@ -508,6 +508,30 @@ int msgpu_open_read_input(msgpu_open* op, uint64_t k, uint64_t* out, uint64_t* l
     });
 }
 
+int msgpu_open_input_dev(msgpu_open* op, uint64_t k, uint64_t** dev_ptr, uint64_t* len_out) {
+    return guard([&] {
+        MSG_REQUIRE(k < op->inputs.size() && (k == 0 || k >= op->next_input), "open_input_dev: input already consumed");
+        if (dev_ptr) *dev_ptr = (uint64_t*)op->inputs[k].ptr;
+        if (len_out) *len_out = op->inputs[k].len;
+    });
+}
+
+int msgpu_open_add_input(msgpu_open* op, uint64_t len, uint64_t** dev_ptr) {
+    return guard([&] {
+        Ctx& c = *op->ctx;
+        MSG_REQUIRE(dev_ptr && is_pow2(len), "open_add_input: bad argument");
+        MSG_REQUIRE(op->layers.empty() && !op->cur_committed && op->next_input <= 1, "open_add_input: the commit phase has started");
+        for (auto& in : op->inputs) MSG_REQUIRE(in.len != len, "open_add_input: this height already has an input (one height class per rank)");
+        u64* buf = (u64*)c.alloc(len * 16);
+        op->inputs.push_back(msgpu_open::Input{buf, len});
+        std::sort(op->inputs.begin(), op->inputs.end(), [](const msgpu_open::Input& a, const msgpu_open::Input& b) { return a.len > b.len; });
+        op->cur = op->inputs[0].ptr;
+        op->cur_len = op->inputs[0].len;
+        op->next_input = 1;
+        *dev_ptr = (uint64_t*)buf;
+    });
+}
+
 int msgpu_fri_current_len(msgpu_open* op, uint64_t* len) {
     return guard([&] {
         MSG_REQUIRE(op->cur, "fri: open_reduce has not run");

@@ -32,22 +32,45 @@ static void build_open_desc(Ctx& c, msgpu_pdata* pd) {
     MSG_CUDA(cudaMemcpyAsync(pd->d_desc, host.data(), host.size(), cudaMemcpyHostToDevice, c.stream));  // pageable: staged before return
 }
 
-void mmcs_build(Ctx& c, msgpu_pdata* pd) {
-    StageScope stage_scope(c, "merkle");
-    MSG_REQUIRE(!pd->mats.empty(), "commit: no matrices given");
+// Stable sort of the matrices by height (descending) and the leaf digests of every height class:
+// digest[i] = BLAKE3(row i of the class's matrices, concatenated in commit order). `first_out`, when given, receives the
+// tallest class (layer 0 of a tree); the other classes get their own buffers. Returns (height, digests), tallest first.
+static std::vector<std::pair<u64, uint8_t*>> hash_classes(Ctx& c, msgpu_pdata* pd, uint8_t* first_out) {
     std::vector<size_t> order(pd->mats.size());
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(),
-                     [&](size_t a, size_t b) { return pd->mats[a].height > pd->mats[b].height; });
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return pd->mats[a].height > pd->mats[b].height; });
     pd->total_width = 0;
+    pd->max_height = 0;
     for (auto& m : pd->mats) {
         MSG_REQUIRE(is_pow2(m.height), "commit: matrix heights must be powers of two");
         pd->total_width += m.width;
+        pd->max_height = std::max(pd->max_height, m.height);
     }
-    u64 max_h = pd->mats[order[0]].height;
+    std::vector<std::pair<u64, uint8_t*>> classes;
+    size_t pos = 0;
+    while (pos < order.size()) {
+        u64 h = pd->mats[order[pos]].height;
+        std::vector<MatRef> group;
+        while (pos < order.size() && pd->mats[order[pos]].height == h) {
+            auto& m = pd->mats[order[pos++]];
+            group.push_back(MatRef{m.ptr, m.height, m.width});
+        }
+        uint8_t* out = (classes.empty() && first_out) ? first_out : (uint8_t*)c.alloc(h * 32);
+        classes.push_back({h, out});
+        try {
+            b3_hash_rows(c, group, out);
+        } catch (...) {
+            for (auto& cl : classes)
+                if (cl.second != first_out) c.free(cl.second);
+            throw;
+        }
+    }
+    return classes;
+}
+
+static void layout_layers(Ctx& c, msgpu_pdata* pd, u64 max_h) {
     pd->max_height = max_h;
-    u64 total = 2 * max_h - 1;
-    pd->digests = (uint8_t*)c.alloc(total * 32);
+    pd->digests = (uint8_t*)c.alloc((2 * max_h - 1) * 32);
     pd->layer_off.clear();
     pd->layer_len.clear();
     u64 off = 0;
@@ -57,29 +80,17 @@ void mmcs_build(Ctx& c, msgpu_pdata* pd) {
         off += len;
         if (len == 1) break;
     }
-    size_t pos = 0;
-    std::vector<MatRef> group;
-    while (pos < order.size() && pd->mats[order[pos]].height == max_h) {
-        auto& m = pd->mats[order[pos++]];
-        group.push_back(MatRef{m.ptr, m.height, m.width});
-    }
-    b3_hash_rows(c, group, pd->digests);
-    // leaf digests of the shorter matrices, per layer they are injected into
+}
+
+// node layers over layer 0 (already in pd->digests) with the shorter classes injected where the layer length equals their
+// height: 10 levels per launch while the layer is large, then everything that is left in one CTA
+static void build_nodes(Ctx& c, msgpu_pdata* pd, const std::vector<std::pair<u64, const uint8_t*>>& classes) {
     size_t n_layers = pd->layer_len.size();
-    std::vector<uint8_t*> inj(n_layers, nullptr);
-    for (size_t l = 1; l < n_layers; l++) {
-        u64 next_len = pd->layer_len[l];
-        group.clear();
-        while (pos < order.size() && pd->mats[order[pos]].height == next_len) {
-            auto& m = pd->mats[order[pos++]];
-            group.push_back(MatRef{m.ptr, m.height, m.width});
-        }
-        if (!group.empty()) {
-            inj[l] = (uint8_t*)c.alloc(next_len * 32);
-            b3_hash_rows(c, group, inj[l]);
-        }
+    std::vector<const uint8_t*> inj(n_layers, nullptr);
+    for (size_t k = 1; k < classes.size(); k++) {
+        MSG_REQUIRE(classes[k].first < classes[k - 1].first && is_pow2(classes[k].first), "commit: height classes must be distinct powers of two, tallest first");
+        inj[ilog2(pd->max_height) - ilog2(classes[k].first)] = classes[k].second;
     }
-    // node layers: 10 per launch while the layer is large, then everything that is left in one CTA
     size_t l = 0;
     while (l + 1 < n_layers) {
         u64 len = pd->layer_len[l];
@@ -93,10 +104,48 @@ void mmcs_build(Ctx& c, msgpu_pdata* pd) {
         b3_merkle_subtrees(c, pd->digests + pd->layer_off[l] * 32, len, levels, outs, injs);
         l += levels;
     }
-    for (auto* p : inj)
-        if (p) c.free(p);
-    MSG_REQUIRE(pos == order.size(), "commit: internal error, matrix not placed in the tree");
+}
+
+void mmcs_build(Ctx& c, msgpu_pdata* pd) {
+    StageScope stage_scope(c, "merkle");
+    MSG_REQUIRE(!pd->mats.empty(), "commit: no matrices given");
+    u64 max_h = 0;
+    for (auto& m : pd->mats) max_h = std::max(max_h, m.height);
+    MSG_REQUIRE(is_pow2(max_h), "commit: matrix heights must be powers of two");
+    layout_layers(c, pd, max_h);
+    std::vector<std::pair<u64, uint8_t*>> cls = hash_classes(c, pd, pd->digests);
+    std::vector<std::pair<u64, const uint8_t*>> view(cls.begin(), cls.end());
+    try {
+        build_nodes(c, pd, view);
+    } catch (...) {
+        for (size_t k = 1; k < cls.size(); k++) c.free(cls[k].second);
+        throw;
+    }
+    for (size_t k = 1; k < cls.size(); k++) c.free(cls[k].second);
     build_open_desc(c, pd);
+    MSG_CUDA(cudaMemcpyAsync(pd->root, pd->digests + pd->layer_off.back() * 32, 32, cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+}
+
+void mmcs_build_local(Ctx& c, msgpu_pdata* pd) {
+    StageScope stage_scope(c, "merkle");
+    MSG_REQUIRE(!pd->mats.empty(), "commit: no matrices given");
+    pd->class_leaves = hash_classes(c, pd, nullptr);
+    pd->layer_off.clear();
+    pd->layer_len.clear();
+    build_open_desc(c, pd);  // rows only: no digest layers
+    memset(pd->root, 0, 32);
+    c.sync();  // the descriptor's host staging buffer dies here
+}
+
+void mmcs_build_from_classes(Ctx& c, msgpu_pdata* pd, const std::vector<std::pair<u64, const uint8_t*>>& classes) {
+    StageScope stage_scope(c, "merkle");
+    MSG_REQUIRE(!classes.empty() && is_pow2(classes[0].first), "tree: no leaf digests given");
+    layout_layers(c, pd, classes[0].first);
+    pd->total_width = 0;
+    MSG_CUDA(cudaMemcpyAsync(pd->digests, classes[0].second, classes[0].first * 32, cudaMemcpyDeviceToDevice, c.stream));
+    build_nodes(c, pd, classes);
+    build_open_desc(c, pd);  // paths only: no matrices
     MSG_CUDA(cudaMemcpyAsync(pd->root, pd->digests + pd->layer_off.back() * 32, 32, cudaMemcpyDeviceToHost, c.stream));
     c.sync();
 }
@@ -137,7 +186,7 @@ void mmcs_open_multi(Ctx& c, const msgpu_pdata* const* pds, const u32* shifts, u
     for (u64 k = 0; k < n_trees; k++) {
         const msgpu_pdata* pd = pds[k];
         MSG_REQUIRE(pd && pd->d_desc, "open_multi: prover data without a tree");
-        u32 depth = ilog2(pd->max_height);
+        u32 depth = pd->digests ? ilog2(pd->max_height) : 0;  // the local part of a sharded commitment has rows only
         for (u64 i = 0; i < n_idx; i++)
             MSG_REQUIRE((indices_host[i] >> shifts[k]) < pd->max_height, "open_multi: index out of range");
         MultiTree& t = mt[k];
@@ -188,6 +237,7 @@ void pdata_destroy(msgpu_pdata* pd) {
     for (auto& m : pd->mats)
         if (m.owned && m.ptr) c.free(m.ptr);
     if (pd->digests) c.free(pd->digests);
+    for (auto& cl : pd->class_leaves) c.free(cl.second);
     delete pd;
 }
 

@@ -18,6 +18,10 @@ struct msgpu_pdata {
     u64 total_width = 0;
     uint8_t root[32];
     void* d_desc = nullptr;          // device copy of the opening descriptors (OpenMat[] then layer offsets), built with the tree
+    // Sharded commitments (one proof over several GPUs): a LOCAL part holds this rank's matrices and, per LDE height
+    // class, the leaf digests of its rows (no tree: digests == nullptr); the TREE part on the tree owner holds the digest
+    // layers built from every rank's class digests (no matrices).
+    std::vector<std::pair<u64, uint8_t*>> class_leaves;  // (LDE height, 32 * height bytes), tallest first
 };
 
 namespace msg {
@@ -28,5 +32,9 @@ void mmcs_open_batch(Ctx& c, const msgpu_pdata* pd, const u64* indices_host, u64
 // Mmcs::open_batch of several trees in one launch: tree k is opened at indices[q] >> shifts[k]
 void mmcs_open_multi(Ctx& c, const msgpu_pdata* const* pds, const u32* shifts, u64 n_trees, const u64* indices_host, u64 n_idx,
                      u64* opened_host, uint8_t* proof_host);
+// Local part of a sharded commitment: leaf digests per height class of pd->mats, no node layers.
+void mmcs_build_local(Ctx& c, msgpu_pdata* pd);
+// Tree part: node layers (with injection) over per-class leaf digests given tallest first; heights strictly decreasing.
+void mmcs_build_from_classes(Ctx& c, msgpu_pdata* pd, const std::vector<std::pair<u64, const uint8_t*>>& classes);
 void pdata_destroy(msgpu_pdata* pd);
 }  // namespace msg

@@ -3,6 +3,7 @@
 #include "system.hpp"
 #include "program.hpp"
 #include "gpu_backend.hpp"
+#include "dist_backend.hpp"
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -73,6 +74,17 @@ void msh_u32add_workload(uint64_t num_adds, uint64_t* byte_trace_out, uint64_t* 
         for (size_t i = 0; i < w.claims.size(); i++)
             for (int k = 0; k < 4; k++) claims_out[4 * i + k] = w.claims[i][k].v;
 }
+// same with other xorshift32 seeds: the K circuits of the "multi:K" system get different additions; the byte multiplicities of
+// all of them are summed by the caller
+void msh_u32add_workload_seeded(uint64_t num_adds, uint32_t seed_a, uint32_t seed_b, uint64_t* byte_trace_out, uint64_t* add_trace_out,
+                                uint64_t* claims_out) {
+    auto w = circuits::u32_add_workload(num_adds, seed_a, seed_b);
+    for (size_t i = 0; i < 256; i++) byte_trace_out[i] = w.byte_trace.values[i].v;
+    for (size_t i = 0; i < w.add_trace.values.size(); i++) add_trace_out[i] = w.add_trace.values[i].v;
+    if (claims_out)
+        for (size_t i = 0; i < w.claims.size(); i++)
+            for (int k = 0; k < 4; k++) claims_out[4 * i + k] = w.claims[i][k].v;
+}
 void msh_wide_trace(uint64_t row0, uint64_t rows, uint64_t width, uint64_t* out) { circuits::wide_cubic_fill(out, row0, rows, width); }
 void msh_fib_trace(uint64_t rows, uint64_t* out) {
     Matrix m = circuits::fib_cubic_trace(rows);
@@ -92,6 +104,22 @@ msh_prover* msh_prover_create(msh_system* s, msgpu_ctx* ctx) {
         auto p = std::make_unique<msh_prover>();
         p->sys = s;
         p->backend = std::make_unique<GpuBackend>(ctx, s->shape);
+        p->prover = std::make_unique<Prover>(s->shape, *p->backend);
+        return p.release();
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+// One proof over several GPUs (dist_backend.hpp): every rank creates the prover with the same `owner` (circuit -> rank) and
+// its own context, then calls msh_prove with the traces of the circuits it owns (other traces: NULL pointer, true height).
+// `comm` is copied; its callbacks must stay valid for the life of the prover. All ranks get the same proof bytes.
+msh_prover* msh_dist_prover_create(msh_system* s, msgpu_ctx* ctx, const msh_comm* comm, const int32_t* owner) {
+    try {
+        auto p = std::make_unique<msh_prover>();
+        p->sys = s;
+        std::vector<int> own(owner, owner + s->shape.circuits.size());
+        p->backend = std::make_unique<DistGpuBackend>(ctx, s->shape, *comm, own);
         p->prover = std::make_unique<Prover>(s->shape, *p->backend);
         return p.release();
     } catch (const std::exception& e) {

@@ -362,7 +362,7 @@ class GpuBackend : public ProverBackend {
         active_.clear();
     }
 
-  private:
+  protected:  // the sharded backend (dist_backend.hpp) reuses the per-circuit state
     // H2D copy + check that every value is canonical (the ABI's precondition, verified on the device)
     uint64_t* upload(const uint64_t* src, size_t n) {
         void* d = nullptr;

@@ -132,13 +132,13 @@ struct U32AddWorkload {
     std::vector<std::vector<Fp>> claims;  // [1, x, y, z]
 };
 // benches/multi_stark.rs:171-238
-inline U32AddWorkload u32_add_workload(size_t num_adds) {
+inline U32AddWorkload u32_add_workload(size_t num_adds, uint32_t seed_a = 0xdeadbeefu, uint32_t seed_b = 0xcafebabeu) {
     U32AddWorkload w;
     size_t h = next_pow2(num_adds);
     w.byte_trace = Matrix(256, 1);
     w.add_trace = Matrix(h, 14);
     w.claims.reserve(num_adds);
-    uint32_t a = 0xdeadbeefu, b = 0xcafebabeu;
+    uint32_t a = seed_a, b = seed_b;
     for (size_t r = 0; r < num_adds; r++) {
         a ^= a << 13; a ^= a >> 17; a ^= a << 5;
         b ^= b << 13; b ^= b >> 17; b ^= b << 5;
@@ -224,11 +224,18 @@ inline void wide_cubic_fill(u64* out, size_t row0, size_t rows, size_t width) {
 //   "mixed"    : [fib_cubic, byte_table, u32_add]      selectors + quotient degree 2 next to the lookup circuits
 //   "fib"      : [fib_cubic]
 //   "wide:W"   : [wide_cubic(W)]                       BASELINE configs[2] shape (W = 256)
+//   "multi:K"  : [byte_table, u32_add x K]             BASELINE configs[3] shape: independent circuits sharing the byte table
 inline std::vector<CircuitInputs> named_system_inputs(const std::string& kind) {
     std::vector<CircuitInputs> v;
     if (kind == "u32_add") { v.push_back(circuits::byte_table()); v.push_back(circuits::u32_add()); }
     else if (kind == "mixed") { v.push_back(circuits::fib_cubic()); v.push_back(circuits::byte_table()); v.push_back(circuits::u32_add()); }
     else if (kind == "fib") { v.push_back(circuits::fib_cubic()); }
+    else if (kind.rfind("multi:", 0) == 0) {  // BASELINE configs[3] shape: K U32-add circuits (of different heights) + the byte table
+        size_t k = (size_t)std::stoul(kind.substr(6));
+        if (k < 1 || k > 64) throw std::runtime_error("multi:K needs 1 <= K <= 64");
+        v.push_back(circuits::byte_table());
+        for (size_t i = 0; i < k; i++) v.push_back(circuits::u32_add());
+    }
     else if (kind.rfind("wide:", 0) == 0) { v.push_back(circuits::wide_cubic((size_t)std::stoul(kind.substr(5)))); }
     else throw std::runtime_error("unknown system kind: " + kind);
     return v;

@@ -71,6 +71,26 @@ def u32_add_workload(num_adds):
     return byte, add, claims
 
 
+def multi_workload(log_heights):
+    """Workload of the "multi:K" system (BASELINE configs[3]): circuit 0 = the byte table, circuit 1 + k = a U32-add circuit
+    with 2^log_heights[k] additions from its own xorshift32 streams. Returns (traces [byte, add_0, ...], claims (n, 4));
+    the byte multiplicities are summed over the K circuits."""
+    H = _ffi.host_lib()
+    byte_total = np.zeros((256, 1), dtype=np.uint64)
+    traces, claims = [], []
+    for k, lh in enumerate(log_heights):
+        n = 1 << lh
+        byte = np.zeros((256, 1), dtype=np.uint64)
+        add = np.zeros((n, 14), dtype=np.uint64)
+        cl = np.zeros((n, 4), dtype=np.uint64)
+        H.msh_u32add_workload_seeded(n, (0xDEADBEEF + 0x9E3779B9 * k) & 0xFFFFFFFF or 1, (0xCAFEBABE + 0x85EBCA6B * k) & 0xFFFFFFFF or 1,
+                                     byte.ctypes.data_as(C.c_void_p), add.ctypes.data_as(C.c_void_p), cl.ctypes.data_as(C.c_void_p))
+        byte_total += byte
+        traces.append(add)
+        claims.append(cl)
+    return [byte_total] + traces, np.concatenate(claims, axis=0)
+
+
 def fib_trace(rows):
     H = _ffi.host_lib()
     out = np.zeros((rows, 3), dtype=np.uint64)
