@@ -5,6 +5,9 @@ so there is NO data-path collective: every rank runs the full single-GPU pipelin
 what the protocol makes public anyway (32-byte commitments / proof digests) and the timing needed for an honest aggregate
 (max over ranks). The reference has no multi-process story at all (rayon inside one process)."""
 import hashlib
+import os
+import sys
+import time
 
 import torch
 import torch.distributed as dist
@@ -138,6 +141,9 @@ class TorchComm:
         self.bytes_dev = 0   # device bytes sent or received by this rank (reported by bench / tools)
         self.bytes_host = 0
         self.errors = []
+        self.seconds = {}    # wall time spent inside the callbacks, by kind
+        self._stage = None
+        self.trace = bool(os.environ.get("MSH_TRACE"))
         self._cb = (_ALLGATHER(self._allgather), _BCAST(self._bcast), _SENDRECV(self._sendrecv))  # keep the thunks alive
         self.struct = MshComm(None, self.rank, self.world, *self._cb)
 
@@ -146,15 +152,43 @@ class TorchComm:
         return torch.frombuffer((_C.c_uint8 * nbytes).from_address(ptr), dtype=torch.uint8)
 
     def _allgather(self, user, send, recv, nbytes):
+        t0 = time.perf_counter()
+        try:
+            return self._allgather_impl(send, recv, nbytes)
+        finally:
+            self.seconds["allgather"] = self.seconds.get("allgather", 0.0) + time.perf_counter() - t0
+
+    def _staging(self, nbytes):
+        """persistent pinned-host and device staging buffers (grow-only): a fresh pageable tensor per call costs ms"""
+        if self._stage is None or self._stage[0].numel() < nbytes:
+            cap = 1 << max(16, int(nbytes - 1).bit_length())
+            dev = torch.device("cuda", torch.cuda.current_device())
+            self._stage = (torch.empty(cap, dtype=torch.uint8).pin_memory(), torch.empty(cap, dtype=torch.uint8, device=dev))
+        return self._stage
+
+    def _allgather_impl(self, send, recv, nbytes):
         try:
             nbytes = int(nbytes)
             s = self._host_tensor(send, nbytes)
             r = self._host_tensor(recv, nbytes * self.world)
             if self.nccl:
-                dev = torch.device("cuda", torch.cuda.current_device())
-                out = torch.empty(nbytes * self.world, dtype=torch.uint8, device=dev)
-                self.dist.all_gather_into_tensor(out, s.to(dev), group=self.group)
-                r.copy_(out.cpu())
+                tr = [time.perf_counter()]
+                pin, dev = self._staging(nbytes * (self.world + 1))
+                tr.append(time.perf_counter())
+                total = nbytes * self.world
+                _C.memmove(pin.data_ptr(), send, nbytes)  # (torch's CPU copy_ spins up its thread pool: ms for 1 MB)
+                dev[total:total + nbytes].copy_(pin[:nbytes], non_blocking=True)
+                tr.append(time.perf_counter())
+                self.dist.all_gather_into_tensor(dev[:total], dev[total:total + nbytes], group=self.group)
+                tr.append(time.perf_counter())
+                pin[:total].copy_(dev[:total], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                tr.append(time.perf_counter())
+                _C.memmove(recv, pin.data_ptr(), total)
+                tr.append(time.perf_counter())
+                if self.trace:
+                    print("[comm] rank %d allgather %d B: staging %.3f, h2d %.3f, nccl call %.3f, d2h+sync %.3f, copy out %.3f ms" % (
+                        (self.rank, nbytes) + tuple((b - a) * 1e3 for a, b in zip(tr, tr[1:]))), file=sys.stderr, flush=True)
             else:
                 self.dist.all_gather_into_tensor(r, s.clone(), group=self.group)
             self.bytes_host += nbytes * self.world
@@ -164,26 +198,42 @@ class TorchComm:
             return 1
 
     def _bcast(self, user, buf, nbytes, root):
+        t0 = time.perf_counter()
         try:
-            t = self._host_tensor(buf, int(nbytes))
+            nbytes = int(nbytes)
+            t = self._host_tensor(buf, nbytes)
             if self.nccl:
-                d = t.to(torch.device("cuda", torch.cuda.current_device()))
-                self.dist.broadcast(d, src=self._global(root), group=self.group)
+                pin, dev = self._staging(nbytes)
+                if self.rank == root:
+                    _C.memmove(pin.data_ptr(), buf, nbytes)
+                    dev[:nbytes].copy_(pin[:nbytes], non_blocking=True)
+                self.dist.broadcast(dev[:nbytes], src=self._global(root), group=self.group)
                 if self.rank != root:
-                    t.copy_(d.cpu())
+                    pin[:nbytes].copy_(dev[:nbytes], non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+                    _C.memmove(buf, pin.data_ptr(), nbytes)
             else:
                 self.dist.broadcast(t, src=self._global(root), group=self.group)
-            self.bytes_host += int(nbytes)
+            self.bytes_host += nbytes
             return 0
         except Exception as e:
             self.errors.append(repr(e))
             return 1
+        finally:
+            self.seconds["bcast"] = self.seconds.get("bcast", 0.0) + time.perf_counter() - t0
 
     def _global(self, r):
         return self.dist.get_global_rank(self.group, r) if self.group is not None else r
 
     # ---- device buffers
     def _sendrecv(self, user, dev, nbytes, src, dst):
+        t0 = time.perf_counter()
+        try:
+            return self._sendrecv_impl(dev, nbytes, src, dst)
+        finally:
+            self.seconds["sendrecv"] = self.seconds.get("sendrecv", 0.0) + time.perf_counter() - t0
+
+    def _sendrecv_impl(self, dev, nbytes, src, dst):
         try:
             nbytes = int(nbytes)
             self.bytes_dev += nbytes

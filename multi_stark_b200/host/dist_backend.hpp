@@ -9,12 +9,16 @@
 //     intermediate accumulators (src/prover.rs:391-409, src/lookup.rs:530-543);
 //   * Pcs::open: opened values are all-gathered (a few KB); after alpha each rank reduces its own height classes (p3-fri keeps
 //     one alpha-power counter per height, so a class that lives on one rank is reduced there exactly as on one GPU); the
-//     reduced vectors (16 B per LDE row) go to the FRI owner, which runs the fold-and-commit rounds and broadcasts each
-//     round's root; query rows come from the matrices' owners, sibling paths from the tree owners, and are all-gathered.
+//     reduced vectors (16 B per LDE row) go to the FRI owner, which runs the fold-and-commit rounds alone and broadcasts the
+//     roots, PoW witnesses and the folded vector ONCE (the other ranks replay the transcript); query rows come from the
+//     matrices' owners, sibling paths from the tree owners, and are all-gathered.
 // Rule: all circuits of one trace height live on one rank (their rows share leaf digests and reduced openings).
 // The proof is byte-identical to the single-GPU proof (tests/test_gpu_dist_prove.py).
 #pragma once
 #include "gpu_backend.hpp"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <set>
 
 extern "C" {
@@ -272,26 +276,53 @@ class DistOpenDevice : public OpenDevice {
         log_max_height = log_max_height_;
     }
     size_t current_len() override { return cur_len_; }
+    // FRI owner only (the default commit_phase loop runs there)
     Digest commit_round() override {
         Digest d{};
-        if (comm_.rank() == fri_owner_) gpu_check(msgpu_fri_commit_round(op_, d.data()));
-        comm_.bcast(d.data(), 32, fri_owner_);
-        n_layers_++;
+        gpu_check(msgpu_fri_commit_round(op_, d.data()));
         return d;
     }
     void fold(Fp2 beta) override {
         uint64_t b[2] = {beta.c[0].v, beta.c[1].v};
-        if (comm_.rank() == fri_owner_) gpu_check(msgpu_fri_fold(op_, b));
+        gpu_check(msgpu_fri_fold(op_, b));
         cur_len_ /= 2;
     }
-    std::vector<Fp2> read_current() override {
-        std::vector<uint64_t> flat(2 * cur_len_);
-        if (comm_.rank() == fri_owner_) gpu_check(msgpu_fri_read_current(op_, flat.data()));
-        comm_.bcast(flat.data(), flat.size() * 8, fri_owner_);
-        std::vector<Fp2> out(cur_len_);
-        for (size_t i = 0; i < cur_len_; i++) { out[i].c[0].v = flat[2 * i]; out[i].c[1].v = flat[2 * i + 1]; }
-        return out;
+    // The owner folds; every other rank replays the transcript from ONE broadcast of (roots, PoW witnesses, folded vector):
+    // the number of rounds and every length are known from the shapes alone.
+    void commit_phase(Challenger& ch, size_t stop_len, size_t pow_bits, FriProof& proof) override {
+        size_t rounds = 0;
+        for (size_t l = cur_len_; l > stop_len; l >>= 1) rounds++;
+        const size_t final_len = cur_len_ >> rounds;
+        std::vector<u8> blob(rounds * 40 + final_len * 16);
+        if (comm_.rank() == fri_owner_) {
+            OpenDevice::commit_phase(ch, stop_len, pow_bits, proof);
+            if (proof.commit_phase_commits.size() != rounds || cur_len_ != final_len) throw DistError("fri: internal error, round count");
+            for (size_t k = 0; k < rounds; k++) {
+                memcpy(blob.data() + 40 * k, proof.commit_phase_commits[k].data(), 32);
+                memcpy(blob.data() + 40 * k + 32, &proof.commit_pow_witnesses[k].v, 8);
+            }
+            gpu_check(msgpu_fri_read_current(op_, (uint64_t*)(blob.data() + rounds * 40)));
+        }
+        comm_.bcast(blob.data(), blob.size(), fri_owner_);
+        if (comm_.rank() != fri_owner_) {
+            for (size_t k = 0; k < rounds; k++) {
+                Digest d;
+                Fp w;
+                memcpy(d.data(), blob.data() + 40 * k, 32);
+                memcpy(&w.v, blob.data() + 40 * k + 32, 8);
+                ch.observe(d);
+                proof.commit_phase_commits.push_back(d);
+                if (!ch.check_witness(pow_bits, w)) throw DistError("fri: the owner's proof-of-work witness does not verify");
+                proof.commit_pow_witnesses.push_back(w);
+                (void)ch.sample_ext();  // beta
+            }
+            cur_len_ = final_len;
+        }
+        folded_.resize(final_len);
+        const uint64_t* f = (const uint64_t*)(blob.data() + rounds * 40);
+        for (size_t i = 0; i < final_len; i++) { folded_[i].c[0].v = f[2 * i]; folded_[i].c[1].v = f[2 * i + 1]; }
     }
+    std::vector<Fp2> read_current() override { return folded_; }
     std::vector<BatchOpening> open_round(size_t, const std::vector<size_t>&) override { throw DistError("open_round: use open_queries"); }
     std::vector<BatchOpening> open_layer(size_t, const std::vector<size_t>&) override { throw DistError("open_layer: use open_queries"); }
 
@@ -321,6 +352,13 @@ class DistOpenDevice : public OpenDevice {
     void open_queries(const std::vector<size_t>& indices, const std::vector<unsigned>& round_shifts, size_t n_layers,
                       std::vector<std::vector<BatchOpening>>& rounds_out, std::vector<std::vector<BatchOpening>>& layers_out) override {
         const size_t n = indices.size();
+        const bool trace = getenv("MSH_TRACE") != nullptr;
+        auto tq0 = std::chrono::steady_clock::now();
+        auto lapq = [&](const char* what) {
+            auto t1 = std::chrono::steady_clock::now();
+            if (trace) fprintf(stderr, "[msh] rank %d queries/%-12s %8.3f ms\n", comm_.rank(), what, std::chrono::duration<double, std::milli>(t1 - tq0).count());
+            tq0 = t1;
+        };
         // this rank's share in one launch
         std::vector<const msgpu_pdata*> trees;
         std::vector<uint32_t> shifts;
@@ -348,7 +386,9 @@ class DistOpenDevice : public OpenDevice {
         std::vector<u8> blob(open_total * 8 + proof_total);
         if (open_total) memcpy(blob.data(), opened.data(), open_total * 8);
         if (proof_total) memcpy(blob.data() + open_total * 8, proofs.data(), proof_total);
+        lapq("local_open");
         std::vector<std::vector<u8>> all = comm_.allgather_var(blob);
+        lapq("allgather");
 
         rounds_out.assign(handles_.size(), std::vector<BatchOpening>(n));
         layers_out.assign(n_layers, std::vector<BatchOpening>(n));
@@ -384,6 +424,7 @@ class DistOpenDevice : public OpenDevice {
                 }
             }
         }
+        lapq("assemble");
     }
 
   private:
@@ -396,7 +437,8 @@ class DistOpenDevice : public OpenDevice {
     std::map<size_t, int, std::greater<size_t>> classes_;
     int fri_owner_ = 0;
     unsigned log_max_height_ = 0;
-    size_t cur_len_ = 0, n_layers_ = 0;
+    size_t cur_len_ = 0;
+    std::vector<Fp2> folded_;
 };
 
 class DistGpuBackend : public GpuBackend {

@@ -47,6 +47,19 @@ struct OpenDevice {
     virtual Digest commit_round() = 0;
     virtual void fold(Fp2 beta) = 0;
     virtual std::vector<Fp2> read_current() = 0;
+    // FRI commit phase (p3-fri `commit_phase`): commit pairs -> observe root -> grind -> sample beta -> fold, until the vector
+    // is stop_len long. A sharded backend overrides it so that only the FRI owner folds and the other ranks replay the
+    // transcript from one broadcast.
+    virtual void commit_phase(Challenger& ch, size_t stop_len, size_t pow_bits, FriProof& proof) {
+        while (current_len() > stop_len) {
+            Digest commit = commit_round();
+            ch.observe(commit);
+            proof.commit_phase_commits.push_back(commit);
+            proof.commit_pow_witnesses.push_back(ch.grind(pow_bits));
+            Fp2 beta = ch.sample_ext();
+            fold(beta);
+        }
+    }
     // Mmcs::open_batch of round `r` at every index (already reduced to the round's height)
     virtual std::vector<BatchOpening> open_round(size_t r, const std::vector<size_t>& indices) = 0;
     // Mmcs::open_batch of commit-phase layer `k` at every pair index: opened row = 2 extension values
@@ -111,14 +124,7 @@ inline void pcs_open(OpenDevice& dev, const std::vector<OpenRound>& rounds, cons
     // commit phase
     proof = FriProof();
     const size_t stop_len = (size_t(1) << cp.log_blowup) << fp.log_final_poly_len;
-    while (dev.current_len() > stop_len) {
-        Digest commit = dev.commit_round();
-        ch.observe(commit);
-        proof.commit_phase_commits.push_back(commit);
-        proof.commit_pow_witnesses.push_back(ch.grind(fp.commit_proof_of_work_bits));
-        Fp2 beta = ch.sample_ext();
-        dev.fold(beta);
-    }
+    dev.commit_phase(ch, stop_len, fp.commit_proof_of_work_bits, proof);
     lap("fri/commit_phase");
     // final polynomial: undo the bit reversal, inverse DFT, keep final_poly_len coefficients
     std::vector<Fp2> folded = dev.read_current();

@@ -40,6 +40,8 @@ def main():
         traces = [ms.fib_trace(1 << log_heights[1]), byte, add]
     else:
         raise SystemExit("unknown kind")
+    traces = [ctx.pinned_copy(t) for t in traces]  # what a production caller hands over: page-locked host buffers
+    claims = ctx.pinned_copy(claims)
     heights = [t.shape[0] for t in traces]
     owner = msd.assign_owners(heights, world) if owners == "auto" else [int(x) for x in owners.split(",")]
     prover = msd.DistProver(ctx, system, owner)
@@ -55,6 +57,7 @@ def main():
         f.write(proof)
     info = {"rank": rank, "owner": owner, "heights": heights, "ms": times, "stages": prover.last_stage_ms,
             "bytes_dev": prover.comm.bytes_dev // reps, "bytes_host": prover.comm.bytes_host // reps, "launches": ctx.launches,
+            "comm_ms_per_proof": {k: v * 1e3 / reps for k, v in prover.comm.seconds.items()},
             "pre_commit": (prover.preprocessed_commit() or b"").hex()}
     if rank == 0 and os.environ.get("DIST_SINGLE", "1") == "1":
         # the same proof on one GPU through the ordinary prover
