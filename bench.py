@@ -264,6 +264,49 @@ def gpu_prove_leg(args, ms, ctx, steps, warmup, verify):
     return out
 
 
+def sharded_prove_leg(args, ms, msd, ctx, rank, world, steps=4):
+    """ONE proof over all ranks (BASELINE configs[3] shape, SURVEY 8e partitioning A): byte table + 7 U32-add circuits of
+    2^18..2^22 rows, circuits -> ranks by height class; compared with the same proof on one GPU (rank 0)."""
+    import hashlib
+    import torch
+    log_heights = [min(h, args.log_rows + 2) for h in (22, 21, 21, 20, 20, 19, 18)]
+    system = ms.System("multi:%d" % len(log_heights), **prove_params(args))
+    traces, claims = ms.multi_workload(log_heights)
+    heights = [t.shape[0] for t in traces]
+    owner = msd.assign_owners(heights, world)
+    prover = msd.DistProver(ctx, system, owner)
+    local = [ctx.pinned_copy(t) if owner[i] == rank else None for i, t in enumerate(traces)]
+    claims_p = ctx.pinned_copy(claims)
+    times = []
+    for it in range(steps + 1):
+        msd.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        proof = prover.prove(local, heights, claims_p)
+        if it:
+            times.append((time.perf_counter() - t0) * 1e3)
+    out = {"log_heights": log_heights, "owner": owner, "ms": msd.max_over_ranks(float(np.median(times))),
+           "stages_ms_rank0": prover.last_stage_ms, "proof_bytes": len(proof), "digest": hashlib.sha256(proof).hexdigest(),
+           "device_bytes_exchanged_this_rank": prover.comm.bytes_dev // (steps + 1),
+           "timing": "host wall clock around the call on every rank, median, max over ranks"}
+    digests = msd.gather_digests([bytes.fromhex(out["digest"])])
+    out["all_ranks_same_proof"] = len(set(digests)) == 1
+    prover.close()
+    if rank == 0:
+        single = ms.Prover(ctx, system)
+        pinned = [ctx.pinned_copy(t) for t in traces]
+        ts = []
+        for it in range(3):
+            t0 = time.perf_counter()
+            want = single.prove(pinned, claims_p)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        out["single_gpu_ms"] = float(np.min(ts[1:]))
+        out["identical_to_single_gpu_proof"] = want == proof
+        single.close()
+    msd.barrier()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -485,6 +528,8 @@ def main():
         if cpu is not None:
             prove["cpu"] = cpu_prove_time(args, min(args.log_rows, args.cpu_prove_log_rows))
         barrier()
+        if world > 1:
+            prove["sharded"] = sharded_prove_leg(args, ms, msd, ctx, rank, world)
 
     if rank == 0:
         print(json.dumps({
