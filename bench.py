@@ -376,6 +376,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: libmsgpu has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
         os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner out of stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 

@@ -165,7 +165,15 @@ __global__ void __launch_bounds__(kRedThreads) k_reduce_openings(ReduceParams p)
     if (p.w == pitch) {
         for (u32 e = threadIdx.x; e < nrows * p.w; e += blockDim.x) tile[e] = src[e];
     } else {
-        for (u32 e = threadIdx.x; e < nrows * p.w; e += blockDim.x) tile[(e / p.w) * pitch + e % p.w] = src[e];
+        // (row, column) of element e is advanced without a division per element
+        u32 rr = threadIdx.x / p.w, cc = threadIdx.x % p.w;
+        const u32 dr = kRedThreads / p.w, dc = kRedThreads % p.w;
+        for (u32 e = threadIdx.x; e < nrows * p.w; e += kRedThreads) {
+            tile[rr * pitch + cc] = src[e];
+            rr += dr;
+            cc += dc;
+            if (cc >= p.w) { cc -= p.w; rr++; }
+        }
     }
     __syncthreads();
     const u32 r = threadIdx.x / tpr, lane = threadIdx.x % tpr;  // tpr divides 32: a row's lanes sit in one warp

@@ -104,6 +104,95 @@ __global__ void __launch_bounds__(kLeafThreads) k_hash_rows_staged(const LeafMat
     }
 }
 
+// Wide rows (more than ~95 columns in total): staging whole rows would leave one warp per CTA hashing (32 rows x 2 KB at 256
+// columns), far too few to keep the ALU pipe busy. Here a CTA of 128 threads owns 128 rows and walks the row message in
+// segments of kSegWords words (4 BLAKE3 blocks): the segment of all 128 rows is staged with coalesced loads, every thread
+// compresses its row's 4 blocks and carries the chunk state (cv, chunk counter, subtree stack) in registers / local memory
+// to the next segment. 33 KB of shared memory per CTA, 6 CTAs = 24 hashing warps per SM.
+constexpr int kSegWords = 64;
+__global__ void __launch_bounds__(kLeafThreads) k_hash_rows_stream(const LeafMat* mats, u32 nmats, u64 height, u32 total_words,
+                                                                   u32* out) {
+    __shared__ u32 tile[kLeafThreads][kSegWords + 1];
+    const u64 row0 = (u64)blockIdx.x * kLeafThreads;
+    const u32 nrows = (u32)min((u64)kLeafThreads, height - row0);
+    const u32 nbytes = total_words * 4u;
+    const u32 nchunks = (nbytes + 1023u) / 1024u;  // >= 2 here
+    const bool live = threadIdx.x < nrows;
+    u32 stack[kMaxStack][8];
+    u32 sp = 0;
+    u32 cv[8];
+    for (u32 seg0 = 0; seg0 < total_words; seg0 += kSegWords) {
+        const u32 seg1 = min(seg0 + (u32)kSegWords, total_words);
+        // stage words [seg0, seg1) of every row: per matrix the overlapping columns (word offsets are even: whole u64)
+        for (u32 k = 0; k < nmats; k++) {
+            const LeafMat mt = mats[k];
+            const u32 w0 = max(seg0, mt.word_off), w1 = min(seg1, mt.word_off + 2u * mt.width);
+            if (w0 >= w1) continue;
+            const u32 c0 = (w0 - mt.word_off) >> 1, ncols = (w1 - w0) >> 1, base = w0 - seg0;
+            const u64* src = mt.ptr + row0 * mt.width + c0;
+            // thread t walks (r, c) pairs t, t + 128, ... with c fastest; the pair is advanced without divisions
+            u32 r = threadIdx.x / ncols, cc = threadIdx.x % ncols;
+            const u32 dr = kLeafThreads / ncols, dc = kLeafThreads % ncols;
+            while (r < nrows) {
+                u64 v = src[(u64)r * mt.width + cc];
+                tile[r][base + 2 * cc] = (u32)v;
+                tile[r][base + 2 * cc + 1] = (u32)(v >> 32);
+                r += dr;
+                cc += dc;
+                if (cc >= ncols) { cc -= ncols; r++; }
+            }
+        }
+        __syncthreads();
+        if (live) {
+            const u32* row = tile[threadIdx.x];
+#pragma unroll 1
+            for (u32 wb = seg0; wb < seg1; wb += 16) {
+                const u32 gb = wb >> 4, ci = gb >> 4, bi = gb & 15u;
+                const u32 cbytes = min(1024u, nbytes - ci * 1024u);
+                const u32 nblocks = (cbytes + 63u) / 64u;
+                if (bi == 0) b3::set_iv(cv);
+                u32 m[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) m[i] = (wb + i < total_words) ? row[wb - seg0 + i] : 0u;
+                const u32 flags = (bi == 0 ? b3::CHUNK_START : 0u) | (bi + 1 == nblocks ? b3::CHUNK_END : 0u);
+                b3::compress(cv, m, ci, 0, min(64u, cbytes - bi * 64u), flags);
+                if (bi + 1 != nblocks) continue;
+                // chunk finished: merge completed subtrees (one parent per trailing zero bit of the chunk count), or close the tree
+                if (ci + 1 < nchunks) {
+                    u32 total = ci + 1;
+                    while ((total & 1u) == 0) {
+                        sp--;
+                        u32 pm[16];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) { pm[i] = stack[sp][i]; pm[8 + i] = cv[i]; }
+                        b3::set_iv(cv);
+                        b3::compress(cv, pm, 0, 0, 64, b3::PARENT);
+                        total >>= 1;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i++) stack[sp][i] = cv[i];
+                    sp++;
+                } else {
+                    while (sp > 0) {
+                        sp--;
+                        u32 pm[16];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) { pm[i] = stack[sp][i]; pm[8 + i] = cv[i]; }
+                        b3::set_iv(cv);
+                        b3::compress(cv, pm, 0, 0, 64, b3::PARENT | (sp == 0 ? b3::ROOT : 0u));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (live) {
+        uint4* o = reinterpret_cast<uint4*>(out + (row0 + threadIdx.x) * 8);
+        o[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+        o[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+    }
+}
+
 // Fallback for rows too wide to stage (more than ~6000 columns in total): words read from global.
 __global__ void __launch_bounds__(kLeafThreads) k_hash_rows_direct(const LeafMat* mats, u32 nmats, u64 height,
                                                                    u32 total_words, u32* out) {
@@ -320,7 +409,11 @@ void b3_hash_rows(Ctx& c, const std::vector<MatRef>& mats, uint8_t* digests) {
     u32 pitch = total_words | 1u;
     size_t budget = 96 * 1024;
     u32 rows = (u32)std::min<size_t>(kLeafThreads, budget / ((size_t)pitch * 4));
-    if (rows >= 32 || (u64)rows >= height) {
+    if (rows < (u32)kLeafThreads && total_words * 4u > 1024u && height >= 32) {
+        u64 blocks = (height + kLeafThreads - 1) / kLeafThreads;
+        KLaunch kl(c, "k_hash_rows_stream");
+        k_hash_rows_stream<<<(unsigned)blocks, kLeafThreads, 0, c.stream>>>(d_mats, (u32)lm.size(), height, total_words, (u32*)digests);
+    } else if (rows >= 32 || (u64)rows >= height) {
         if (rows > 32) rows = rows / 32 * 32;
         if (rows == 0) rows = 1;
         static bool attr = false;

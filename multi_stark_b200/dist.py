@@ -318,11 +318,12 @@ class DistProver:
                                    for i, m in enumerate(mats)])
         hs = (_C.c_uint64 * n)(*[int(h) for h in heights])
         cl = np.ascontiguousarray(claims, dtype=np.uint64)
-        flat = cl.ravel() if cl.size else np.zeros(1, dtype=np.uint64)
-        offs = np.arange(cl.shape[0] + 1, dtype=np.uint64) * np.uint64(cl.shape[1] if cl.ndim == 2 else 0)
+        if cl.ndim != 2:
+            raise ValueError("claims: an (n, len) array is expected")
+        flat = cl.reshape(-1) if cl.size else np.zeros(1, dtype=np.uint64)
         out, ln = _C.c_void_p(), _C.c_uint64()
         ms = (_C.c_double * 6)()
-        rc = self.H.msh_prove(self.h, ptrs, hs, flat.ctypes.data_as(_ffi.c_u64p), offs.ctypes.data_as(_ffi.c_u64p), cl.shape[0],
+        rc = self.H.msh_prove(self.h, ptrs, hs, flat.ctypes.data_as(_ffi.c_u64p), None, cl.shape[1], cl.shape[0],
                               _C.byref(out), _C.byref(ln), ms)
         if rc != 0:
             raise _ffi.MsgpuError(rc, (self.H.msh_last_error() or b"").decode() + " " + "; ".join(self.comm.errors))

@@ -136,10 +136,10 @@ int msh_prover_preprocessed_commit(const msh_prover* p, uint8_t* out32) {
     return 1;
 }
 // traces[i]: HOST heights[i] x main_width of circuit i, canonical values (heights[i] = 0: circuit inactive).
-// claims: flat values, offsets[n_claims + 1]. proof_out receives Proof::to_bytes (src/prover.rs:246-249), to be released with
+// claims: flat values, offsets[n_claims + 1], or offsets = NULL and claim_stride values per claim. proof_out receives Proof::to_bytes (src/prover.rs:246-249), to be released with
 // msh_bytes_free. stage_ms[6] (optional): stage1_commit, claims, stage2_commit, quotient, fri_open, total (host wall clock).
 int msh_prove(msh_prover* p, const uint64_t* const* traces, const uint64_t* heights, const uint64_t* claims, const uint64_t* offsets,
-              uint64_t n_claims, uint8_t** proof_out, uint64_t* proof_len, double* stage_ms) {
+              uint64_t claim_stride, uint64_t n_claims, uint8_t** proof_out, uint64_t* proof_len, double* stage_ms) {
     try {
         const SystemShape& shape = p->sys->shape;
         std::vector<MatrixView> views;
@@ -147,7 +147,8 @@ int msh_prove(msh_prover* p, const uint64_t* const* traces, const uint64_t* heig
             views.push_back(MatrixView((const Fp*)traces[i], (size_t)heights[i], shape.circuits[i].main_width));
         ClaimsView cl;
         cl.values = (const Fp*)claims;
-        cl.offsets = offsets;
+        cl.offsets = offsets;  // NULL: n_claims claims of claim_stride values each
+        cl.stride = (size_t)claim_stride;
         cl.n = (size_t)n_claims;
         ProveTimings tm;
         Proof proof = p->prover->prove(cl, views, &tm);

@@ -175,16 +175,20 @@ struct MatrixView {
 };
 
 // Borrowed claims: `values` flat, claim i = values[offsets[i] .. offsets[i+1])  (src/prover.rs:289-294 `claims: &[&[Val]]`).
+// offsets == nullptr: every claim has `stride` values (one call shape, the common case: no offsets array to build or scan).
 struct ClaimsView {
     const Fp* values = nullptr;
     const u64* offsets = nullptr;
     size_t n = 0;
+    size_t stride = 0;
     size_t size() const { return n; }
-    size_t len(size_t i) const { return (size_t)(offsets[i + 1] - offsets[i]); }
-    const Fp* at(size_t i) const { return values + offsets[i]; }
-    // all claims of one length (the common case: one call shape), 0 if empty or ragged
+    size_t len(size_t i) const { return offsets ? (size_t)(offsets[i + 1] - offsets[i]) : stride; }
+    const Fp* at(size_t i) const { return values + (offsets ? (size_t)offsets[i] : i * stride); }
+    size_t total() const { return n == 0 ? 0 : (offsets ? (size_t)offsets[n] : n * stride); }
+    // all claims of one length, 0 if empty or ragged
     size_t uniform_len() const {
         if (n == 0) return 0;
+        if (!offsets) return stride;
         size_t l = len(0);
         for (size_t i = 1; i < n; i++)
             if (len(i) != l) return 0;

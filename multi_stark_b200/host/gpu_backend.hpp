@@ -246,7 +246,7 @@ class GpuBackend : public ProverBackend {
     bool observe_claims(Challenger& ch, const ClaimsView& claims) override {
         size_t len = claims.uniform_len();
         if (len == 0 || claims.size() * len < 4096) {  // small or ragged: the host loop is cheaper; the ABI's precondition is checked here
-            size_t total = claims.size() ? (size_t)claims.offsets[claims.size()] : 0;
+            size_t total = claims.total();
             for (size_t k = 0; k < total; k++)
                 if (claims.values[k].v >= GL_P) throw GpuError("claim value is not canonical");
             return false;

@@ -66,7 +66,11 @@ def test_gen_pcs_refs_merkle(gpu):
 @pytest.mark.parametrize("shapes", [[(16, 1)], [(16, 3), (16, 2)], [(4, 5), (32, 1), (32, 9), (8, 2)], [(2, 140)],
                                     [(64, 14), (2, 1)], [(8, 300), (8, 1), (4, 129)], [(1, 5)], [(1, 1), (1, 2)],
                                     [(4096, 14), (256, 1)], [(1 << 14, 26), (1 << 14, 2), (1 << 9, 2)],
-                                    [(512, 256)], [(256, 2625)]])
+                                    [(512, 256)], [(256, 2625)],
+                                    # the streamed wide-row kernel: segment / chunk boundaries, matrices straddling segments,
+                                    # ragged last block, partial last CTA
+                                    [(64, 129)], [(256, 200), (256, 57)], [(128, 300), (128, 3), (128, 64), (32, 131)],
+                                    [(32, 513)], [(1024, 97), (1024, 33), (64, 1000)]])
 def test_mmcs_random_vs_oracle(gpu, oracle, shapes):
     ms, ctx = gpu
     rng = np.random.default_rng(len(shapes) * 31 + shapes[0][0])
