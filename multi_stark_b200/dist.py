@@ -259,6 +259,38 @@ class TorchComm:
             return 1
 
 
+def _all_to_all_dev(self, send_ptr, send_counts, recv_ptr, recv_counts):
+    """Device all-to-all with per-peer byte counts (chunks in rank order in both buffers)."""
+    t0 = time.perf_counter()
+    self.bytes_dev += sum(send_counts) - send_counts[self.rank] + sum(recv_counts) - recv_counts[self.rank]
+    if self.nccl:
+        dev = torch.device("cuda", torch.cuda.current_device())
+        s = torch.as_tensor(_DevView(send_ptr, sum(send_counts)), device=dev)
+        r = torch.as_tensor(_DevView(recv_ptr, sum(recv_counts)), device=dev)
+        self.dist.all_to_all_single(r, s, output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts), group=self.group)
+        torch.cuda.current_stream().synchronize()
+    else:  # gloo: staged through the host, pairwise
+        so = [sum(send_counts[:k]) for k in range(self.world)]
+        ro = [sum(recv_counts[:k]) for k in range(self.world)]
+        host_s = torch.empty(max(sum(send_counts), 1), dtype=torch.uint8)
+        host_r = torch.empty(max(sum(recv_counts), 1), dtype=torch.uint8)
+        check(self.ctx.L.msgpu_memcpy_d2h(self.ctx.h, _C.c_void_p(host_s.data_ptr()), _C.c_void_p(send_ptr), sum(send_counts)))
+        reqs = []
+        for k in range(self.world):
+            if k == self.rank:
+                host_r[ro[k]:ro[k] + recv_counts[k]] = host_s[so[k]:so[k] + send_counts[k]]
+                continue
+            reqs.append(self.dist.isend(host_s[so[k]:so[k] + send_counts[k]], dst=self._global(k), group=self.group))
+            reqs.append(self.dist.irecv(host_r[ro[k]:ro[k] + recv_counts[k]], src=self._global(k), group=self.group))
+        for q in reqs:
+            q.wait()
+        check(self.ctx.L.msgpu_memcpy_h2d(self.ctx.h, _C.c_void_p(recv_ptr), _C.c_void_p(host_r.data_ptr()), sum(recv_counts)))
+    self.seconds["all_to_all"] = self.seconds.get("all_to_all", 0.0) + time.perf_counter() - t0
+
+
+TorchComm.all_to_all_dev = _all_to_all_dev
+
+
 def assign_owners(heights, world_size):
     """Circuit -> rank for one sharded proof. Circuits of one trace height must share a rank (their rows share leaf digests
     and reduced openings); height classes are placed greedily, heaviest first, on the least loaded rank. `heights[i]` = trace
@@ -336,3 +368,139 @@ class DistProver:
         if getattr(self, "h", None):
             self.H.msh_prover_free(self.h)
             self.h = None
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Pcs::commit of ONE wide matrix over the ranks (SURVEY 8e partitioning B, BASELINE configs[2]): column blocks.
+# ------------------------------------------------------------------------------------------------------------------
+def column_blocks(width, world_size):
+    """Contiguous balanced column blocks [c0, c1) per rank (the first width % world ranks get one more column)."""
+    base, rem = divmod(width, world_size)
+    out, c = [], 0
+    for r in range(world_size):
+        n = base + (1 if r < rem else 0)
+        out.append((c, c + n))
+        c += n
+    return out
+
+
+class WideCommit:
+    """Prover data of a column-block sharded commitment: this rank's ROW shard of the LDE (every column, rows
+    [rank * H / N, (rank + 1) * H / N) of the bit-reversed storage) with its Merkle subtree, and the top of the tree."""
+
+    def __init__(self, ctx, comm, local, top, root, lde_height, widths, recv_buf):
+        self.ctx, self.comm, self.local, self.top, self.root = ctx, comm, local, top, root
+        self.lde_height, self.widths, self._recv = lde_height, widths, recv_buf
+
+    def open_batch(self, indices):
+        """Mmcs::open_batch: (rows [n, width], sibling paths [n, log2(H), 32]) -- the same on every rank. The row and the
+        lower part of the path come from the rank that holds the row, the top log2(N) siblings from the top tree."""
+        import numpy as np
+        n, world = len(indices), self.comm.world
+        shard = self.lde_height // world
+        lo_depth, width = shard.bit_length() - 1, sum(self.widths)
+        rows = np.zeros((n, width), dtype=np.uint64)
+        paths = np.zeros((n, lo_depth + (world.bit_length() - 1), 32), dtype=np.uint8)
+        mine = [k for k, i in enumerate(indices) if int(i) // shard == self.comm.rank]
+        if mine:
+            o, p = self.local.open_batch([int(indices[k]) % shard for k in mine])
+            rows[mine] = o
+            paths[mine, :lo_depth] = p
+        if world > 1:
+            # the top tree has no matrices: sibling paths only
+            tidx = np.array([int(i) // shard for i in indices], dtype=np.uint64)
+            tp = np.zeros((n, world.bit_length() - 1, 32), dtype=np.uint8)
+            dummy = np.zeros(1, dtype=np.uint64)
+            check(self.ctx.L.msgpu_open_batch(self.ctx.h, self.top.h, tidx.ctypes.data_as(_C.c_void_p), n,
+                                              dummy.ctypes.data_as(_C.c_void_p), tp.ctypes.data_as(_C.c_void_p)))
+            # every rank holds the same top tree; rows / lower paths are summed over the ranks (all others contribute zeros)
+            blob = np.concatenate([rows.view(np.uint8).ravel(), paths[:, :lo_depth].ravel()])
+            allb = np.zeros(blob.size * world, dtype=np.uint8)
+            if self.comm.struct.allgather_host(None, blob.ctypes.data, allb.ctypes.data, blob.size) != 0:
+                raise RuntimeError("allgather failed: %s" % self.comm.errors)
+            allb = allb.reshape(world, -1)
+            for k, i in enumerate(indices):
+                src = allb[int(i) // shard]
+                rows[k] = src[:rows.nbytes].view(np.uint64).reshape(n, width)[k]
+                paths[k, :lo_depth] = src[rows.nbytes:].reshape(n, lo_depth, 32)[k]
+            paths[:, lo_depth:] = tp
+        return rows, paths
+
+    def free(self):
+        for h in (self.local, self.top):
+            if h is not None:
+                h.free()
+        if self._recv:
+            self.ctx.free(self._recv)
+            self._recv = None
+
+
+def commit_wide_sharded(ctx, comm, block, width, log_blowup, timings=None):
+    """`Pcs::commit` (src/prover.rs:350) of one n x `width` matrix whose COLUMN block `column_blocks(width, N)[rank]` is
+    `block` (host array n x w_r, canonical values) on this rank. Per rank: upload + coset LDE of the block (the NTT is
+    column-local), ONE all-to-all that turns column blocks into row shards (the block's rows [d * H / N, (d+1) * H / N) are
+    contiguous and go to rank d), leaf hashing of the shard's full rows + its Merkle subtree, then the N subtree roots are
+    all-gathered and the top log2(N) levels built on every rank. Root and openings are bit-identical to a single-GPU commit."""
+    import numpy as np
+    from .pcs import ProverData
+    L = ctx.L
+    world, rank = comm.world, comm.rank
+    if world & (world - 1):
+        raise ValueError("column-block sharding needs a power-of-two number of ranks")
+    blocks = column_blocks(width, world)
+    widths = [c1 - c0 for c0, c1 in blocks]
+    a = np.ascontiguousarray(block, dtype=np.uint64)
+    n, w = a.shape
+    if w != widths[rank] or min(widths) == 0:
+        raise ValueError("this rank's block must have %d columns (and every rank at least one)" % widths[rank])
+    H = n << log_blowup
+    if H % world or H // world < 1:
+        raise ValueError("LDE height must be a multiple of the number of ranks")
+    shard = H // world
+    t = [time.perf_counter()]
+    d_in = ctx.upload_canonical(a)
+    t.append(time.perf_counter())
+    d_lde = ctx.malloc(H * w * 8)
+    check(L.msgpu_coset_lde_batch_bitrev_dev(ctx.h, _C.c_void_p(d_in), n, w, log_blowup, 7, _C.c_void_p(d_lde)))
+    ctx.free(d_in)
+    ctx.sync()
+    t.append(time.perf_counter())
+    # all-to-all: chunk d of my LDE (rows of shard d, my columns) -> rank d; I receive shard `rank` of every block
+    recv = ctx.malloc(shard * width * 8)
+    send_counts = [shard * w * 8] * world
+    recv_counts = [shard * ws * 8 for ws in widths]
+    comm.all_to_all_dev(d_lde, send_counts, recv, recv_counts)
+    ctx.free(d_lde)
+    ctx.sync()
+    t.append(time.perf_counter())
+    # the shard as N matrices of one height: their rows concatenate in column order inside the leaf hash
+    ptrs, off = [], 0
+    for ws in widths:
+        ptrs.append(recv + off)
+        off += shard * ws * 8
+    pa = (_C.c_void_p * world)(*ptrs)
+    hs = (_C.c_uint64 * world)(*([shard] * world))
+    wa = (_C.c_uint64 * world)(*widths)
+    h = _C.c_void_p()
+    sub_root = np.zeros(32, dtype=np.uint8)
+    check(L.msgpu_commit_ldes_dev(ctx.h, pa, hs, wa, world, 0, _C.byref(h), sub_root.ctypes.data_as(_C.c_void_p)))
+    local = ProverData(ctx, h, bytes(sub_root))
+    t.append(time.perf_counter())
+    top, root = None, bytes(sub_root)
+    if world > 1:
+        roots = np.zeros(32 * world, dtype=np.uint8)
+        if comm.struct.allgather_host(None, sub_root.ctypes.data, roots.ctypes.data, 32) != 0:
+            raise RuntimeError("allgather failed: %s" % comm.errors)
+        d_roots = ctx.upload(roots)
+        th = _C.c_void_p()
+        r32 = np.zeros(32, dtype=np.uint8)
+        hh = (_C.c_uint64 * 1)(world)
+        pp = (_C.c_void_p * 1)(d_roots)
+        check(L.msgpu_tree_from_digests(ctx.h, 1, hh, pp, _C.byref(th), r32.ctypes.data_as(_C.c_void_p)))
+        ctx.free(d_roots)
+        top, root = ProverData(ctx, th, bytes(r32)), bytes(r32)
+    t.append(time.perf_counter())
+    if timings is not None:
+        for k, name in enumerate(["upload", "lde", "all_to_all", "leaf_hash_subtree", "top"]):
+            timings[name] = timings.get(name, 0.0) + (t[k + 1] - t[k]) * 1e3
+    return root, WideCommit(ctx, comm, local, top, root, H, widths, recv)
