@@ -204,6 +204,12 @@ int msgpu_claims_accumulator(msgpu_ctx* ctx, const uint64_t* claims, uint64_t n_
 typedef struct msgpu_claims msgpu_claims;
 int msgpu_claims_upload(msgpu_ctx* ctx, const uint64_t* claims, uint64_t n_claims, uint64_t claim_len,
                         const uint8_t* transcript_prefix, uint64_t prefix_len, msgpu_claims** out, uint8_t* digest32);
+/* The same in two steps, so that the transfer overlaps kernels: claims_prefetch starts the host-to-device copy on the
+ * context's copy stream, ordered behind everything already enqueued on the main stream (call it right after the trace
+ * upload: PCIe is idle while the stage-1 LDE and Merkle kernels run); claims_digest then waits for the copy and returns the
+ * digest of msgpu_claims_upload. `claims` must stay valid (pinned host memory for a real overlap) until claims_digest returns. */
+int msgpu_claims_prefetch(msgpu_ctx* ctx, const uint64_t* claims, uint64_t n_claims, uint64_t claim_len, msgpu_claims** out);
+int msgpu_claims_digest(msgpu_claims* cl, const uint8_t* transcript_prefix, uint64_t prefix_len, uint8_t* digest32);
 int msgpu_claims_accumulate(msgpu_claims* cl, const uint64_t* beta2, const uint64_t* gamma2, uint64_t* out2);
 void msgpu_claims_free(msgpu_claims* cl);
 

@@ -66,6 +66,8 @@ SIGNATURES = {
     "msgpu_claims_accumulator": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                            C.c_void_p]),
     "msgpu_claims_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, c_vpp, C.c_void_p]),
+    "msgpu_claims_prefetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, c_vpp]),
+    "msgpu_claims_digest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "msgpu_claims_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "msgpu_claims_free": (None, [C.c_void_p]),
     "msgpu_quotient": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,

@@ -207,6 +207,7 @@ void msgpu_ctx_destroy(msgpu_ctx* h) {
     cudaStreamSynchronize(h->c.stream);
     for (void* p : h->c.owned) cudaFree(p);
     h->c.arena_destroy();
+    if (h->c.copy_stream) cudaStreamDestroy(h->c.copy_stream);
     if (h->c.own_stream) cudaStreamDestroy(h->c.stream);
     delete h;
 }

@@ -44,6 +44,7 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;  // lazily created: host-to-device prefetches that overlap kernels of `stream`
     unsigned long long launches = 0;  // kernels of this library launched so far
     int sm_count = 148;
     u64* tw_full[2] = {nullptr, nullptr};  // w_1024^{i} / w_1024^{-i}, i < 1024

@@ -655,6 +655,7 @@ struct msgpu_claims {
     Ctx* ctx;
     u64* d;
     u64 n, len;
+    cudaEvent_t ready = nullptr;  // prefetched claims: the copy on the context's copy stream has finished
 };
 
 namespace msg {
@@ -778,16 +779,62 @@ int msgpu_claims_accumulator(msgpu_ctx* h, const uint64_t* claims, uint64_t n_cl
     });
 }
 
+// BLAKE3(prefix || encoded claims) of device-resident claims + the canonical check (shared by upload and digest)
+static void claims_digest(Ctx& c, const u64* d_claims, u64 n_claims, u64 claim_len, const uint8_t* prefix, u64 prefix_len, uint8_t* digest32);
+
 int msgpu_claims_upload(msgpu_ctx* h, const uint64_t* claims, uint64_t n_claims, uint64_t claim_len, const uint8_t* prefix,
                         uint64_t prefix_len, msgpu_claims** out, uint8_t* digest32) {
     return guard([&] {
         Ctx& c = h->c;
         MSG_REQUIRE(out && digest32 && claims && n_claims > 0 && claim_len > 0, "claims_upload: null or empty argument");
         MSG_REQUIRE(claim_len < (1ull << 31) && n_claims <= (~0ull) / 16 / (claim_len + 1), "claims_upload: too large");
+        u64 n_vals = n_claims * claim_len;
+        DevBuf d(c, n_vals * 8);
+        MSG_CUDA(cudaMemcpyAsync(d.p, claims, n_vals * 8, cudaMemcpyHostToDevice, c.stream));
+        claims_digest(c, d.u(), n_claims, claim_len, prefix, prefix_len, digest32);
+        *out = new msgpu_claims{&c, (u64*)d.release(), n_claims, claim_len};
+    });
+}
+
+int msgpu_claims_prefetch(msgpu_ctx* h, const uint64_t* claims, uint64_t n_claims, uint64_t claim_len, msgpu_claims** out) {
+    return guard([&] {
+        Ctx& c = h->c;
+        MSG_REQUIRE(out && claims && n_claims > 0 && claim_len > 0, "claims_prefetch: null or empty argument");
+        MSG_REQUIRE(claim_len < (1ull << 31) && n_claims <= (~0ull) / 16 / (claim_len + 1), "claims_prefetch: too large");
+        if (!c.copy_stream) MSG_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        u64 n_vals = n_claims * claim_len;
+        DevBuf d(c, n_vals * 8);
+        // the copy starts behind everything already enqueued on the main stream (the block may have just been freed by it,
+        // and the trace upload should have the link to itself) and runs under whatever the main stream does next
+        cudaEvent_t e0, ready;
+        MSG_CUDA(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+        MSG_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        MSG_CUDA(cudaEventRecord(e0, c.stream));
+        MSG_CUDA(cudaStreamWaitEvent(c.copy_stream, e0, 0));
+        MSG_CUDA(cudaMemcpyAsync(d.p, claims, n_vals * 8, cudaMemcpyHostToDevice, c.copy_stream));
+        MSG_CUDA(cudaEventRecord(ready, c.copy_stream));
+        cudaEventDestroy(e0);
+        msgpu_claims* cl = new msgpu_claims{&c, (u64*)d.release(), n_claims, claim_len};
+        cl->ready = ready;
+        *out = cl;
+    });
+}
+
+int msgpu_claims_digest(msgpu_claims* cl, const uint8_t* prefix, uint64_t prefix_len, uint8_t* digest32) {
+    return guard([&] {
+        MSG_REQUIRE(cl && digest32, "claims_digest: null argument");
+        Ctx& c = *cl->ctx;
+        if (cl->ready) MSG_CUDA(cudaStreamWaitEvent(c.stream, cl->ready, 0));
+        claims_digest(c, cl->d, cl->n, cl->len, prefix, prefix_len, digest32);
+    });
+}
+
+static void claims_digest(Ctx& c, const u64* d_claims, u64 n_claims, u64 claim_len, const uint8_t* prefix, u64 prefix_len, uint8_t* digest32) {
+    {
         StageScope ss(c, "transcript");
         u64 n_vals = n_claims * claim_len, n_words = n_claims * (claim_len + 1), msg_len = prefix_len + 8 * n_words;
-        DevBuf d(c, n_vals * 8), msg(c, msg_len + 64), flag(c, 4);
-        MSG_CUDA(cudaMemcpyAsync(d.p, claims, n_vals * 8, cudaMemcpyHostToDevice, c.stream));
+        DevBuf msg(c, msg_len + 64), flag(c, 4);
+        struct { const u64* p; const u64* u() const { return p; } } d{d_claims};
         MSG_CUDA(cudaMemsetAsync(flag.p, 0, 4, c.stream));
         check_canonical(c, d.u(), n_vals, (u32*)flag.p);
         if (prefix_len) MSG_CUDA(cudaMemcpyAsync(msg.p, prefix, prefix_len, cudaMemcpyHostToDevice, c.stream));
@@ -813,17 +860,21 @@ int msgpu_claims_upload(msgpu_ctx* h, const uint64_t* claims, uint64_t n_claims,
             memcpy(digest32, dg.data(), 32);
         }
         MSG_REQUIRE(bad == 0, "claims_upload: claim value is not a canonical field element (>= p)");
-        *out = new msgpu_claims{&c, (u64*)d.release(), n_claims, claim_len};
-    });
+    }
 }
 int msgpu_claims_accumulate(msgpu_claims* cl, const uint64_t* beta2, const uint64_t* gamma2, uint64_t* out2) {
     return guard([&] {
         MSG_REQUIRE(cl && beta2 && gamma2 && out2, "claims_accumulate: null argument");
+        if (cl->ready) MSG_CUDA(cudaStreamWaitEvent(cl->ctx->stream, cl->ready, 0));
         claims_sum(*cl->ctx, cl->d, cl->n, cl->len, beta2, gamma2, out2);
     });
 }
 void msgpu_claims_free(msgpu_claims* cl) {
     if (!cl) return;
+    if (cl->ready) {
+        cudaEventSynchronize(cl->ready);  // the copy must not outlive the block
+        cudaEventDestroy(cl->ready);
+    }
     try {
         cl->ctx->free(cl->d);
     } catch (...) {

@@ -494,6 +494,7 @@ class DistGpuBackend : public GpuBackend {
             trace_rows_.push_back(m.height());
             mats.push_back(dm);
         }
+        prefetch_announced_claims();
         return dist_commit(ctx_, comm_, mats, (uint32_t)shape_.log_blowup(), false, root);
     }
 

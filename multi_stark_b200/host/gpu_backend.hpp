@@ -238,10 +238,13 @@ class GpuBackend : public ProverBackend {
             hs.push_back(m.height());
             ws.push_back(m.width);
         }
+        prefetch_announced_claims();  // the traces are on the device: the claims travel under the LDE / Merkle kernels
         msgpu_pdata* pd = nullptr;
         gpu_check(msgpu_commit_dev(ctx_, ptrs.data(), hs.data(), ws.data(), traces.size(), (uint32_t)shape_.log_blowup(), &pd, root.data()));
         return std::make_shared<GpuPcsHandle>(pd);
     }
+
+    void announce_claims(const ClaimsView& claims) override { announced_ = claims; }
 
     bool observe_claims(Challenger& ch, const ClaimsView& claims) override {
         size_t len = claims.uniform_len();
@@ -251,11 +254,16 @@ class GpuBackend : public ProverBackend {
                 if (claims.values[k].v >= GL_P) throw GpuError("claim value is not canonical");
             return false;
         }
-        drop_claims();
         Digest d;
         const std::vector<u8>& prefix = ch.input_buffer();
-        gpu_check(msgpu_claims_upload(ctx_, (const uint64_t*)claims.at(0), claims.size(), len, prefix.data(), prefix.size(), &claims_dev_,
-                                      d.data()));
+        if (claims_dev_ && prefetched_from_ == (const void*)claims.at(0) && prefetched_n_ == claims.size() && prefetched_len_ == len) {
+            gpu_check(msgpu_claims_digest(claims_dev_, prefix.data(), prefix.size(), d.data()));
+        } else {
+            drop_claims();
+            gpu_check(msgpu_claims_upload(ctx_, (const uint64_t*)claims.at(0), claims.size(), len, prefix.data(), prefix.size(), &claims_dev_,
+                                          d.data()));
+        }
+        prefetched_from_ = nullptr;
         ch.set_flushed(d);
         return true;
     }
@@ -379,7 +387,23 @@ class GpuBackend : public ProverBackend {
     void drop_claims() {
         if (claims_dev_) msgpu_claims_free(claims_dev_);
         claims_dev_ = nullptr;
+        prefetched_from_ = nullptr;
     }
+    // same size rule as observe_claims: small or ragged claim sets stay on the host
+    void prefetch_announced_claims() {
+        ClaimsView cl = announced_;
+        announced_ = ClaimsView();
+        size_t len = cl.uniform_len();
+        if (len == 0 || cl.size() * len < 4096) return;
+        drop_claims();
+        gpu_check(msgpu_claims_prefetch(ctx_, (const uint64_t*)cl.at(0), cl.size(), len, &claims_dev_));
+        prefetched_from_ = (const void*)cl.at(0);
+        prefetched_n_ = cl.size();
+        prefetched_len_ = len;
+    }
+    ClaimsView announced_;
+    const void* prefetched_from_ = nullptr;
+    size_t prefetched_n_ = 0, prefetched_len_ = 0;
     msgpu_ctx* ctx_;
     msgpu_claims* claims_dev_ = nullptr;
     const SystemShape& shape_;

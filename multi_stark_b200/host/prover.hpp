@@ -27,6 +27,9 @@ struct ProverBackend {
     virtual PcsHandlePtr commit_stage1(const std::vector<size_t>& circuits, const std::vector<MatrixView>& traces, Digest& root) = 0;
     // sum over claims of 1 / (beta + fingerprint(gamma, claim))  (src/prover.rs:381-387)
     virtual Fp2 claims_accumulator(const ClaimsView& claims, Fp2 beta, Fp2 gamma) = 0;
+    // Optional: the claims of the proof about to start; a device backend begins their upload once the traces are on the
+    // device, under the stage-1 kernels (the claims are first needed after the stage-1 root, src/prover.rs:364-387).
+    virtual void announce_claims(const ClaimsView&) {}
     // Optional: observe every claim (length-prefixed, src/prover.rs:369-372) into the transcript on the backend's side and
     // leave the challenger flushed (the next transcript operation is always a sample, src/prover.rs:376). false = not done.
     virtual bool observe_claims(Challenger&, const ClaimsView&) { return false; }
@@ -113,6 +116,7 @@ class Prover {
             log_degrees.push_back(log2_strict(traces[ci].height()));
             active_traces.push_back(traces[ci]);
         }
+        be_.announce_claims(claims);
         PcsHandlePtr s1 = be_.commit_stage1(active_indices, active_traces, proof.stage_1_trace);
         lap("stark/stage1_commit");
         if (key_.has_preprocessed) ch.observe(key_.preprocessed_commit);
