@@ -14,6 +14,14 @@ struct LeafMat {
     u32 width;
     u32 word_off;  // offset of this matrix's words inside the concatenated row message
 };
+// The matrices of one height class: up to kInlineMats travel as a kernel parameter (no allocation, no upload: a FRI proof
+// commits ~20 single-matrix layers), longer lists through device memory.
+constexpr int kInlineMats = 8;
+struct LeafList {
+    LeafMat inl[kInlineMats];
+    const LeafMat* ext;
+    __device__ __forceinline__ LeafMat at(u32 k) const { return ext ? ext[k] : inl[k]; }
+};
 
 constexpr int kLeafThreads = 128;
 constexpr int kMaxStack = 24;
@@ -75,14 +83,14 @@ __device__ __forceinline__ void hash_words(Get get, u32 total_words, u32 out[8])
 
 // One thread per leaf; rows are staged through shared memory with an odd word pitch so that the
 // coalesced global reads turn into conflict-free per-thread row reads.
-__global__ void __launch_bounds__(kLeafThreads) k_hash_rows_staged(const LeafMat* mats, u32 nmats, u64 height,
+__global__ void __launch_bounds__(kLeafThreads) k_hash_rows_staged(const __grid_constant__ LeafList mats, u32 nmats, u64 height,
                                                                    u32 total_words, u32 pitch, u32 rows_per_cta,
                                                                    u32* out) {
     extern __shared__ u32 sm32[];
     const u64 row0 = (u64)blockIdx.x * rows_per_cta;
     const u32 nrows = (u32)min((u64)rows_per_cta, height - row0);
     for (u32 k = 0; k < nmats; k++) {
-        const LeafMat mt = mats[k];
+        const LeafMat mt = mats.at(k);
         const u64* src = mt.ptr + row0 * mt.width;
         const u32 total = nrows * mt.width;
         for (u32 e = threadIdx.x; e < total; e += blockDim.x) {
@@ -110,7 +118,7 @@ __global__ void __launch_bounds__(kLeafThreads) k_hash_rows_staged(const LeafMat
 // compresses its row's 4 blocks and carries the chunk state (cv, chunk counter, subtree stack) in registers / local memory
 // to the next segment. 33 KB of shared memory per CTA, 6 CTAs = 24 hashing warps per SM.
 constexpr int kSegWords = 64;
-__global__ void __launch_bounds__(kLeafThreads) k_hash_rows_stream(const LeafMat* mats, u32 nmats, u64 height, u32 total_words,
+__global__ void __launch_bounds__(kLeafThreads) k_hash_rows_stream(const __grid_constant__ LeafList mats, u32 nmats, u64 height, u32 total_words,
                                                                    u32* out) {
     __shared__ u32 tile[kLeafThreads][kSegWords + 1];
     const u64 row0 = (u64)blockIdx.x * kLeafThreads;
@@ -125,7 +133,7 @@ __global__ void __launch_bounds__(kLeafThreads) k_hash_rows_stream(const LeafMat
         const u32 seg1 = min(seg0 + (u32)kSegWords, total_words);
         // stage words [seg0, seg1) of every row: per matrix the overlapping columns (word offsets are even: whole u64)
         for (u32 k = 0; k < nmats; k++) {
-            const LeafMat mt = mats[k];
+            const LeafMat mt = mats.at(k);
             const u32 w0 = max(seg0, mt.word_off), w1 = min(seg1, mt.word_off + 2u * mt.width);
             if (w0 >= w1) continue;
             const u32 c0 = (w0 - mt.word_off) >> 1, ncols = (w1 - w0) >> 1, base = w0 - seg0;
@@ -194,7 +202,7 @@ __global__ void __launch_bounds__(kLeafThreads) k_hash_rows_stream(const LeafMat
 }
 
 // Fallback for rows too wide to stage (more than ~6000 columns in total): words read from global.
-__global__ void __launch_bounds__(kLeafThreads) k_hash_rows_direct(const LeafMat* mats, u32 nmats, u64 height,
+__global__ void __launch_bounds__(kLeafThreads) k_hash_rows_direct(const __grid_constant__ LeafList mats, u32 nmats, u64 height,
                                                                    u32 total_words, u32* out) {
     u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= height) return;
@@ -202,9 +210,10 @@ __global__ void __launch_bounds__(kLeafThreads) k_hash_rows_direct(const LeafMat
     hash_words(
         [&](u32 k) {
             u32 mi = 0;
-            while (mi + 1 < nmats && mats[mi + 1].word_off <= k) mi++;
-            u32 kk = k - mats[mi].word_off;
-            u64 v = mats[mi].ptr[r * mats[mi].width + (kk >> 1)];
+            while (mi + 1 < nmats && mats.at(mi + 1).word_off <= k) mi++;
+            const LeafMat mt = mats.at(mi);
+            u32 kk = k - mt.word_off;
+            u64 v = mt.ptr[r * mt.width + (kk >> 1)];
             return (kk & 1) ? (u32)(v >> 32) : (u32)v;
         },
         total_words, dg);
@@ -402,9 +411,15 @@ void b3_hash_rows(Ctx& c, const std::vector<MatRef>& mats, uint8_t* digests) {
         words += 2 * m.width;
     }
     if (height == 0) return;
-    LeafMat* d_mats = (LeafMat*)c.alloc(std::max<size_t>(lm.size(), 1) * sizeof(LeafMat));
-    if (!lm.empty())
-        MSG_CUDA(cudaMemcpyAsync(d_mats, lm.data(), lm.size() * sizeof(LeafMat), cudaMemcpyHostToDevice, c.stream));
+    LeafList d_mats{};
+    LeafMat* d_ext = nullptr;
+    if (lm.size() <= (size_t)kInlineMats) {
+        for (size_t k = 0; k < lm.size(); k++) d_mats.inl[k] = lm[k];
+    } else {
+        d_ext = (LeafMat*)c.alloc(lm.size() * sizeof(LeafMat));
+        MSG_CUDA(cudaMemcpyAsync(d_ext, lm.data(), lm.size() * sizeof(LeafMat), cudaMemcpyHostToDevice, c.stream));
+        d_mats.ext = d_ext;
+    }
     u32 total_words = (u32)words;
     u32 pitch = total_words | 1u;
     size_t budget = 96 * 1024;
@@ -433,7 +448,7 @@ void b3_hash_rows(Ctx& c, const std::vector<MatRef>& mats, uint8_t* digests) {
     }
     MSG_CUDA(cudaGetLastError());
     // the host vector `lm` was copied with a pageable-memory async copy, which is staged before return
-    c.free(d_mats);
+    if (d_ext) c.free(d_ext);
 }
 
 void b3_compress_layer(Ctx& c, const uint8_t* prev, const uint8_t* inject, uint8_t* next, u64 next_len) {

@@ -15,23 +15,6 @@ struct OpenMat {
     u64 out_off;  // column offset inside one query's opened block
 };
 
-// device-resident descriptors for the query kernels: OpenMat[n_mats] then u64 layer_off[n_layers]
-static void build_open_desc(Ctx& c, msgpu_pdata* pd) {
-    u32 log_max = ilog2(pd->max_height);
-    std::vector<OpenMat> om;
-    u64 off = 0;
-    for (auto& m : pd->mats) {
-        om.push_back(OpenMat{m.ptr, (u32)m.width, log_max - ilog2(m.height), off});
-        off += m.width;
-    }
-    size_t sz_mats = om.size() * sizeof(OpenMat), sz_off = pd->layer_off.size() * 8;
-    std::vector<uint8_t> host(sz_mats + sz_off);
-    memcpy(host.data(), om.data(), sz_mats);
-    memcpy(host.data() + sz_mats, pd->layer_off.data(), sz_off);
-    pd->d_desc = c.alloc(host.size());
-    MSG_CUDA(cudaMemcpyAsync(pd->d_desc, host.data(), host.size(), cudaMemcpyHostToDevice, c.stream));  // pageable: staged before return
-}
-
 // Stable sort of the matrices by height (descending) and the leaf digests of every height class:
 // digest[i] = BLAKE3(row i of the class's matrices, concatenated in commit order). `first_out`, when given, receives the
 // tallest class (layer 0 of a tree); the other classes get their own buffers. Returns (height, digests), tallest first.
@@ -122,7 +105,6 @@ void mmcs_build(Ctx& c, msgpu_pdata* pd) {
         throw;
     }
     for (size_t k = 1; k < cls.size(); k++) c.free(cls[k].second);
-    build_open_desc(c, pd);
     MSG_CUDA(cudaMemcpyAsync(pd->root, pd->digests + pd->layer_off.back() * 32, 32, cudaMemcpyDeviceToHost, c.stream));
     c.sync();
 }
@@ -133,9 +115,7 @@ void mmcs_build_local(Ctx& c, msgpu_pdata* pd) {
     pd->class_leaves = hash_classes(c, pd, nullptr);
     pd->layer_off.clear();
     pd->layer_len.clear();
-    build_open_desc(c, pd);  // rows only: no digest layers
-    memset(pd->root, 0, 32);
-    c.sync();  // the descriptor's host staging buffer dies here
+    memset(pd->root, 0, 32);  // rows only: no digest layers
 }
 
 void mmcs_build_from_classes(Ctx& c, msgpu_pdata* pd, const std::vector<std::pair<u64, const uint8_t*>>& classes) {
@@ -145,7 +125,6 @@ void mmcs_build_from_classes(Ctx& c, msgpu_pdata* pd, const std::vector<std::pai
     pd->total_width = 0;
     MSG_CUDA(cudaMemcpyAsync(pd->digests, classes[0].second, classes[0].first * 32, cudaMemcpyDeviceToDevice, c.stream));
     build_nodes(c, pd, classes);
-    build_open_desc(c, pd);  // paths only: no matrices
     MSG_CUDA(cudaMemcpyAsync(pd->root, pd->digests + pd->layer_off.back() * 32, 32, cudaMemcpyDeviceToHost, c.stream));
     c.sync();
 }
@@ -181,17 +160,38 @@ __global__ void __launch_bounds__(128) k_open_multi(const MultiTree* trees, cons
 void mmcs_open_multi(Ctx& c, const msgpu_pdata* const* pds, const u32* shifts, u64 n_trees, const u64* indices_host, u64 n_idx,
                      u64* opened_host, uint8_t* proof_host) {
     if (n_idx == 0 || n_trees == 0) return;
+    // one host buffer, one upload: MultiTree[n_trees], the indices, then per tree its OpenMat[] and layer offsets (the
+    // descriptors are built here rather than with every tree: a FRI proof commits ~20 layers that are opened once)
     std::vector<MultiTree> mt(n_trees);
     u64 opened_total = 0, proof_total = 0;
+    size_t desc_bytes = 0;
     for (u64 k = 0; k < n_trees; k++) {
         const msgpu_pdata* pd = pds[k];
-        MSG_REQUIRE(pd && pd->d_desc, "open_multi: prover data without a tree");
-        u32 depth = pd->digests ? ilog2(pd->max_height) : 0;  // the local part of a sharded commitment has rows only
+        MSG_REQUIRE(pd && pd->max_height > 0, "open_multi: prover data without a tree");
         for (u64 i = 0; i < n_idx; i++)
             MSG_REQUIRE((indices_host[i] >> shifts[k]) < pd->max_height, "open_multi: index out of range");
+        desc_bytes += pd->mats.size() * sizeof(OpenMat) + pd->layer_off.size() * 8;
+    }
+    const size_t sz_t = n_trees * sizeof(MultiTree), sz_idx = n_idx * 8;
+    std::vector<uint8_t> host(sz_t + sz_idx + desc_bytes);
+    uint8_t* d_in = (uint8_t*)c.alloc(host.size());
+    size_t off = sz_t + sz_idx;
+    for (u64 k = 0; k < n_trees; k++) {
+        const msgpu_pdata* pd = pds[k];
+        u32 depth = pd->digests ? ilog2(pd->max_height) : 0;  // the local part of a sharded commitment has rows only
         MultiTree& t = mt[k];
-        t.mats = (const OpenMat*)pd->d_desc;
-        t.layer_off = (const u64*)((const uint8_t*)pd->d_desc + pd->mats.size() * sizeof(OpenMat));
+        t.mats = (const OpenMat*)(d_in + off);
+        const u32 log_max = ilog2(pd->max_height);
+        u64 col = 0;
+        for (auto& m : pd->mats) {
+            OpenMat om{m.ptr, (u32)m.width, log_max - ilog2(m.height), col};
+            memcpy(host.data() + off, &om, sizeof om);
+            off += sizeof om;
+            col += m.width;
+        }
+        t.layer_off = (const u64*)(d_in + off);
+        if (!pd->layer_off.empty()) memcpy(host.data() + off, pd->layer_off.data(), pd->layer_off.size() * 8);
+        off += pd->layer_off.size() * 8;
         t.digests = (const uint4*)pd->digests;
         t.nmats = (u32)pd->mats.size();
         t.shift = shifts[k];
@@ -202,11 +202,8 @@ void mmcs_open_multi(Ctx& c, const msgpu_pdata* const* pds, const u32* shifts, u
         opened_total += n_idx * pd->total_width;
         proof_total += n_idx * depth;
     }
-    size_t sz_t = n_trees * sizeof(MultiTree), sz_idx = n_idx * 8;
-    std::vector<uint8_t> host(sz_t + sz_idx);
     memcpy(host.data(), mt.data(), sz_t);
     memcpy(host.data() + sz_t, indices_host, sz_idx);
-    uint8_t* d_in = (uint8_t*)c.alloc(host.size());
     u64* d_open = (u64*)c.alloc(std::max<u64>(opened_total * 8, 8));
     uint4* d_proof = (uint4*)c.alloc(std::max<u64>(proof_total * 32, 32));
     MSG_CUDA(cudaMemcpyAsync(d_in, host.data(), host.size(), cudaMemcpyHostToDevice, c.stream));
@@ -233,7 +230,6 @@ void mmcs_open_batch(Ctx& c, const msgpu_pdata* pd, const u64* indices_host, u64
 void pdata_destroy(msgpu_pdata* pd) {
     if (!pd) return;
     Ctx& c = *pd->ctx;
-    if (pd->d_desc) c.free(pd->d_desc);
     for (auto& m : pd->mats)
         if (m.owned && m.ptr) c.free(m.ptr);
     if (pd->digests) c.free(pd->digests);

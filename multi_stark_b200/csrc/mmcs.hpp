@@ -17,7 +17,6 @@ struct msgpu_pdata {
     u64 max_height = 0;
     u64 total_width = 0;
     uint8_t root[32];
-    void* d_desc = nullptr;          // device copy of the opening descriptors (OpenMat[] then layer offsets), built with the tree
     // Sharded commitments (one proof over several GPUs): a LOCAL part holds this rank's matrices and, per LDE height
     // class, the leaf digests of its rows (no tree: digests == nullptr); the TREE part on the tree owner holds the digest
     // layers built from every rank's class digests (no matrices).
