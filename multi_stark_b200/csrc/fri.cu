@@ -139,6 +139,20 @@ __global__ void __launch_bounds__(256) k_bary_partial(BaryParams p) {
     }
 }
 
+// sums[e] = sum over the CTAs of partial[cta][e], e over (column, slot): the host then sees W * (npts + 1) extension values
+// per matrix instead of one set per CTA (at 2^16 rows the host-side sum over 592 CTAs cost more than the kernels)
+__global__ void __launch_bounds__(128) k_bary_sum(const u64* partial, u32 ctas, u32 n, u64* sums) {
+    const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    gl::e2 s = gl::e2_make(0, 0);
+    for (u32 b = 0; b < ctas; b++) {
+        const u64* o = partial + ((size_t)b * n + e) * 2;
+        s = gl::e2_add(s, gl::e2_make(o[0], o[1]));
+    }
+    sums[2 * (size_t)e] = s.a;
+    sums[2 * (size_t)e + 1] = s.b;
+}
+
 // ro[i] += sum_p aoff_p * (yred_p - Mred_i) * invden_p[i],  Mred_i = sum_c alpha^c M[i][c]
 struct ReduceParams {
     const u64* M;
@@ -303,11 +317,18 @@ static void evaluate_all(Ctx& c, msgpu_open* op) {
     struct Pending {
         msgpu_open::Mat* m;
         u64* d_partial;
-        std::vector<u64> h_partial;
+        size_t sums_off;  // u64 offset of this launch's (column, slot) sums inside the shared sums buffer
         u32 ctas, npts, c0, wc;
         size_t p0;
     };
     std::vector<Pending> pend;
+    size_t sums_total = 0;
+    for (auto& round : op->rounds)
+        for (auto& m : round)
+            for (size_t p0 = 0; p0 < m.points.size(); p0 += kMaxPts)
+                sums_total += m.width * (std::min<size_t>(kMaxPts, m.points.size() - p0) + 1) * 2;
+    DevBuf d_sums(c, std::max<size_t>(sums_total, 1) * 8);
+    size_t sums_off = 0;
     for (auto& round : op->rounds)
         for (auto& m : round) {
             m.values.assign(m.points.size(), std::vector<msh::Fp2>(m.width));
@@ -328,7 +349,8 @@ static void evaluate_all(Ctx& c, msgpu_open* op) {
                     bp.tile_rows = (u32)std::min<u64>(256, std::max<u64>(8, 4096 / bp.wc));
                     u64 want = (h + bp.tile_rows - 1) / bp.tile_rows;
                     u32 ctas = (u32)std::min<u64>(want, (u64)c.sm_count * 4);
-                    Pending pd{&m, nullptr, {}, ctas, npts, c0, bp.wc, p0};
+                    Pending pd{&m, nullptr, sums_off, ctas, npts, c0, bp.wc, p0};
+                    sums_off += (size_t)bp.wc * (npts + 1) * 2;
                     pd.d_partial = (u64*)c.alloc((size_t)ctas * bp.wc * (npts + 1) * 16);
                     bp.partial = pd.d_partial;
                     size_t smem = std::max((size_t)bp.rows_per_step * bp.wc * (npts + 1) * 16,
@@ -343,12 +365,18 @@ static void evaluate_all(Ctx& c, msgpu_open* op) {
                         }
                     }
                     MSG_CUDA(cudaGetLastError());
-                    pd.h_partial.resize((size_t)ctas * bp.wc * (npts + 1) * 2);
-                    MSG_CUDA(cudaMemcpyAsync(pd.h_partial.data(), pd.d_partial, pd.h_partial.size() * 8, cudaMemcpyDeviceToHost, c.stream));
+                    {
+                        const u32 n = bp.wc * (npts + 1);
+                        KLaunch kl(c, "k_bary_sum");
+                        k_bary_sum<<<(n + 127) / 128, 128, 0, c.stream>>>(pd.d_partial, ctas, n, d_sums.u() + pd.sums_off);
+                    }
+                    MSG_CUDA(cudaGetLastError());
                     pend.push_back(std::move(pd));
                 }
             }
         }
+    std::vector<u64> h_sums(std::max<size_t>(sums_total, 1));
+    if (sums_total) MSG_CUDA(cudaMemcpyAsync(h_sums.data(), d_sums.p, sums_total * 8, cudaMemcpyDeviceToHost, c.stream));  // ONE read-back
     c.sync();
     for (auto& pd : pend) {
         c.free(pd.d_partial);
@@ -358,18 +386,15 @@ static void evaluate_all(Ctx& c, msgpu_open* op) {
         msh::Fp shift_pow = msh::Fp(msh::GL_GENERATOR).exp_power_of_2(log_h);
         msh::Fp denom_inv = (shift_pow * msh::Fp((msh::u64)1 << log_h)).inverse();
         const u32 nslots = pd.npts + 1;
+        msh::Fp2 scale[kMaxPts];
+        for (u32 k = 0; k < pd.npts; k++) scale[k] = (m.points[pd.p0 + k].exp_power_of_2(log_h) - shift_pow) * denom_inv;
+        const u64* hs = h_sums.data() + pd.sums_off;
         for (u32 cc = 0; cc < pd.wc; cc++) {
-            msh::Fp s1;
-            for (u32 b = 0; b < pd.ctas; b++) s1 += msh::Fp(pd.h_partial[(((size_t)b * pd.wc + cc) * nslots) * 2]);
+            msh::Fp s1 = msh::Fp(hs[((size_t)cc * nslots) * 2]);
             for (u32 k = 0; k < pd.npts; k++) {
-                msh::Fp2 z = m.points[pd.p0 + k];
-                msh::Fp2 scale = (z.exp_power_of_2(log_h) - shift_pow) * denom_inv;
-                msh::Fp2 s2;
-                for (u32 b = 0; b < pd.ctas; b++) {
-                    size_t o = (((size_t)b * pd.wc + cc) * nslots + k + 1) * 2;
-                    s2 += msh::Fp2(msh::Fp(pd.h_partial[o]), msh::Fp(pd.h_partial[o + 1]));
-                }
-                m.values[pd.p0 + k][pd.c0 + cc] = (z * s2 - s1) * scale;
+                size_t o = ((size_t)cc * nslots + k + 1) * 2;
+                msh::Fp2 s2 = msh::Fp2(msh::Fp((msh::u64)hs[o]), msh::Fp((msh::u64)hs[o + 1]));
+                m.values[pd.p0 + k][pd.c0 + cc] = (m.points[pd.p0 + k] * s2 - s1) * scale[k];
             }
         }
     }
