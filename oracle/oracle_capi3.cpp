@@ -78,6 +78,26 @@ int orc_verify(void* s, const u64* claims, const u64* offsets, u64 n_claims, con
     }
 }
 
+// The two transcript scripts of the reference's `gen_challenger_refs` (src/types.rs:284-319): a challenger over an EMPTY seed.
+// out8 = SAMPLE_BITS, APCS (c0, c1), AFRI (c0, c1), BETA (c0, c1), SAMPLE_BITS2
+void orc_gen_challenger_refs(u64* out8) {
+    Challenger a{std::vector<u8>()};
+    a.observe(Fp(0x0102030405060708ull));
+    out8[0] = a.sample_bits(20);
+    Challenger ch{std::vector<u8>()};
+    ch.observe(Fp(0x0102030405060708ull));
+    ch.observe(Fp(0x1122334455667788ull));
+    Fp2 apcs = ch.sample_ext(), afri = ch.sample_ext();
+    out8[1] = apcs.c[0].v; out8[2] = apcs.c[1].v;
+    out8[3] = afri.c[0].v; out8[4] = afri.c[1].v;
+    ch.observe(Fp(0x00000000deadbeefull));
+    Fp2 beta = ch.sample_ext();
+    out8[5] = beta.c[0].v; out8[6] = beta.c[1].v;
+    ch.observe(Fp(0x0a0b0c0d01020304ull));
+    ch.observe(Fp(0x0000000000000002ull));
+    out8[7] = ch.sample_bits(20);
+}
+
 }  // extern "C"
 
 // ---- examples/pcs_example.rs:28-122 on the CPU: commit -> observe -> sample zeta -> open at [zeta; num_open] -> bytes,
