@@ -5,6 +5,7 @@
 // pinned by the tests against the CPU restatement and a restated verifier.
 #include "capi_common.hpp"
 #include "mmcs.hpp"
+#include "blake3.cuh"
 #include <algorithm>
 #include <cstring>
 #include <memory>
@@ -236,6 +237,64 @@ __global__ void __launch_bounds__(256) k_fri_fold(const u64* in, u64* out, u64 h
     out[2 * i + 1] = r.b;
 }
 
+// Small commit-phase rounds in ONE launch of one CTA: fold the committed vector (as k_fri_fold), hash the rows of the folded
+// vector (2 extension elements = 32 bytes = one BLAKE3 block) and build every node layer through shared memory. Replaces
+// k_fri_fold + k_hash_rows_staged + k_merkle_subtree of the NEXT round for vectors of at most kFusedFoldMax elements: the
+// tail of the commit phase is latency, not work (a dozen rounds of ~8 us kernels each waiting for a root read-back).
+constexpr u32 kFusedFoldMax = 4096;  // folded length; rows = 2048 -> 64 KB + 32 KB of shared memory
+struct FoldCommitParams {
+    const u64* in;
+    u64* out;
+    const u64* roll;
+    uint4* digests;          // all layers back to back
+    u64 layer_off[13];
+    gl::e2 half_beta, beta_sq;
+    gl::PowTable ginv_tab;
+    u32 half_len, log_half, n_layers;
+};
+__device__ __forceinline__ gl::e2 fold_one(const FoldCommitParams& p, u32 i) {
+    gl::e2 lo = gl::e2_make(p.in[4 * i], p.in[4 * i + 1]), hi = gl::e2_make(p.in[4 * i + 2], p.in[4 * i + 3]);
+    gl::e2 s = gl::e2_add(lo, hi), d = gl::e2_sub(lo, hi);
+    s = gl::e2_make(gl::halve(s.a), gl::halve(s.b));
+    u64 gp = gl::pow_lookup(p.ginv_tab, gl::rev_bits(i, p.log_half));
+    gl::e2 r = gl::e2_add(s, gl::e2_mul_base(gl::e2_mul(p.half_beta, d), gp));
+    if (p.roll) r = gl::e2_add(r, gl::e2_mul(p.beta_sq, gl::e2_make(p.roll[2 * i], p.roll[2 * i + 1])));
+    return r;
+}
+__global__ void __launch_bounds__(256) k_fri_fold_commit(const __grid_constant__ FoldCommitParams p) {
+    extern __shared__ uint4 sm_f[];
+    const u32 rows = p.half_len >> 1;
+    uint4* bufA = sm_f;             // rows digests
+    uint4* bufB = sm_f + 2 * rows;  // rows / 2 digests
+    for (u32 j = threadIdx.x; j < rows; j += blockDim.x) {
+        gl::e2 a = fold_one(p, 2 * j), b = fold_one(p, 2 * j + 1);
+        p.out[4 * j] = a.a; p.out[4 * j + 1] = a.b; p.out[4 * j + 2] = b.a; p.out[4 * j + 3] = b.b;
+        u32 m[16] = {(u32)a.a, (u32)(a.a >> 32), (u32)a.b, (u32)(a.b >> 32), (u32)b.a, (u32)(b.a >> 32), (u32)b.b, (u32)(b.b >> 32),
+                     0, 0, 0, 0, 0, 0, 0, 0};
+        u32 cv[8];
+        b3::set_iv(cv);
+        b3::compress<false>(cv, m, 0, 0, 32, b3::CHUNK_START | b3::CHUNK_END | b3::ROOT);
+        uint4 d0 = make_uint4(cv[0], cv[1], cv[2], cv[3]), d1 = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+        bufA[2 * j] = d0; bufA[2 * j + 1] = d1;
+        p.digests[2 * (p.layer_off[0] + j)] = d0; p.digests[2 * (p.layer_off[0] + j) + 1] = d1;
+    }
+    __syncthreads();
+    for (u32 l = 1; l < p.n_layers; l++) {
+        const u32 nodes = rows >> l;
+        const uint4* src = (l & 1) ? bufA : bufB;
+        uint4* dst = (l & 1) ? bufB : bufA;
+        for (u32 i = threadIdx.x; i < nodes; i += blockDim.x) {
+            uint4 a0 = src[4 * i], a1 = src[4 * i + 1], b0 = src[4 * i + 2], b1 = src[4 * i + 3];
+            u32 x[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, y[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w}, d[8];
+            b3::hash_pair(x, y, d);
+            uint4 d0 = make_uint4(d[0], d[1], d[2], d[3]), d1 = make_uint4(d[4], d[5], d[6], d[7]);
+            dst[2 * i] = d0; dst[2 * i + 1] = d1;
+            p.digests[2 * (p.layer_off[l] + i)] = d0; p.digests[2 * (p.layer_off[l] + i) + 1] = d1;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace msg
 
 struct msgpu_open {
@@ -267,6 +326,7 @@ struct msgpu_open {
     u64 cur_len = 0;
     bool cur_committed = false;
     std::vector<msgpu_pdata*> layers;
+    msgpu_pdata* pending = nullptr;  // layer over `cur` built ahead by the fused fold (owns cur); adopted by the next commit_round
 };
 
 namespace msg {
@@ -286,7 +346,8 @@ static void open_destroy(msgpu_open* op) {
     Ctx& c = *op->ctx;
     for (auto& d : op->invdens) c.free(d.ptr);
     for (size_t k = op->next_input; k < op->inputs.size(); k++) c.free(op->inputs[k].ptr);
-    if (op->cur && !op->cur_committed) c.free(op->cur);
+    if (op->pending) pdata_destroy(op->pending);  // owns cur
+    else if (op->cur && !op->cur_committed) c.free(op->cur);
     for (auto* pd : op->layers) pdata_destroy(pd);
     delete op;
 }
@@ -578,6 +639,15 @@ int msgpu_fri_commit_round(msgpu_open* op, uint8_t* root32) {
         StageScope ss(c, "fri");
         MSG_REQUIRE(op->cur && !op->cur_committed, "fri_commit_round: nothing to commit");
         MSG_REQUIRE(op->cur_len >= 2, "fri_commit_round: vector too short to fold");
+        if (op->pending) {  // the fused fold has already hashed this vector: wait for its root
+            msgpu_pdata* pd = op->pending;
+            op->pending = nullptr;
+            op->cur_committed = true;
+            op->layers.push_back(pd);
+            c.sync();
+            memcpy(root32, pd->root, 32);
+            return;
+        }
         msgpu_pdata* pd = new msgpu_pdata();
         pd->ctx = &c;
         // rows of 2 extension elements = 4 base columns (ExtensionMmcs flattening)
@@ -602,7 +672,45 @@ int msgpu_fri_fold(msgpu_open* op, const uint64_t* beta2) {
         if (op->next_input < op->inputs.size() && op->inputs[op->next_input].len == half) roll = op->inputs[op->next_input].ptr;
         u64* out = (u64*)c.alloc(half * 16);
         gl::PowTable tab = c.pow_table(msh::two_adic_generator(log_half + 1).inverse().v, 1, log_half + 1).view();
-        {
+        if (half >= 2 && half <= kFusedFoldMax) {
+            // fold + Merkle commitment of the folded vector (rows of 2 extension elements) in one launch
+            msgpu_pdata* pd = new msgpu_pdata();
+            pd->ctx = &c;
+            const u64 rows = half / 2;
+            try {
+                mmcs_layout_layers(c, pd, rows);
+            } catch (...) {
+                delete pd;
+                c.free(out);
+                throw;
+            }
+            pd->mats.push_back(msgpu_pdata::Mat{out, rows, 4, true});
+            pd->total_width = 4;
+            FoldCommitParams fp{};
+            fp.in = op->cur;
+            fp.out = out;
+            fp.roll = roll;
+            fp.digests = (uint4*)pd->digests;
+            fp.n_layers = (u32)pd->layer_off.size();
+            for (size_t l = 0; l < pd->layer_off.size(); l++) fp.layer_off[l] = pd->layer_off[l];
+            fp.half_beta = gl::e2{hb.c[0].v, hb.c[1].v};
+            fp.beta_sq = gl::e2{bsq.c[0].v, bsq.c[1].v};
+            fp.ginv_tab = tab;
+            fp.half_len = (u32)half;
+            fp.log_half = log_half;
+            static bool attr = false;
+            if (!attr) {
+                MSG_CUDA(cudaFuncSetAttribute(k_fri_fold_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFusedFoldMax / 2 * 48)));
+                attr = true;
+            }
+            {
+                KLaunch kl(c, "k_fri_fold_commit");
+                k_fri_fold_commit<<<1, 256, (size_t)rows * 48, c.stream>>>(fp);
+            }
+            MSG_CUDA(cudaGetLastError());
+            MSG_CUDA(cudaMemcpyAsync(pd->root, pd->digests + pd->layer_off.back() * 32, 32, cudaMemcpyDeviceToHost, c.stream));
+            op->pending = pd;
+        } else {
             KLaunch kl(c, "k_fri_fold");
             k_fri_fold<<<(unsigned)((half + 255) / 256), 256, 0, c.stream>>>(op->cur, out, half, log_half, gl::e2{hb.c[0].v, hb.c[1].v},
                                                                              tab, roll, gl::e2{bsq.c[0].v, bsq.c[1].v});

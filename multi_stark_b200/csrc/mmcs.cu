@@ -51,7 +51,7 @@ static std::vector<std::pair<u64, uint8_t*>> hash_classes(Ctx& c, msgpu_pdata* p
     return classes;
 }
 
-static void layout_layers(Ctx& c, msgpu_pdata* pd, u64 max_h) {
+void mmcs_layout_layers(Ctx& c, msgpu_pdata* pd, u64 max_h) {
     pd->max_height = max_h;
     pd->digests = (uint8_t*)c.alloc((2 * max_h - 1) * 32);
     pd->layer_off.clear();
@@ -95,7 +95,7 @@ void mmcs_build(Ctx& c, msgpu_pdata* pd) {
     u64 max_h = 0;
     for (auto& m : pd->mats) max_h = std::max(max_h, m.height);
     MSG_REQUIRE(is_pow2(max_h), "commit: matrix heights must be powers of two");
-    layout_layers(c, pd, max_h);
+    mmcs_layout_layers(c, pd, max_h);
     std::vector<std::pair<u64, uint8_t*>> cls = hash_classes(c, pd, pd->digests);
     std::vector<std::pair<u64, const uint8_t*>> view(cls.begin(), cls.end());
     try {
@@ -121,7 +121,7 @@ void mmcs_build_local(Ctx& c, msgpu_pdata* pd) {
 void mmcs_build_from_classes(Ctx& c, msgpu_pdata* pd, const std::vector<std::pair<u64, const uint8_t*>>& classes) {
     StageScope stage_scope(c, "merkle");
     MSG_REQUIRE(!classes.empty() && is_pow2(classes[0].first), "tree: no leaf digests given");
-    layout_layers(c, pd, classes[0].first);
+    mmcs_layout_layers(c, pd, classes[0].first);
     pd->total_width = 0;
     MSG_CUDA(cudaMemcpyAsync(pd->digests, classes[0].second, classes[0].first * 32, cudaMemcpyDeviceToDevice, c.stream));
     build_nodes(c, pd, classes);

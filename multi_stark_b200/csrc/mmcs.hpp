@@ -35,5 +35,7 @@ void mmcs_open_multi(Ctx& c, const msgpu_pdata* const* pds, const u32* shifts, u
 void mmcs_build_local(Ctx& c, msgpu_pdata* pd);
 // Tree part: node layers (with injection) over per-class leaf digests given tallest first; heights strictly decreasing.
 void mmcs_build_from_classes(Ctx& c, msgpu_pdata* pd, const std::vector<std::pair<u64, const uint8_t*>>& classes);
+// allocates pd->digests for a tree over max_h leaves and fills layer_off / layer_len (layer 0 = leaf digests)
+void mmcs_layout_layers(Ctx& c, msgpu_pdata* pd, u64 max_h);
 void pdata_destroy(msgpu_pdata* pd);
 }  // namespace msg
