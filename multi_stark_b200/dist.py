@@ -394,36 +394,41 @@ class WideCommit:
 
     def open_batch(self, indices):
         """Mmcs::open_batch: (rows [n, width], sibling paths [n, log2(H), 32]) -- the same on every rank. The row and the
-        lower part of the path come from the rank that holds the row, the top log2(N) siblings from the top tree."""
+        lower log2(H / N) siblings come from the rank that holds the row, the top log2(N) siblings from the top tree
+        (which every rank holds)."""
         import numpy as np
         n, world = len(indices), self.comm.world
         shard = self.lde_height // world
-        lo_depth, width = shard.bit_length() - 1, sum(self.widths)
+        lo_depth, top_depth, width = shard.bit_length() - 1, world.bit_length() - 1, sum(self.widths)
+        owner = [int(i) // shard for i in indices]
         rows = np.zeros((n, width), dtype=np.uint64)
-        paths = np.zeros((n, lo_depth + (world.bit_length() - 1), 32), dtype=np.uint8)
-        mine = [k for k, i in enumerate(indices) if int(i) // shard == self.comm.rank]
+        low = np.zeros((n, lo_depth, 32), dtype=np.uint8)
+        mine = [k for k in range(n) if owner[k] == self.comm.rank]
         if mine:
             o, p = self.local.open_batch([int(indices[k]) % shard for k in mine])
             rows[mine] = o
-            paths[mine, :lo_depth] = p
-        if world > 1:
-            # the top tree has no matrices: sibling paths only
-            tidx = np.array([int(i) // shard for i in indices], dtype=np.uint64)
-            tp = np.zeros((n, world.bit_length() - 1, 32), dtype=np.uint8)
-            dummy = np.zeros(1, dtype=np.uint64)
-            check(self.ctx.L.msgpu_open_batch(self.ctx.h, self.top.h, tidx.ctypes.data_as(_C.c_void_p), n,
-                                              dummy.ctypes.data_as(_C.c_void_p), tp.ctypes.data_as(_C.c_void_p)))
-            # every rank holds the same top tree; rows / lower paths are summed over the ranks (all others contribute zeros)
-            blob = np.concatenate([rows.view(np.uint8).ravel(), paths[:, :lo_depth].ravel()])
-            allb = np.zeros(blob.size * world, dtype=np.uint8)
-            if self.comm.struct.allgather_host(None, blob.ctypes.data, allb.ctypes.data, blob.size) != 0:
-                raise RuntimeError("allgather failed: %s" % self.comm.errors)
-            allb = allb.reshape(world, -1)
-            for k, i in enumerate(indices):
-                src = allb[int(i) // shard]
-                rows[k] = src[:rows.nbytes].view(np.uint64).reshape(n, width)[k]
-                paths[k, :lo_depth] = src[rows.nbytes:].reshape(n, lo_depth, 32)[k]
-            paths[:, lo_depth:] = tp
+            low[mine] = p
+        if world == 1:
+            return rows, low
+        # every rank contributes the openings of the rows it holds (zeros elsewhere); pick each index from its owner
+        blob = np.concatenate([rows.view(np.uint8).ravel(), low.ravel()])
+        gathered = np.zeros(blob.size * world, dtype=np.uint8)
+        if self.comm.struct.allgather_host(None, blob.ctypes.data, gathered.ctypes.data, blob.size) != 0:
+            raise RuntimeError("allgather failed: %s" % self.comm.errors)
+        gathered = gathered.reshape(world, -1)
+        all_rows = gathered[:, :rows.nbytes].copy().view(np.uint64).reshape(world, n, width)
+        all_low = gathered[:, rows.nbytes:].reshape(world, n, lo_depth, 32)
+        paths = np.zeros((n, lo_depth + top_depth, 32), dtype=np.uint8)
+        for k in range(n):
+            rows[k] = all_rows[owner[k], k]
+            paths[k, :lo_depth] = all_low[owner[k], k]
+        # the top tree has no matrices: sibling paths only
+        tidx = np.array(owner, dtype=np.uint64)
+        tp = np.zeros((n, top_depth, 32), dtype=np.uint8)
+        dummy = np.zeros(1, dtype=np.uint64)
+        check(self.ctx.L.msgpu_open_batch(self.ctx.h, self.top.h, tidx.ctypes.data_as(_C.c_void_p), n,
+                                          dummy.ctypes.data_as(_C.c_void_p), tp.ctypes.data_as(_C.c_void_p)))
+        paths[:, lo_depth:] = tp
         return rows, paths
 
     def free(self):
