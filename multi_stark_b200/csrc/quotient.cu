@@ -161,8 +161,35 @@ struct RowCtx {
     u64 first, last, trans;
 };
 
+// Working values of the interpreter (one per live node after liveness analysis). A per-thread array indexed by the bytecode
+// lives in LOCAL memory: 256 B per thread that L1 cannot hold for a full SM, so every row's slots were written back to DRAM
+// (ncu at 2^22 rows: 2.25 GB of DRAM writes for a kernel whose output is 67 MB). k_lookup_messages keeps up to 128 slots in
+// shared memory instead, slot-major ([slot][thread]: conflict-free), 32 KB per 128-thread CTA at 32 slots (2.17 -> 1.68 ms);
+// for k_quotient_eval the same change was a loss, its DRAM is far from saturated and the L1-resident local array is faster.
+constexpr int kInterpThreads = 128;
+constexpr int kSmemSlotsMax = 128;
+template <int NSLOT, bool SMEM>
+struct Slots;
 template <int NSLOT>
-__device__ __forceinline__ void run_program(const Instr* __restrict__ prog, u32 n, u64* slots, const RowCtx& cx) {
+struct Slots<NSLOT, false> {
+    u64 v[NSLOT];
+    __device__ __forceinline__ Slots() {}
+    __device__ __forceinline__ u64& operator[](u32 k) { return v[k]; }
+};
+template <int NSLOT>
+struct Slots<NSLOT, true> {
+    u64* base;
+    __device__ __forceinline__ Slots() {
+        extern __shared__ u64 sm_slots[];
+        base = sm_slots + threadIdx.x;
+    }
+    __device__ __forceinline__ u64& operator[](u32 k) { return base[(size_t)k * kInterpThreads]; }
+};
+template <int NSLOT>
+constexpr size_t slots_smem_bytes() { return NSLOT <= kSmemSlotsMax ? (size_t)NSLOT * kInterpThreads * 8 : 0; }
+
+template <int NSLOT, class S>
+__device__ __forceinline__ void run_program(const Instr* __restrict__ prog, u32 n, S& slots, const RowCtx& cx) {
     for (u32 pc = 0; pc < n; pc++) {
         const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(prog + pc));
         const u64 imm = __ldg(reinterpret_cast<const u64*>(prog + pc) + 2);
@@ -267,7 +294,7 @@ __global__ void __launch_bounds__(128) k_quotient_eval(QuotParams p) {
     cx.first = p.sel_first[s];
     cx.last = p.sel_last[s];
     cx.trans = gl::sub(gl::pow_lookup(p.xtab, i), p.g_inv);
-    u64 slots[NSLOT];
+    Slots<NSLOT, false> slots;  // measured: shared-memory slots make THIS kernel slower (1.83 -> 2.58 ms at 2^22 rows), local ones stay
     run_program<NSLOT>(p.prog, p.n_instr, slots, cx);
 
     // alpha-fold with lazy 160-bit accumulation: one reduction per coordinate at the end
@@ -351,7 +378,7 @@ __global__ void __launch_bounds__(128) k_lookup_messages(MsgParams p) {
     cx.first = r == 0;
     cx.last = r + 1 == p.rows;
     cx.trans = r + 1 != p.rows;
-    u64 slots[NSLOT];
+    Slots<NSLOT, (NSLOT <= kSmemSlotsMax)> slots;
     run_program<NSLOT>(p.prog, p.n_instr, slots, cx);
     const gl::e2 beta = gl::e2_make(p.beta[0], p.beta[1]), gamma = gl::e2_make(p.gamma[0], p.gamma[1]);
     for (u32 j = 0; j < p.n_lookups; j++) {
@@ -745,7 +772,10 @@ int msgpu_stage2_trace(msgpu_ctx* h, const msgpu_program* prog, const uint64_t* 
         mp.wmain = prog->main_width;
         launch_by_slots(prog->slots_prefix, [&](auto ns) {
             KLaunch kl(c, "k_lookup_messages");
-            k_lookup_messages<decltype(ns)::value><<<(unsigned)((rows + 127) / 128), 128, 0, c.stream>>>(mp);
+            constexpr int NS = decltype(ns)::value;
+            constexpr size_t smem = slots_smem_bytes<NS>();
+            if (smem > 48 * 1024) MSG_CUDA(cudaFuncSetAttribute(k_lookup_messages<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_lookup_messages<NS><<<(unsigned)((rows + 127) / 128), kInterpThreads, smem, c.stream>>>(mp);
         });
         MSG_CUDA(cudaGetLastError());
         {
@@ -941,7 +971,7 @@ int msgpu_quotient(msgpu_ctx* h, const msgpu_program* prog, const msgpu_pdata* p
         qp.log_q = log_q;
         launch_by_slots(prog->slots_full, [&](auto ns) {
             KLaunch kl(c, "k_quotient_eval");
-            k_quotient_eval<decltype(ns)::value><<<(unsigned)((nq + 127) / 128), 128, 0, c.stream>>>(qp);
+            k_quotient_eval<decltype(ns)::value><<<(unsigned)((nq + 127) / 128), kInterpThreads, 0, c.stream>>>(qp);
         });
         MSG_CUDA(cudaGetLastError());
         if (quotient_values_out) MSG_CUDA(cudaMemcpyAsync(quotient_values_out, qv.p, nq * 16, cudaMemcpyDeviceToHost, c.stream));
