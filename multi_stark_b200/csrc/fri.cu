@@ -38,22 +38,30 @@ __global__ void __launch_bounds__(256) k_inv_denoms(u64* invden, u32 log_h, gl::
     const u64 H = 1ull << log_h;
     u64 i0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * kInvPerThread;
     if (i0 >= H) return;
-    gl::e2 v[kInvPerThread], pref[kInvPerThread];
-    int cnt = 0;
-    for (int k = 0; k < kInvPerThread; k++) {
-        if (i0 + k >= H) break;
-        u64 x = gl::pow_lookup(xtab, gl::rev_bits((u32)(i0 + k), log_h));
-        v[k] = gl::e2_make(gl::sub(z.a, x), z.b);
-        cnt = k + 1;
-    }
+    // fully unrolled with constant indices: the batch lives in registers (a dynamically indexed array is local memory)
+    const int cnt = (int)min((u64)kInvPerThread, H - i0);
+    u64 va[kInvPerThread];
+    gl::e2 pref[kInvPerThread];
     gl::e2 acc = gl::e2_make(1, 0);
-    for (int k = 0; k < cnt; k++) { pref[k] = acc; acc = gl::e2_mul(acc, v[k]); }
+#pragma unroll
+    for (int k = 0; k < kInvPerThread; k++) {
+        pref[k] = acc;
+        va[k] = 0;
+        if (k < cnt) {
+            u64 x = gl::pow_lookup(xtab, gl::rev_bits((u32)(i0 + k), log_h));
+            va[k] = gl::sub(z.a, x);
+            acc = gl::e2_mul(acc, gl::e2_make(va[k], z.b));
+        }
+    }
     gl::e2 inv = e2_inverse_d(acc);
-    for (int k = cnt; k-- > 0;) {
-        gl::e2 r = gl::e2_mul(inv, pref[k]);
-        inv = gl::e2_mul(inv, v[k]);
-        invden[2 * (i0 + k)] = r.a;
-        invden[2 * (i0 + k) + 1] = r.b;
+#pragma unroll
+    for (int k = kInvPerThread - 1; k >= 0; k--) {
+        if (k < cnt) {
+            gl::e2 r = gl::e2_mul(inv, pref[k]);
+            inv = gl::e2_mul(inv, gl::e2_make(va[k], z.b));
+            invden[2 * (i0 + k)] = r.a;
+            invden[2 * (i0 + k) + 1] = r.b;
+        }
     }
 }
 

@@ -418,22 +418,29 @@ __device__ __forceinline__ gl::e2 block_sum(gl::e2 v, gl::e2* sm) {
 __global__ void __launch_bounds__(kScanThreads) k_terms_and_block_sums(u64* msgs, const u64* mults, u64 total, u64* block_sums) {
     __shared__ gl::e2 sm[kScanThreads / 32];
     u64 i0 = ((u64)blockIdx.x * kScanThreads + threadIdx.x) * kScanPerThread;
-    gl::e2 v[kScanPerThread], pref[kScanPerThread];
-    int cnt = 0;
-    for (int k = 0; k < kScanPerThread; k++)
-        if (i0 + k < total) { v[k] = gl::e2_make(msgs[2 * (i0 + k)], msgs[2 * (i0 + k) + 1]); cnt = k + 1; }
+    // prefix products in registers (fully unrolled, constant indices: a dynamically indexed array would live in local memory,
+    // 256 B per thread that ends up in DRAM); the messages themselves are read a second time on the way back (L1 / L2 hits)
+    gl::e2 pref[kScanPerThread];
+    const int cnt = (int)min((u64)kScanPerThread, total > i0 ? total - i0 : 0);
     gl::e2 acc = gl::e2_make(1, 0);
-    for (int k = 0; k < cnt; k++) { pref[k] = acc; acc = gl::e2_mul(acc, v[k]); }
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; k++) {
+        pref[k] = acc;
+        if (k < cnt) acc = gl::e2_mul(acc, gl::e2_make(msgs[2 * (i0 + k)], msgs[2 * (i0 + k) + 1]));
+    }
     gl::e2 inv = cnt ? e2_inverse(acc) : acc;
     gl::e2 sum = gl::e2_make(0, 0);
-    for (int k = cnt; k-- > 0;) {
-        gl::e2 x = v[k];
-        gl::e2 xi = gl::e2_mul(inv, pref[k]);
-        inv = gl::e2_mul(inv, x);
-        gl::e2 term = gl::e2_mul_base(xi, mults[i0 + k]);
-        msgs[2 * (i0 + k)] = term.a;
-        msgs[2 * (i0 + k) + 1] = term.b;
-        sum = gl::e2_add(sum, term);
+#pragma unroll
+    for (int k = kScanPerThread - 1; k >= 0; k--) {
+        if (k < cnt) {
+            gl::e2 x = gl::e2_make(msgs[2 * (i0 + k)], msgs[2 * (i0 + k) + 1]);
+            gl::e2 xi = gl::e2_mul(inv, pref[k]);
+            inv = gl::e2_mul(inv, x);
+            gl::e2 term = gl::e2_mul_base(xi, mults[i0 + k]);
+            msgs[2 * (i0 + k)] = term.a;
+            msgs[2 * (i0 + k) + 1] = term.b;
+            sum = gl::e2_add(sum, term);
+        }
     }
     gl::e2 bs = block_sum(sum, sm);
     if (threadIdx.x == 0) { block_sums[2 * blockIdx.x] = bs.a; block_sums[2 * blockIdx.x + 1] = bs.b; }
@@ -505,26 +512,33 @@ __global__ void __launch_bounds__(kScanThreads) k_claims(const u64* claims, u64 
                                                          u64* partial) {
     __shared__ gl::e2 sm[kScanThreads / 32];
     u64 i0 = ((u64)blockIdx.x * kScanThreads + threadIdx.x) * kScanPerThread;
+    // fully unrolled, constant indices: the batch of 8 stays in registers
+    const int cnt = (int)min((u64)kScanPerThread, n_claims > i0 ? n_claims - i0 : 0);
     gl::e2 v[kScanPerThread], pref[kScanPerThread];
-    int cnt = 0;
-    for (int k = 0; k < kScanPerThread; k++) {
-        if (i0 + k >= n_claims) break;
-        const u64* c = claims + (i0 + k) * len;
-        gl::e2 f = gl::e2_make(0, 0);
-        for (u32 a = len; a-- > 0;) {
-            f = gl::e2_mul(f, gamma);
-            f.a = gl::add(f.a, c[a]);
-        }
-        v[k] = gl::e2_add(f, beta);
-        cnt = k + 1;
-    }
     gl::e2 acc = gl::e2_make(1, 0);
-    for (int k = 0; k < cnt; k++) { pref[k] = acc; acc = gl::e2_mul(acc, v[k]); }
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; k++) {
+        pref[k] = acc;
+        v[k] = acc;
+        if (k < cnt) {
+            const u64* c = claims + (i0 + k) * len;
+            gl::e2 f = gl::e2_make(0, 0);
+            for (u32 a = len; a-- > 0;) {
+                f = gl::e2_mul(f, gamma);
+                f.a = gl::add(f.a, c[a]);
+            }
+            v[k] = gl::e2_add(f, beta);
+            acc = gl::e2_mul(acc, v[k]);
+        }
+    }
     gl::e2 inv = cnt ? e2_inverse(acc) : acc;
     gl::e2 sum = gl::e2_make(0, 0);
-    for (int k = cnt; k-- > 0;) {
-        sum = gl::e2_add(sum, gl::e2_mul(inv, pref[k]));
-        inv = gl::e2_mul(inv, v[k]);
+#pragma unroll
+    for (int k = kScanPerThread - 1; k >= 0; k--) {
+        if (k < cnt) {
+            sum = gl::e2_add(sum, gl::e2_mul(inv, pref[k]));
+            inv = gl::e2_mul(inv, v[k]);
+        }
     }
     gl::e2 bs = block_sum(sum, sm);
     if (threadIdx.x == 0) { partial[2 * blockIdx.x] = bs.a; partial[2 * blockIdx.x + 1] = bs.b; }
