@@ -94,6 +94,18 @@ int msgpu_lde_from_shifted_coefficients_dev(msgpu_ctx* ctx, const uint64_t* in, 
  * (cap_height 0). */
 int msgpu_commit(msgpu_ctx* ctx, const uint64_t* const* mats, const uint64_t* heights, const uint64_t* widths,
                  uint64_t n_mats, uint32_t log_blowup, msgpu_pdata** out, uint8_t* root32);
+/* The same in two steps with the uploads on the context's COPY stream, so that matrix i is extended while matrices
+ * i + 1 ... are still crossing PCIe (and anything enqueued on the copy stream in between, e.g. msgpu_claims_prefetch, travels
+ * under the kernels). upload_begin returns at once; the host matrices (pinned memory for a real overlap) must stay valid until
+ * commit_upload returns. commit_upload consumes the handle; verify_canonical = 1 checks every value < p on the device;
+ * kept_inputs (optional, n_mats pointers out) receives the natural-order device copies, owned by the caller (msgpu_free);
+ * local_only = 1 builds the local part of a sharded commitment (as msgpu_commit_local_dev: no tree, root32 may be NULL). */
+typedef struct msgpu_upload msgpu_upload;
+int msgpu_upload_begin(msgpu_ctx* ctx, const uint64_t* const* mats, const uint64_t* heights, const uint64_t* widths,
+                       uint64_t n_mats, msgpu_upload** out);
+int msgpu_commit_upload(msgpu_upload* up, uint32_t log_blowup, int verify_canonical, uint64_t** kept_inputs, int local_only,
+                        msgpu_pdata** out, uint8_t* root32);
+void msgpu_upload_free(msgpu_upload* up);
 /* same with DEVICE input pointers (inputs are not modified) */
 int msgpu_commit_dev(msgpu_ctx* ctx, const uint64_t* const* mats, const uint64_t* heights, const uint64_t* widths,
                      uint64_t n_mats, uint32_t log_blowup, msgpu_pdata** out, uint8_t* root32);

@@ -42,6 +42,9 @@ SIGNATURES = {
     "msgpu_lde_from_shifted_coefficients_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32,
                                                           C.c_void_p]),
     "msgpu_commit": (C.c_int, [C.c_void_p, c_vpp, c_u64p, c_u64p, C.c_uint64, C.c_uint32, c_vpp, C.c_void_p]),
+    "msgpu_upload_begin": (C.c_int, [C.c_void_p, c_vpp, c_u64p, c_u64p, C.c_uint64, c_vpp]),
+    "msgpu_commit_upload": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, c_vpp, C.c_int, c_vpp, C.c_void_p]),
+    "msgpu_upload_free": (None, [C.c_void_p]),
     "msgpu_commit_dev": (C.c_int, [C.c_void_p, c_vpp, c_u64p, c_u64p, C.c_uint64, C.c_uint32, c_vpp, C.c_void_p]),
     "msgpu_commit_ldes_dev": (C.c_int, [C.c_void_p, c_vpp, c_u64p, c_u64p, C.c_uint64, C.c_int, c_vpp, C.c_void_p]),
     "msgpu_commit_local_dev": (C.c_int, [C.c_void_p, c_vpp, c_u64p, c_u64p, C.c_uint64, C.c_uint32, C.c_int, c_vpp]),

@@ -406,6 +406,108 @@ int msgpu_commit(msgpu_ctx* h, const uint64_t* const* mats, const uint64_t* heig
         *out = pd;
     });
 }
+// ---- pipelined host commit: uploads on the copy stream, LDEs on the main stream --------------------------------------------
+struct msgpu_upload {
+    Ctx* ctx;
+    struct Item {
+        u64* dev;
+        u64 height, width;
+        cudaEvent_t ready;
+    };
+    std::vector<Item> items;
+};
+static void upload_destroy(msgpu_upload* up, bool free_buffers) {
+    if (!up) return;
+    for (auto& it : up->items) {
+        if (it.ready) {
+            cudaEventSynchronize(it.ready);  // a copy must not outlive its block
+            cudaEventDestroy(it.ready);
+        }
+        if (free_buffers && it.dev) up->ctx->free(it.dev);
+    }
+    delete up;
+}
+int msgpu_upload_begin(msgpu_ctx* h, const uint64_t* const* mats, const uint64_t* heights, const uint64_t* widths, uint64_t n_mats,
+                       msgpu_upload** out) {
+    return guard([&] {
+        Ctx& c = h->c;
+        MSG_REQUIRE(out && mats && heights && widths && n_mats > 0, "upload_begin: null or empty argument");
+        if (!c.copy_stream) MSG_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        msgpu_upload* up = new msgpu_upload();
+        up->ctx = &c;
+        try {
+            // the blocks may just have been freed by work still running on the main stream: the copies start behind it
+            cudaEvent_t e0;
+            MSG_CUDA(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+            MSG_CUDA(cudaEventRecord(e0, c.stream));
+            MSG_CUDA(cudaStreamWaitEvent(c.copy_stream, e0, 0));
+            cudaEventDestroy(e0);
+            for (u64 i = 0; i < n_mats; i++) {
+                check_shape(heights[i], widths[i]);
+                msgpu_upload::Item it{nullptr, heights[i], widths[i], nullptr};
+                const u64 bytes = heights[i] * widths[i] * 8;
+                it.dev = (u64*)c.alloc(bytes);
+                up->items.push_back(it);
+                MSG_CUDA(cudaEventCreateWithFlags(&up->items.back().ready, cudaEventDisableTiming));
+                if (bytes) {
+                    MSG_REQUIRE(mats[i], "upload_begin: null matrix");
+                    MSG_CUDA(cudaMemcpyAsync(it.dev, mats[i], bytes, cudaMemcpyHostToDevice, c.copy_stream));
+                }
+                MSG_CUDA(cudaEventRecord(up->items.back().ready, c.copy_stream));
+            }
+        } catch (...) {
+            upload_destroy(up, true);
+            throw;
+        }
+        *out = up;
+    });
+}
+void msgpu_upload_free(msgpu_upload* up) { upload_destroy(up, true); }
+int msgpu_commit_upload(msgpu_upload* up, uint32_t log_blowup, int verify_canonical, uint64_t** kept_inputs, int local_only,
+                        msgpu_pdata** out, uint8_t* root32) {
+    return guard([&] {
+        MSG_REQUIRE(up && out && (root32 || local_only), "commit_upload: null argument");
+        Ctx& c = *up->ctx;
+        msgpu_pdata* pd = new msgpu_pdata();
+        pd->ctx = &c;
+        DevBuf flag(c, 4);
+        try {
+            MSG_CUDA(cudaMemsetAsync(flag.p, 0, 4, c.stream));
+            for (auto& it : up->items) {
+                // matrix i is extended while matrices i + 1 ... are still arriving
+                MSG_CUDA(cudaStreamWaitEvent(c.stream, it.ready, 0));
+                const u64 out_h = it.height << log_blowup;
+                msgpu_pdata::Mat m{(u64*)c.alloc(out_h * it.width * 8), out_h, it.width, true};
+                pd->mats.push_back(m);
+                if (it.width == 0) continue;
+                if (verify_canonical) check_canonical(c, it.dev, it.height * it.width, (u32*)flag.p);
+                StageScope stage_scope(c, "lde");
+                DevBuf tmp(c, it.height * it.width * 8);
+                ntt_coset_lde(c, it.dev, m.ptr, tmp.u(), it.height, it.width, log_blowup, msh::GL_GENERATOR);
+            }
+            u32 bad = 0;
+            MSG_CUDA(cudaMemcpyAsync(&bad, flag.p, 4, cudaMemcpyDeviceToHost, c.stream));
+            if (local_only) {
+                mmcs_build_local(c, pd);  // leaf digests per height class only (sharded commitments)
+                c.sync();
+            } else {
+                mmcs_build(c, pd);  // synchronises
+            }
+            MSG_REQUIRE(bad == 0, "commit_upload: value is not a canonical field element (>= p)");
+        } catch (...) {
+            pdata_destroy(pd);
+            upload_destroy(up, true);
+            throw;
+        }
+        for (size_t i = 0; i < up->items.size(); i++) {
+            if (kept_inputs) kept_inputs[i] = (uint64_t*)up->items[i].dev;
+        }
+        upload_destroy(up, kept_inputs == nullptr);
+        if (root32) memcpy(root32, pd->root, 32);
+        *out = pd;
+    });
+}
+
 int msgpu_commit_dev(msgpu_ctx* h, const uint64_t* const* mats, const uint64_t* heights, const uint64_t* widths,
                      uint64_t n_mats, uint32_t log_blowup, msgpu_pdata** out, uint8_t* root32) {
     return guard([&] {

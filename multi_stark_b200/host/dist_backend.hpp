@@ -115,9 +115,11 @@ struct DistMatrix {
 };
 
 // Pcs::commit / commit_ldes over the ranks. Adopts `dev` buffers when inputs_are_ldes.
+// `prebuilt_local`: the local part already built from `mats` (msgpu_commit_upload with local_only = 1), adopted.
 inline std::shared_ptr<DistPcsHandle> dist_commit(msgpu_ctx* ctx, const CommView& comm, const std::vector<DistMatrix>& mats, uint32_t log_blowup,
-                                                  bool inputs_are_ldes, Digest& root) {
+                                                  bool inputs_are_ldes, Digest& root, msgpu_pdata* prebuilt_local = nullptr) {
     auto h = std::make_shared<DistPcsHandle>();
+    h->local = prebuilt_local;  // adopted first: released with the handle on every error path
     std::vector<uint64_t*> ptrs;
     std::vector<uint64_t> hs, ws;
     for (auto& m : mats) {
@@ -135,7 +137,7 @@ inline std::shared_ptr<DistPcsHandle> dist_commit(msgpu_ctx* ctx, const CommView
     if (mats.empty()) throw DistError("commit: no matrices given");
     auto cls = class_owners(h->shapes, h->owner);
     h->tree_owner = cls.begin()->second;
-    if (!ptrs.empty()) gpu_check(msgpu_commit_local_dev(ctx, ptrs.data(), hs.data(), ws.data(), ptrs.size(), log_blowup, inputs_are_ldes ? 1 : 0, &h->local));
+    if (!prebuilt_local && !ptrs.empty()) gpu_check(msgpu_commit_local_dev(ctx, ptrs.data(), hs.data(), ws.data(), ptrs.size(), log_blowup, inputs_are_ldes ? 1 : 0, &h->local));
     // class digests -> tree owner
     std::vector<uint64_t> class_h;
     std::vector<const uint8_t*> class_ptr;
@@ -483,19 +485,42 @@ class DistGpuBackend : public GpuBackend {
         end_proof();
         active_ = circuits;
         std::vector<DistMatrix> mats;
+        std::vector<const uint64_t*> ptrs;
+        std::vector<uint64_t> hs, ws;
+        std::vector<size_t> local_pos;
         for (size_t p = 0; p < circuits.size(); p++) {
             const MatrixView& m = traces[p];
-            DistMatrix dm{m.height(), m.width, owner_[circuits[p]], nullptr};
-            if (dm.owner == comm_.rank()) {
-                if (!m.data) throw DistError("sharded prover: the trace of a circuit this rank owns is missing");
-                dm.dev = upload((const uint64_t*)m.data, m.height() * m.width);
-            }
-            trace_dev_.push_back(dm.dev);
+            mats.push_back(DistMatrix{m.height(), m.width, owner_[circuits[p]], nullptr});
             trace_rows_.push_back(m.height());
-            mats.push_back(dm);
+            if (mats.back().owner != comm_.rank()) continue;
+            if (!m.data) throw DistError("sharded prover: the trace of a circuit this rank owns is missing");
+            ptrs.push_back((const uint64_t*)m.data);
+            hs.push_back(m.height());
+            ws.push_back(m.width);
+            local_pos.push_back(p);
         }
-        prefetch_announced_claims();
-        return dist_commit(ctx_, comm_, mats, (uint32_t)shape_.log_blowup(), false, root);
+        trace_dev_.assign(circuits.size(), nullptr);
+        msgpu_pdata* local = nullptr;
+        if (!ptrs.empty()) {
+            // this rank's traces cross PCIe on the copy stream while the earlier ones are extended; the claims follow them
+            msgpu_upload* up = nullptr;
+            gpu_check(msgpu_upload_begin(ctx_, ptrs.data(), hs.data(), ws.data(), ptrs.size(), &up));
+            try {
+                prefetch_announced_claims();
+            } catch (...) {
+                msgpu_upload_free(up);
+                throw;
+            }
+            std::vector<uint64_t*> kept(ptrs.size(), nullptr);
+            gpu_check(msgpu_commit_upload(up, (uint32_t)shape_.log_blowup(), 1, kept.data(), 1, &local, nullptr));
+            for (size_t k = 0; k < kept.size(); k++) {
+                trace_dev_[local_pos[k]] = kept[k];
+                mats[local_pos[k]].dev = kept[k];
+            }
+        } else {
+            prefetch_announced_claims();
+        }
+        return dist_commit(ctx_, comm_, mats, (uint32_t)shape_.log_blowup(), false, root, local);
     }
 
     PcsHandlePtr commit_stage2(Fp2 beta, Fp2 gamma, Fp2 acc, std::vector<Fp2>& intermediate, Digest& root) override {

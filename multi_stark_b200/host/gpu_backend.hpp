@@ -231,16 +231,27 @@ class GpuBackend : public ProverBackend {
         std::vector<const uint64_t*> ptrs;
         std::vector<uint64_t> hs, ws;
         for (auto& m : traces) {
-            uint64_t* d = upload((const uint64_t*)m.data, m.height() * m.width);
-            trace_dev_.push_back(d);
-            trace_rows_.push_back(m.height());
-            ptrs.push_back(d);
+            ptrs.push_back((const uint64_t*)m.data);
             hs.push_back(m.height());
             ws.push_back(m.width);
+            trace_rows_.push_back(m.height());
         }
-        prefetch_announced_claims();  // the traces are on the device: the claims travel under the LDE / Merkle kernels
+        // uploads on the copy stream (trace i + 1 crosses PCIe while trace i is extended), the claims queued right behind them
+        msgpu_upload* up = nullptr;
+        gpu_check(msgpu_upload_begin(ctx_, ptrs.data(), hs.data(), ws.data(), traces.size(), &up));
+        try {
+            prefetch_announced_claims();
+        } catch (...) {
+            msgpu_upload_free(up);
+            throw;
+        }
+        trace_dev_.assign(traces.size(), nullptr);
         msgpu_pdata* pd = nullptr;
-        gpu_check(msgpu_commit_dev(ctx_, ptrs.data(), hs.data(), ws.data(), traces.size(), (uint32_t)shape_.log_blowup(), &pd, root.data()));
+        int rc = msgpu_commit_upload(up, (uint32_t)shape_.log_blowup(), 1, trace_dev_.data(), 0, &pd, root.data());
+        if (rc != 0) {
+            trace_dev_.clear();  // the library released the buffers
+            gpu_check(rc);
+        }
         return std::make_shared<GpuPcsHandle>(pd);
     }
 
