@@ -499,6 +499,16 @@ class DistGpuBackend : public GpuBackend {
             ws.push_back(m.width);
             local_pos.push_back(p);
         }
+        // The claims (global, not sharded) are uploaded, hashed and accumulated by ONE rank, the one with the least trace
+        // data; the others receive 32 + 16 bytes. (Every rank doing it put N copies of the claims on the host's PCIe.)
+        {
+            std::vector<uint64_t> load(comm_.world(), 0);
+            for (auto& m : mats) load[m.owner] += (uint64_t)m.height * m.width;
+            claims_rank_ = 0;
+            for (int r = 0; r < comm_.world(); r++)
+                if (load[r] <= load[claims_rank_]) claims_rank_ = r;
+            if (comm_.rank() != claims_rank_) announced_ = ClaimsView();
+        }
         trace_dev_.assign(circuits.size(), nullptr);
         msgpu_pdata* local = nullptr;
         if (!ptrs.empty()) {
@@ -521,6 +531,27 @@ class DistGpuBackend : public GpuBackend {
             prefetch_announced_claims();
         }
         return dist_commit(ctx_, comm_, mats, (uint32_t)shape_.log_blowup(), false, root, local);
+    }
+
+    bool observe_claims(Challenger& ch, const ClaimsView& claims) override {
+        if (!claims_on_device(claims)) return GpuBackend::observe_claims(ch, claims);  // small set: every rank runs the host loop
+        Digest d{};
+        if (comm_.rank() == claims_rank_ && !claims_transcript_digest(ch.input_buffer(), claims, d))
+            throw DistError("claims: internal error, device path refused");
+        comm_.bcast(d.data(), 32, claims_rank_);
+        ch.set_flushed(d);
+        return true;
+    }
+    Fp2 claims_accumulator(const ClaimsView& claims, Fp2 beta, Fp2 gamma) override {
+        if (!claims_on_device(claims)) return GpuBackend::claims_accumulator(claims, beta, gamma);
+        uint64_t out[2] = {0, 0};
+        if (comm_.rank() == claims_rank_) {
+            Fp2 a = GpuBackend::claims_accumulator(claims, beta, gamma);
+            out[0] = a.c[0].v;
+            out[1] = a.c[1].v;
+        }
+        comm_.bcast(out, 16, claims_rank_);
+        return Fp2(Fp(out[0]), Fp(out[1]));
     }
 
     PcsHandlePtr commit_stage2(Fp2 beta, Fp2 gamma, Fp2 acc, std::vector<Fp2>& intermediate, Digest& root) override {
@@ -615,6 +646,7 @@ class DistGpuBackend : public GpuBackend {
   private:
     CommView comm_;
     std::vector<int> owner_;
+    int claims_rank_ = 0;
 };
 
 }  // namespace msh

@@ -258,23 +258,8 @@ class GpuBackend : public ProverBackend {
     void announce_claims(const ClaimsView& claims) override { announced_ = claims; }
 
     bool observe_claims(Challenger& ch, const ClaimsView& claims) override {
-        size_t len = claims.uniform_len();
-        if (len == 0 || claims.size() * len < 4096) {  // small or ragged: the host loop is cheaper; the ABI's precondition is checked here
-            size_t total = claims.total();
-            for (size_t k = 0; k < total; k++)
-                if (claims.values[k].v >= GL_P) throw GpuError("claim value is not canonical");
-            return false;
-        }
         Digest d;
-        const std::vector<u8>& prefix = ch.input_buffer();
-        if (claims_dev_ && prefetched_from_ == (const void*)claims.at(0) && prefetched_n_ == claims.size() && prefetched_len_ == len) {
-            gpu_check(msgpu_claims_digest(claims_dev_, prefix.data(), prefix.size(), d.data()));
-        } else {
-            drop_claims();
-            gpu_check(msgpu_claims_upload(ctx_, (const uint64_t*)claims.at(0), claims.size(), len, prefix.data(), prefix.size(), &claims_dev_,
-                                          d.data()));
-        }
-        prefetched_from_ = nullptr;
+        if (!claims_transcript_digest(ch.input_buffer(), claims, d)) return false;
         ch.set_flushed(d);
         return true;
     }
@@ -382,6 +367,31 @@ class GpuBackend : public ProverBackend {
     }
 
   protected:  // the sharded backend (dist_backend.hpp) reuses the per-circuit state
+    // true if the claim set is large and uniform (same rule on every rank: it depends on the shape only)
+    static bool claims_on_device(const ClaimsView& claims) {
+        size_t len = claims.uniform_len();
+        return len != 0 && claims.size() * len >= 4096;
+    }
+    // BLAKE3(prefix || length-prefixed claims) on the device (false = small or ragged set: the host loop is cheaper; the
+    // ABI's precondition is then checked here)
+    bool claims_transcript_digest(const std::vector<u8>& prefix, const ClaimsView& claims, Digest& d) {
+        if (!claims_on_device(claims)) {
+            size_t total = claims.total();
+            for (size_t k = 0; k < total; k++)
+                if (claims.values[k].v >= GL_P) throw GpuError("claim value is not canonical");
+            return false;
+        }
+        size_t len = claims.uniform_len();
+        if (claims_dev_ && prefetched_from_ == (const void*)claims.at(0) && prefetched_n_ == claims.size() && prefetched_len_ == len) {
+            gpu_check(msgpu_claims_digest(claims_dev_, prefix.data(), prefix.size(), d.data()));
+        } else {
+            drop_claims();
+            gpu_check(msgpu_claims_upload(ctx_, (const uint64_t*)claims.at(0), claims.size(), len, prefix.data(), prefix.size(), &claims_dev_,
+                                          d.data()));
+        }
+        prefetched_from_ = nullptr;
+        return true;
+    }
     // H2D copy + check that every value is canonical (the ABI's precondition, verified on the device)
     uint64_t* upload(const uint64_t* src, size_t n) {
         void* d = nullptr;
