@@ -625,7 +625,9 @@ class DistGpuBackend : public GpuBackend {
             }
             return dist_commit(ctx_, comm_, mats, lb, true, root);  // adopts the LDE buffers
         } catch (...) {
-            // buffers not yet adopted are leaked only on error paths before msgpu_commit_local_dev; free what we can
+            // LDE buffers the commitment has not adopted yet are still ours; the arena refuses (without harm) the ones it
+            // has already released with the handle
+            for (auto* d : ldes) msgpu_free(ctx_, d);
             throw;
         }
     }
