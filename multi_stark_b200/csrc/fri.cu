@@ -483,11 +483,7 @@ static void reduce_all(Ctx& c, msgpu_open* op, msh::Fp2 alpha) {
     MSG_CUDA(cudaMemcpyAsync(d_apow.p, apow_flat.data(), apow_flat.size() * 8, cudaMemcpyHostToDevice, c.stream));
     u64* ro[33] = {nullptr};
     u64 num_reduced[33] = {0};
-    static bool attr = false;
-    if (!attr) {
-        MSG_CUDA(cudaFuncSetAttribute(k_reduce_openings, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
-    }
+    ensure_max_smem(k_reduce_openings, 200 * 1024);
     for (auto& round : op->rounds)
         for (auto& m : round) {
             u32 lh = m.log_h;
@@ -706,11 +702,7 @@ int msgpu_fri_fold(msgpu_open* op, const uint64_t* beta2) {
             fp.ginv_tab = tab;
             fp.half_len = (u32)half;
             fp.log_half = log_half;
-            static bool attr = false;
-            if (!attr) {
-                MSG_CUDA(cudaFuncSetAttribute(k_fri_fold_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFusedFoldMax / 2 * 48)));
-                attr = true;
-            }
+            ensure_max_smem(k_fri_fold_commit, (int)(kFusedFoldMax / 2 * 48));
             {
                 KLaunch kl(c, "k_fri_fold_commit");
                 k_fri_fold_commit<<<1, 256, (size_t)rows * 48, c.stream>>>(fp);

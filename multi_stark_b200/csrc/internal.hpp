@@ -5,6 +5,8 @@
 #include <cstdint>
 #include <cstddef>
 #include <map>
+#include <mutex>
+#include <set>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -94,6 +96,20 @@ struct Ctx {
 };
 
 void ctx_init_tables(Ctx& c);
+
+// Opt a kernel in to more than 48 KB of dynamic shared memory, once per (device, kernel): the attribute belongs to the
+// device's instance of the function, so a process-wide "done" flag would leave a second device without it.
+template <class F>
+inline void ensure_max_smem(F* func, int bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<int, const void*>> done;
+    int dev = 0;
+    MSG_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count({dev, (const void*)func})) return;
+    MSG_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.insert({dev, (const void*)func});
+}
 
 inline double host_now_us() {
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();

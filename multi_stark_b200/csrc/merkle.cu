@@ -431,11 +431,7 @@ void b3_hash_rows(Ctx& c, const std::vector<MatRef>& mats, uint8_t* digests) {
     } else if (rows >= 32 || (u64)rows >= height) {
         if (rows > 32) rows = rows / 32 * 32;
         if (rows == 0) rows = 1;
-        static bool attr = false;
-        if (!attr) {
-            MSG_CUDA(cudaFuncSetAttribute(k_hash_rows_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-            attr = true;
-        }
+        ensure_max_smem(k_hash_rows_staged, (int)budget);
         u64 blocks = (height + rows - 1) / rows;
         KLaunch kl(c, "k_hash_rows_staged");
         k_hash_rows_staged<<<(unsigned)blocks, kLeafThreads, (size_t)rows * pitch * 4, c.stream>>>(
@@ -473,11 +469,7 @@ void b3_merkle_subtrees(Ctx& c, const uint8_t* in, u64 len, u32 levels, uint8_t*
         p.inject[l] = (const uint4*)inject[l];
     }
     size_t smem = ((size_t)1 << levels) * 24;  // chunk/2 + chunk/4 digests
-    static bool attr = false;
-    if (!attr) {
-        MSG_CUDA(cudaFuncSetAttribute(k_merkle_subtree, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 << kMaxFusedLevels));
-        attr = true;
-    }
+    ensure_max_smem(k_merkle_subtree, 24 << kMaxFusedLevels);
     u32 threads = (u32)std::min<u64>(256, std::max<u64>(32, (1ull << levels) / 2));
     {
         KLaunch kl(c, "k_merkle_subtree");

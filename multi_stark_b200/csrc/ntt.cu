@@ -358,28 +358,17 @@ static u32 tile_threads(u32 log_t) {
 
 template <int TB>
 static void launch_strided_tb(const StridedParams& p, bool inverse, u64 blocks, cudaStream_t st) {
-    static bool attr[2] = {false, false};
     if (inverse) {
-        if (!attr[1]) {
-            MSG_CUDA(cudaFuncSetAttribute(k_ntt_strided<TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(kMaxLogT)));
-            attr[1] = true;
-        }
+        ensure_max_smem(k_ntt_strided<TB, true>, (int)tile_smem(kMaxLogT));
         k_ntt_strided<TB, true><<<(unsigned)blocks, tile_threads(TB), tile_smem(TB), st>>>(p);
     } else {
-        if (!attr[0]) {
-            MSG_CUDA(cudaFuncSetAttribute(k_ntt_strided<TB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(kMaxLogT)));
-            attr[0] = true;
-        }
+        ensure_max_smem(k_ntt_strided<TB, false>, (int)tile_smem(kMaxLogT));
         k_ntt_strided<TB, false><<<(unsigned)blocks, tile_threads(TB), tile_smem(TB), st>>>(p);
     }
 }
 template <int TB>
 static void launch_block_tb(const BlockParams& p, dim3 grid, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
-        MSG_CUDA(cudaFuncSetAttribute(k_ntt_block<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem(kMaxLogT)));
-        attr = true;
-    }
+    ensure_max_smem(k_ntt_block<TB>, (int)tile_smem(kMaxLogT));
     k_ntt_block<TB><<<grid, tile_threads(TB), tile_smem(TB), st>>>(p);
 }
 

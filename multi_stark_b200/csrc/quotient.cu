@@ -788,7 +788,7 @@ int msgpu_stage2_trace(msgpu_ctx* h, const msgpu_program* prog, const uint64_t* 
             KLaunch kl(c, "k_lookup_messages");
             constexpr int NS = decltype(ns)::value;
             constexpr size_t smem = slots_smem_bytes<NS>();
-            if (smem > 48 * 1024) MSG_CUDA(cudaFuncSetAttribute(k_lookup_messages<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (smem > 48 * 1024) ensure_max_smem(k_lookup_messages<NS>, (int)smem);
             k_lookup_messages<NS><<<(unsigned)((rows + 127) / 128), kInterpThreads, smem, c.stream>>>(mp);
         });
         MSG_CUDA(cudaGetLastError());
