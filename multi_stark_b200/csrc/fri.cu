@@ -417,7 +417,7 @@ static void evaluate_all(Ctx& c, msgpu_open* op) {
                     for (u32 k = 0; k < npts; k++) bp.invden[k] = find_invden(op, m.points[p0 + k], m.log_h);
                     bp.tile_rows = (u32)std::min<u64>(256, std::max<u64>(8, 4096 / bp.wc));
                     u64 want = (h + bp.tile_rows - 1) / bp.tile_rows;
-                    u32 ctas = (u32)std::min<u64>(want, (u64)c.sm_count * 4);
+                    u32 ctas = (u32)std::min<u64>(want, (u64)c.sm_count * 6);
                     Pending pd{&m, nullptr, sums_off, ctas, npts, c0, bp.wc, p0};
                     sums_off += (size_t)bp.wc * (npts + 1) * 2;
                     pd.d_partial = (u64*)c.alloc((size_t)ctas * bp.wc * (npts + 1) * 16);
