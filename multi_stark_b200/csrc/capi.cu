@@ -578,6 +578,40 @@ int msgpu_tree_from_digests(msgpu_ctx* h, uint64_t n_classes, const uint64_t* ld
     });
 }
 uint64_t msgpu_pdata_max_height(const msgpu_pdata* pd) { return pd->max_height; }
+int msgpu_pdata_root(const msgpu_pdata* pd, uint8_t* root32) {
+    return guard([&] {
+        MSG_REQUIRE(pd && root32 && pd->digests, "pdata_root: prover data without a tree");
+        memcpy(root32, pd->root, 32);
+    });
+}
+int msgpu_pdata_digests(const msgpu_pdata* pd, uint8_t** dev_ptr, uint64_t* n_digests) {
+    return guard([&] {
+        MSG_REQUIRE(pd && pd->digests && dev_ptr && n_digests, "pdata_digests: prover data without a tree");
+        *dev_ptr = pd->digests;
+        *n_digests = 2 * pd->max_height - 1;
+    });
+}
+int msgpu_pdata_from_parts(msgpu_ctx* h, uint64_t n_blocks, const uint64_t* const* blocks, const uint64_t* widths, uint64_t lde_height,
+                           uint64_t n_parts, const uint8_t* const* part_digests, msgpu_pdata** out, uint8_t* root32) {
+    return guard([&] {
+        Ctx& c = h->c;
+        MSG_REQUIRE(blocks && widths && part_digests && out && root32 && n_blocks > 0 && n_parts > 0, "pdata_from_parts: null or empty argument");
+        std::vector<const u64*> bl;
+        std::vector<u64> ws;
+        for (u64 b = 0; b < n_blocks; b++) { bl.push_back((const u64*)blocks[b]); ws.push_back(widths[b]); }
+        std::vector<const uint8_t*> parts(part_digests, part_digests + n_parts);
+        msgpu_pdata* pd = new msgpu_pdata();
+        pd->ctx = &c;
+        try {
+            mmcs_from_parts(c, pd, bl, ws, lde_height, parts);
+        } catch (...) {
+            pdata_destroy(pd);
+            throw;
+        }
+        memcpy(root32, pd->root, 32);
+        *out = pd;
+    });
+}
 
 int msgpu_mmcs_commit(msgpu_ctx* h, const uint64_t* const* mats, const uint64_t* heights, const uint64_t* widths,
                       uint64_t n_mats, msgpu_pdata** out, uint8_t* root32) {

@@ -227,6 +227,84 @@ void mmcs_open_batch(Ctx& c, const msgpu_pdata* pd, const u64* indices_host, u64
     mmcs_open_multi(c, &pd, &shift, 1, indices_host, n_idx, opened_host, proof_host);
 }
 
+// ---- assembling one rank's prover data from a column-block sharded commitment ----------------------------------------
+constexpr int kMaxBlocks = 16;
+struct InterleaveParams {
+    const u64* blocks[kMaxBlocks];
+    u32 col0[kMaxBlocks + 1];  // first column of block b; col0[n_blocks] = total width
+    u32 n_blocks;
+    u64 rows;
+    u64* out;
+};
+// out[r][col0_b + c] = blocks[b][r][c]
+__global__ void __launch_bounds__(256) k_interleave_columns(const __grid_constant__ InterleaveParams p) {
+    const u32 W = p.col0[p.n_blocks];
+    const u64 total = p.rows * W;
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (u64)gridDim.x * blockDim.x) {
+        const u64 r = e / W;
+        const u32 col = (u32)(e % W);
+        u32 b = 0;
+        while (b + 1 < p.n_blocks && p.col0[b + 1] <= col) b++;
+        const u32 wb = p.col0[b + 1] - p.col0[b];
+        p.out[e] = p.blocks[b][r * wb + (col - p.col0[b])];
+    }
+}
+
+void mmcs_from_parts(Ctx& c, msgpu_pdata* pd, const std::vector<const u64*>& blocks, const std::vector<u64>& widths, u64 height,
+                     const std::vector<const uint8_t*>& part_digests) {
+    const u64 n_parts = part_digests.size();
+    MSG_REQUIRE(!blocks.empty() && blocks.size() <= (size_t)kMaxBlocks && blocks.size() == widths.size(), "from_parts: 1..16 column blocks expected");
+    MSG_REQUIRE(is_pow2(height) && is_pow2(n_parts) && n_parts <= height, "from_parts: heights and part counts must be powers of two");
+    u64 W = 0;
+    InterleaveParams ip{};
+    for (size_t b = 0; b < blocks.size(); b++) {
+        MSG_REQUIRE(blocks[b] && widths[b] > 0 && W + widths[b] < (1ull << 31), "from_parts: bad column block");
+        ip.blocks[b] = blocks[b];
+        ip.col0[b] = (u32)W;
+        W += widths[b];
+    }
+    ip.col0[blocks.size()] = (u32)W;
+    ip.n_blocks = (u32)blocks.size();
+    ip.rows = height;
+    u64* lde = (u64*)c.alloc(height * W * 8);
+    pd->mats.push_back(msgpu_pdata::Mat{lde, height, W, true});
+    pd->total_width = W;
+    ip.out = lde;
+    {
+        StageScope ss(c, "lde");
+        KLaunch kl(c, "k_interleave_columns");
+        k_interleave_columns<<<(unsigned)std::min<u64>((height * W + 255) / 256, (u64)c.sm_count * 16), 256, 0, c.stream>>>(ip);
+    }
+    MSG_CUDA(cudaGetLastError());
+    // digest layers: layer l of the tree is the concatenation of the parts' layer l while a part still has one
+    StageScope ss(c, "merkle");
+    mmcs_layout_layers(c, pd, height);
+    const u64 shard = height / n_parts;
+    const u32 part_layers = ilog2(shard) + 1;
+    for (u64 p = 0; p < n_parts; p++) {
+        MSG_REQUIRE(part_digests[p], "from_parts: null digest part");
+        u64 off = 0;
+        for (u32 l = 0; l < part_layers; l++) {
+            const u64 len = shard >> l;
+            MSG_CUDA(cudaMemcpyAsync(pd->digests + (pd->layer_off[l] + p * len) * 32, part_digests[p] + off * 32, len * 32,
+                                     cudaMemcpyDeviceToDevice, c.stream));
+            off += len;
+        }
+    }
+    if (n_parts > 1) {  // the top log2(n_parts) levels over the parts' roots
+        const u32 l0 = part_layers - 1, levels = ilog2(n_parts);
+        uint8_t* outs[16];
+        const uint8_t* injs[16];
+        for (u32 k = 0; k < levels; k++) {
+            outs[k] = pd->digests + pd->layer_off[l0 + 1 + k] * 32;
+            injs[k] = nullptr;
+        }
+        b3_merkle_subtrees(c, pd->digests + pd->layer_off[l0] * 32, n_parts, levels, outs, injs);
+    }
+    MSG_CUDA(cudaMemcpyAsync(pd->root, pd->digests + pd->layer_off.back() * 32, 32, cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+}
+
 void pdata_destroy(msgpu_pdata* pd) {
     if (!pd) return;
     Ctx& c = *pd->ctx;

@@ -756,7 +756,8 @@ int msgpu_stage2_trace(msgpu_ctx* h, const msgpu_program* prog, const uint64_t* 
     return guard([&] {
         Ctx& c = h->c;
         StageScope ss(c, "stage2");
-        MSG_REQUIRE(prog && main_dev && stage2_out_dev && local_sum2, "stage2_trace: null argument");
+        MSG_REQUIRE(prog && stage2_out_dev && local_sum2, "stage2_trace: null argument");
+        MSG_REQUIRE(main_dev || prog->n_lookups == 0, "stage2_trace: the main trace is needed to evaluate the lookups");
         MSG_REQUIRE(prog->pre_width == 0 || pre_dev, "stage2_trace: circuit has a preprocessed trace but none was given");
         local_sum2[0] = local_sum2[1] = 0;
         if (rows == 0) return;

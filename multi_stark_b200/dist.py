@@ -440,7 +440,7 @@ class WideCommit:
             self._recv = None
 
 
-def commit_wide_sharded(ctx, comm, block, width, log_blowup, timings=None):
+def commit_wide_sharded(ctx, comm, block, width, log_blowup, timings=None, keep_block=False):
     """`Pcs::commit` (src/prover.rs:350) of one n x `width` matrix whose COLUMN block `column_blocks(width, N)[rank]` is
     `block` (host array n x w_r, canonical values) on this rank. Per rank: upload + coset LDE of the block (the NTT is
     column-local), ONE all-to-all that turns column blocks into row shards (the block's rows [d * H / N, (d+1) * H / N) are
@@ -475,7 +475,9 @@ def commit_wide_sharded(ctx, comm, block, width, log_blowup, timings=None):
     send_counts = [shard * w * 8] * world
     recv_counts = [shard * ws * 8 for ws in widths]
     comm.all_to_all_dev(d_lde, send_counts, recv, recv_counts)
-    ctx.free(d_lde)
+    if not keep_block:
+        ctx.free(d_lde)
+        d_lde = None
     ctx.sync()
     t.append(time.perf_counter())
     # the shard as N matrices of one height: their rows concatenate in column order inside the leaf hash
@@ -508,4 +510,66 @@ def commit_wide_sharded(ctx, comm, block, width, log_blowup, timings=None):
     if timings is not None:
         for k, name in enumerate(["upload", "lde", "all_to_all", "leaf_hash_subtree", "top"]):
             timings[name] = timings.get(name, 0.0) + (t[k + 1] - t[k]) * 1e3
-    return root, WideCommit(ctx, comm, local, top, root, H, widths, recv)
+    wc = WideCommit(ctx, comm, local, top, root, H, widths, recv)
+    wc.lde_block = d_lde  # this rank's column block of the LDE (H x w), kept for prove_wide_sharded
+    return root, wc
+
+
+def prove_wide_sharded(ctx, comm, prover, block, width, log_blowup, claims=None, timings=None):
+    """`prove()` of a system with ONE wide, lookup-free circuit (BASELINE configs[2]) whose trace arrives as column blocks, one
+    per rank. The stage-1 commitment -- upload, LDE and leaf hashing of 256 columns, 83 % of the single-GPU proof -- is made
+    by all ranks (commit_wide_sharded); rank 0 then gathers the LDE blocks and the shards' digest layers over NVLink,
+    assembles ordinary prover data (msgpu_pdata_from_parts) and runs the remaining stages alone. Returns the proof bytes on
+    rank 0 (None elsewhere); they equal the single-GPU proof byte for byte. `prover` is a `Prover` on rank 0, None elsewhere."""
+    import numpy as np
+    L = ctx.L
+    t = [time.perf_counter()]
+    root, wc = commit_wide_sharded(ctx, comm, block, width, log_blowup, timings=timings, keep_block=True)
+    t.append(time.perf_counter())
+    world, rank = comm.world, comm.rank
+    H, widths = wc.lde_height, wc.widths
+    dg, nd = _C.c_void_p(), _C.c_uint64()
+    check(L.msgpu_pdata_digests(wc.local.h, _C.byref(dg), _C.byref(nd)))
+    nd = int(nd.value)
+    proof = None
+    if rank == 0:
+        blocks, parts = [wc.lde_block], [dg.value]
+        for r in range(1, world):
+            blocks.append(ctx.malloc(H * widths[r] * 8))
+            parts.append(ctx.malloc(nd * 32))
+        for r in range(1, world):
+            for ptr, nbytes in ((blocks[r], H * widths[r] * 8), (parts[r], nd * 32)):
+                if comm.struct.sendrecv_dev(None, ptr, nbytes, r, 0) != 0:
+                    raise RuntimeError("gather failed: %s" % comm.errors)
+        t.append(time.perf_counter())
+        pd, r32 = _C.c_void_p(), np.zeros(32, dtype=np.uint8)
+        ba = (_C.c_void_p * world)(*blocks)
+        wa = (_C.c_uint64 * world)(*widths)
+        pa = (_C.c_void_p * world)(*parts)
+        check(L.msgpu_pdata_from_parts(ctx.h, world, ba, wa, H, world, pa, _C.byref(pd), r32.ctypes.data_as(_C.c_void_p)))
+        for r in range(1, world):
+            ctx.free(blocks[r])
+            ctx.free(parts[r])
+        if bytes(r32) != root:
+            L.msgpu_pdata_free(pd)
+            raise RuntimeError("assembled commitment differs from the sharded one")
+        ctx.free(wc.lde_block)
+        wc.lde_block = None
+        wc.free()  # the row shard and its subtree are not needed any more: the assembled prover data serves the openings
+        t.append(time.perf_counter())
+        proof = prover.prove_precommitted(pd, [H >> log_blowup], claims)
+        t.append(time.perf_counter())
+        names = ["commit_sharded", "gather", "assemble", "prove_rest"]
+    else:
+        for ptr, nbytes in ((wc.lde_block, H * widths[rank] * 8), (dg.value, nd * 32)):
+            if comm.struct.sendrecv_dev(None, ptr, nbytes, rank, 0) != 0:
+                raise RuntimeError("gather failed: %s" % comm.errors)
+        t.append(time.perf_counter())
+        ctx.free(wc.lde_block)
+        wc.lde_block = None
+        wc.free()
+        names = ["commit_sharded", "gather"]
+    if timings is not None:
+        for k, name in enumerate(names):
+            timings[name] = (t[k + 1] - t[k]) * 1e3
+    return proof

@@ -98,9 +98,16 @@ def fib_trace(rows):
     return out
 
 
-def wide_trace(rows, width, row0=0, out=None):
-    """Trace of the "wide:W" system (BASELINE configs[2]): column 2k = splitmix64(row * W + 2k) mod p, column 2k+1 its cube."""
+def wide_trace(rows, width, row0=0, out=None, cols=None):
+    """Trace of the "wide:W" system (BASELINE configs[2]): column 2k = splitmix64(row * W + 2k) mod p, column 2k+1 its cube.
+    cols = (c0, c1): only that column block, as a dense rows x (c1 - c0) matrix (one rank's share of a column-sharded commit)."""
     H = _ffi.host_lib()
+    if cols is not None:
+        c0, c1 = cols
+        if out is None:
+            out = np.zeros((rows, c1 - c0), dtype=np.uint64)
+        H.msh_wide_trace_block(row0, rows, width, c0, c1, out.ctypes.data_as(C.c_void_p))
+        return out
     if out is None:
         out = np.zeros((rows, width), dtype=np.uint64)
     H.msh_wide_trace(row0, rows, width, out.ctypes.data_as(C.c_void_p))
@@ -226,6 +233,30 @@ class Prover:
         out, ln = C.c_void_p(), C.c_uint64()
         ms = (C.c_double * 6)()
         rc = self.H.msh_prove(self.h, ptrs, hs, flat.ctypes.data_as(_ffi.c_u64p), offs_p, stride, n_claims,
+                              C.byref(out), C.byref(ln), ms)
+        if rc != 0:
+            raise _ffi.MsgpuError(rc, (self.H.msh_last_error() or b"").decode())
+        data = C.string_at(out.value, ln.value)
+        self.H.msh_bytes_free(out)
+        self.last_stage_ms = dict(zip(STAGE_NAMES, ms))
+        return data
+
+    def prove_precommitted(self, stage1_pdata, heights, claims=None):
+        """prove() whose stage-1 commitment was made elsewhere (`msgpu_pdata_from_parts`: one wide matrix committed by column
+        blocks over several GPUs). `stage1_pdata`: raw msgpu_pdata handle, adopted; heights[i]: trace rows of circuit i. Only
+        for lookup-free circuits (the stage-2 construction of a circuit with lookups reads its main trace)."""
+        n = self.system.num_circuits
+        if len(heights) != n:
+            raise _ffi.MsgpuError(-1, "expected one height per circuit")
+        if self.H.msh_prover_inject_stage1(self.h, stage1_pdata) != 0:
+            raise _ffi.MsgpuError(-1, (self.H.msh_last_error() or b"").decode())
+        ptrs = (C.c_void_p * n)(*([None] * n))
+        hs = (C.c_uint64 * n)(*[int(h) for h in heights])
+        cl = np.zeros((0, 1), dtype=np.uint64) if claims is None or len(claims) == 0 else np.ascontiguousarray(claims, dtype=np.uint64)
+        flat = cl.reshape(-1) if cl.size else np.zeros(1, dtype=np.uint64)
+        out, ln = C.c_void_p(), C.c_uint64()
+        ms = (C.c_double * 6)()
+        rc = self.H.msh_prove(self.h, ptrs, hs, flat.ctypes.data_as(_ffi.c_u64p), None, cl.shape[1], cl.shape[0],
                               C.byref(out), C.byref(ln), ms)
         if rc != 0:
             raise _ffi.MsgpuError(rc, (self.H.msh_last_error() or b"").decode())
