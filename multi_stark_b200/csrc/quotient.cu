@@ -16,6 +16,8 @@
 // committed LDEs are read where they lie: the quotient domain GENERATOR * H_{nq} is the first nq stored
 // rows of every LDE in bit-reversed order, so the "current row" stream is fully coalesced.
 #include "capi_common.hpp"
+#include <cstdio>
+#include <cstdlib>
 #include "../host/blake3_host.hpp"
 #include <cstring>
 #include "mmcs.hpp"
@@ -24,7 +26,8 @@
 
 namespace msg {
 
-enum : u32 { OP_CONST = 0, OP_VAR = 1, OP_PUBLIC = 2, OP_FIRST = 3, OP_LAST = 4, OP_TRANS = 5, OP_ADD = 6, OP_SUB = 7, OP_MUL = 8, OP_NEG = 9 };
+enum : u32 { OP_CONST = 0, OP_VAR = 1, OP_PUBLIC = 2, OP_FIRST = 3, OP_LAST = 4, OP_TRANS = 5, OP_ADD = 6, OP_SUB = 7, OP_MUL = 8, OP_NEG = 9,
+             OP_ROOT = 10 };  // OP_ROOT (lowering only): constraint `imm` has the value of slot `a`; folded at once, the slot is free again
 
 struct alignas(16) Instr {  // 32 bytes: two 16-byte uniform loads per instruction
     u32 op, dst, a, b;
@@ -38,8 +41,11 @@ struct Lowered {
     u32 n_slots = 0;
 };
 
-// Lower nodes [0, len) keeping `pinned` nodes alive to the end. Dead nodes are dropped.
-static Lowered lower(const msgpu_graph_desc& g, u32 len, const std::vector<u32>& pinned) {
+// Lower nodes [0, len) keeping `pinned` nodes alive to the end. Dead nodes are dropped. `roots[j]` = node of constraint j:
+// an OP_ROOT instruction follows the node's own, so that the kernel folds the value into the alpha accumulators at once and
+// the slot dies with the node's last real use (a wide AIR has hundreds of roots: kept alive to the end they made the
+// interpreter's working set 2 KB per thread, k_quotient_eval<256>, issue rate 32 %).
+static Lowered lower(const msgpu_graph_desc& g, u32 len, const std::vector<u32>& pinned, const std::vector<u32>& roots = {}) {
     const u32 NONE = 0xffffffffu;
     std::vector<u32> last_use(len, NONE);
     std::vector<char> pin(len, 0), live(len, 0);
@@ -47,6 +53,12 @@ static Lowered lower(const msgpu_graph_desc& g, u32 len, const std::vector<u32>&
         MSG_REQUIRE(p < len, "program: pinned node outside the evaluated range");
         pin[p] = 1;
         live[p] = 1;
+    }
+    std::vector<std::vector<u32>> root_ids(len);
+    for (u32 j = 0; j < roots.size(); j++) {
+        MSG_REQUIRE(roots[j] < len, "program: constraint root outside the evaluated range");
+        live[roots[j]] = 1;
+        root_ids[roots[j]].push_back(j);
     }
     auto nchildren = [&](u32 i) -> int {
         uint8_t op = g.op[i];
@@ -71,8 +83,9 @@ static Lowered lower(const msgpu_graph_desc& g, u32 len, const std::vector<u32>&
     Lowered out;
     out.slot_of.assign(len, NONE);
     std::vector<u32> free_slots;
-    for (u32 i = 0; i < len; i++) {
-        if (!live[i]) continue;
+    // Leaves (constants, column reads, publics, selectors) are materialised at their FIRST USE, not at their node id: the
+    // graph interns every column read up front, which would keep all of them alive at once.
+    auto emit = [&](u32 i) {
         Instr in{};
         in.op = g.op[i];
         MSG_REQUIRE(in.op <= OP_NEG, "program: bad opcode");
@@ -106,6 +119,23 @@ static Lowered lower(const msgpu_graph_desc& g, u32 len, const std::vector<u32>&
         out.slot_of[i] = slot;
         in.dst = slot;
         out.code.push_back(in);
+        for (u32 j : root_ids[i]) {
+            Instr r{};
+            r.op = OP_ROOT;
+            r.a = slot;
+            r.imm = j;
+            out.code.push_back(r);
+        }
+        // a root nobody reads later (and that no lookup needs) gives its slot back right after the fold
+        if (!root_ids[i].empty() && !pin[i] && last_use[i] == NONE) free_slots.push_back(slot);
+    };
+    for (u32 i = 0; i < len; i++) {
+        if (!live[i] || out.slot_of[i] != NONE) continue;
+        const int nc = nchildren(i);
+        if (nc == 0 && !pin[i] && root_ids[i].empty()) continue;  // lazy leaf
+        if (nc >= 1 && out.slot_of[g.a[i]] == NONE) emit(g.a[i]);
+        if (nc == 2 && out.slot_of[g.b[i]] == NONE) emit(g.b[i]);
+        emit(i);
     }
     if (out.n_slots == 0) out.n_slots = 1;
     return out;
@@ -188,13 +218,29 @@ struct Slots<NSLOT, true> {
 template <int NSLOT>
 constexpr size_t slots_smem_bytes() { return NSLOT <= kSmemSlotsMax ? (size_t)NSLOT * kInterpThreads * 8 : 0; }
 
-template <int NSLOT, class S>
-__device__ __forceinline__ void run_program(const Instr* __restrict__ prog, u32 n, S& slots, const RowCtx& cx) {
+struct NoRoots {
+    __device__ __forceinline__ void operator()(u32, u64) const {}
+};
+template <int NSLOT, class S, class Root = NoRoots>
+__device__ __forceinline__ void run_program(const Instr* __restrict__ prog, u32 n, S& slots, const RowCtx& cx, Root on_root = Root()) {
+    static_assert(sizeof(Instr) == 32, "Instr must be 32 bytes");
+    if (n == 0) return;
+    // the next instruction is fetched while the current one executes (its fetch latency would otherwise sit on the critical
+    // path of every interpreted instruction)
+    uint4 nw0 = __ldg(reinterpret_cast<const uint4*>(prog));
+    u64 nimm = __ldg(reinterpret_cast<const u64*>(prog) + 2);
     for (u32 pc = 0; pc < n; pc++) {
-        const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(prog + pc));
-        const u64 imm = __ldg(reinterpret_cast<const u64*>(prog + pc) + 2);
-        static_assert(sizeof(Instr) == 32, "Instr must be 32 bytes");
+        const uint4 w0 = nw0;
+        const u64 imm = nimm;
+        if (pc + 1 < n) {
+            nw0 = __ldg(reinterpret_cast<const uint4*>(prog + pc + 1));
+            nimm = __ldg(reinterpret_cast<const u64*>(prog + pc + 1) + 2);
+        }
         const u32 op = w0.x, dst = w0.y, a = w0.z, b = w0.w;
+        if (op == OP_ROOT) {
+            on_root((u32)imm, slots[a]);
+            continue;
+        }
         u64 v;
         switch (op) {
             case OP_CONST: v = imm; break;
@@ -295,16 +341,14 @@ __global__ void __launch_bounds__(128) k_quotient_eval(QuotParams p) {
     cx.last = p.sel_last[s];
     cx.trans = gl::sub(gl::pow_lookup(p.xtab, i), p.g_inv);
     Slots<NSLOT, false> slots;  // measured: shared-memory slots make THIS kernel slower (1.83 -> 2.58 ms at 2^22 rows), local ones stay
-    run_program<NSLOT>(p.prog, p.n_instr, slots, cx);
-
-    // alpha-fold with lazy 160-bit accumulation: one reduction per coordinate at the end
+    // alpha-fold with lazy 160-bit accumulation: one reduction per coordinate at the end. Constraint j of the DAG is folded by
+    // the OP_ROOT instruction that follows its node (weight apow[j]); the logUp constraints continue at index n_zeros.
     gl::Acc160 fa0 = gl::acc_zero(), fa1 = gl::acc_zero();
-    u32 ci = 0;
-    for (u32 j = 0; j < p.n_zeros; j++, ci++) {
-        u64 v = slots[p.zero_slots[j]];
-        gl::acc_mac(fa0, v, __ldg(p.apow + 2 * ci));
-        gl::acc_mac(fa1, v, __ldg(p.apow + 2 * ci + 1));
-    }
+    run_program<NSLOT>(p.prog, p.n_instr, slots, cx, [&](u32 j, u64 v) {
+        gl::acc_mac(fa0, v, __ldg(p.apow + 2 * j));
+        gl::acc_mac(fa1, v, __ldg(p.apow + 2 * j + 1));
+    });
+    u32 ci = p.n_zeros;
     // logUp constraint values (src/lookup.rs:167-208)
     const u64* s2c = cx.rows[2][0];
     const u64* s2n = cx.rows[2][1];
@@ -564,11 +608,14 @@ static msgpu_program* program_create(Ctx& c, const msgpu_graph_desc& g) {
     for (u32 j = 0; j < g.n_lookups; j++) pin_lk.push_back(g.lookup_mult[j]);
     for (u32 k = 0; k < n_args; k++) pin_lk.push_back(g.lookup_args[k]);
     pin_all = pin_lk;
-    for (u32 j = 0; j < g.n_zeros; j++) pin_all.push_back(g.zeros[j]);
+    std::vector<u32> roots(g.zeros, g.zeros + g.n_zeros);
     for (u32 p : pin_lk) MSG_REQUIRE(p < g.lookup_prefix_len, "program: lookup node outside the prefix");
-    Lowered full = lower(g, g.n_nodes, pin_all);
+    Lowered full = lower(g, g.n_nodes, pin_all, roots);
     Lowered prefix = lower(g, g.lookup_prefix_len, pin_lk);
     MSG_REQUIRE(full.n_slots <= 4096 && prefix.n_slots <= 4096, "program: circuit needs more than 4096 live values");
+    if (getenv("MSGPU_TIMELINE"))
+        fprintf(stderr, "[program] %u nodes, %u roots, %u lookups: full program %zu instructions / %u slots, lookup prefix %zu / %u\n", g.n_nodes,
+                g.n_zeros, g.n_lookups, full.code.size(), full.n_slots, prefix.code.size(), prefix.n_slots);
     auto* prog = new msgpu_program();
     prog->ctx = &c;
     try {
@@ -585,7 +632,7 @@ static msgpu_program* program_create(Ctx& c, const msgpu_graph_desc& g) {
         prog->d_full = upload_vec(c, prog, full.code);
         prog->d_prefix = upload_vec(c, prog, prefix.code);
         std::vector<u32> zs, mf, af, mp, ap, off;
-        for (u32 j = 0; j < g.n_zeros; j++) zs.push_back(full.slot_of[g.zeros[j]]);
+        zs.assign(std::max<u32>(g.n_zeros, 1), 0);  // (the roots are folded by OP_ROOT instructions; kept for the layout)
         for (u32 j = 0; j < g.n_lookups; j++) { mf.push_back(full.slot_of[g.lookup_mult[j]]); mp.push_back(prefix.slot_of[g.lookup_mult[j]]); }
         for (u32 k = 0; k < n_args; k++) { af.push_back(full.slot_of[g.lookup_args[k]]); ap.push_back(prefix.slot_of[g.lookup_args[k]]); }
         for (u32 j = 0; j <= g.n_lookups; j++) off.push_back(g.n_lookups ? g.lookup_arg_off[j] : 0);
