@@ -51,3 +51,16 @@ def test_product_does_not_reference_oracle():
                 if re.search(r"oracle/|liboracle|orc_", t):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_rust_bindings_cover_the_header():
+    """integration/msgpu-sys/src/lib.rs is generated from include/msgpu.h (tools/gen_rust_bindings.py): it must be up to date
+    and declare every function the header declares (there is no cargo here to compile it)."""
+    import subprocess
+    import sys
+    assert subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_rust_bindings.py"), "--check"]).returncode == 0, \
+        "run python tools/gen_rust_bindings.py"
+    src = open(os.path.join(ROOT, "integration", "msgpu-sys", "src", "lib.rs")).read()
+    for s in header_symbols():
+        assert re.search(r"pub fn %s\(" % s, src), "Rust binding misses %s" % s
+    assert "pub pre_width: u32" in src and "pub main_width: u32" in src and "pub stage2_width: u32" in src
