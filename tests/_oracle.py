@@ -72,6 +72,7 @@ def lib():
         "orc_pcs_example_prove": (C.c_int, [C.POINTER(C.c_void_p), u64p, u64p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
                                             C.c_uint32, C.c_uint32, C.c_uint32, u8p, u64p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
         "orc_gen_challenger_refs": (None, [u64p]),
+        "orc_check_lowering": (C.c_uint64, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, u32p]),
         "orc_pcs_example_verify": (C.c_int, [u8p, u64p, u64p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                              C.c_uint32, C.c_uint32, u8p, C.c_uint64]),
     }
