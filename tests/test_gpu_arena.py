@@ -119,3 +119,57 @@ def test_local_commit_plus_tree_equals_commit(gpu):
     pd.free()
     for d in dev:
         ctx.free(d)
+
+
+def _upload_begin(ms, ctx, mats):
+    n = len(mats)
+    ptrs = (C.c_void_p * n)(*[m.ctypes.data for m in mats])
+    hs = (C.c_uint64 * n)(*[m.shape[0] for m in mats])
+    ws = (C.c_uint64 * n)(*[m.shape[1] for m in mats])
+    up = C.c_void_p()
+    rc = ctx.L.msgpu_upload_begin(ctx.h, ptrs, hs, ws, n, C.byref(up))
+    return rc, up
+
+
+def test_pipelined_commit_equals_commit(gpu):
+    """msgpu_upload_begin + msgpu_commit_upload (uploads on the copy stream) == msgpu_commit, and the kept device inputs are the
+    natural-order matrices"""
+    ms, ctx = gpu
+    rng = np.random.default_rng(21)
+    mats = [ctx.pinned_copy(rng.integers(0, ms.P, size=s, dtype=np.uint64)) for s in [(256, 1), (4096, 14), (1024, 3), (4096, 2)]]
+    want_root, want_pd = ms.GpuPcs(ctx, 1).commit(mats)
+    rc, up = _upload_begin(ms, ctx, mats)
+    assert rc == 0
+    kept = (C.c_void_p * len(mats))()
+    pd, root = C.c_void_p(), np.zeros(32, dtype=np.uint8)
+    assert ctx.L.msgpu_commit_upload(up, 1, 1, kept, 0, C.byref(pd), root.ctypes.data_as(C.c_void_p)) == 0
+    assert bytes(root) == bytes(want_root)
+    for k, m in enumerate(mats):
+        assert np.array_equal(ctx.download(kept[k], m.shape), m)
+        ctx.free(kept[k])
+    ctx.L.msgpu_pdata_free(pd)
+    want_pd.free()
+
+
+def test_pipelined_commit_rejects_non_canonical_values(gpu):
+    ms, ctx = gpu
+    bad = np.zeros((64, 2), dtype=np.uint64)
+    bad[17, 1] = ms.P            # = 0 mod p, but not the canonical representative
+    rc, up = _upload_begin(ms, ctx, [np.ones((64, 3), dtype=np.uint64), bad])
+    assert rc == 0
+    pd, root = C.c_void_p(), np.zeros(32, dtype=np.uint8)
+    assert ctx.L.msgpu_commit_upload(up, 1, 1, None, 0, C.byref(pd), root.ctypes.data_as(C.c_void_p)) != 0
+    assert b"canonical" in ctx.L.msgpu_last_error()
+    # the handle was consumed and its buffers released: the arena serves the same sizes again
+    rc, up = _upload_begin(ms, ctx, [np.ones((64, 3), dtype=np.uint64)])
+    assert rc == 0
+    ctx.L.msgpu_upload_free(up)   # abandoning an upload is allowed
+
+
+def test_upload_begin_argument_checks(gpu):
+    ms, ctx = gpu
+    up = C.c_void_p()
+    assert ctx.L.msgpu_upload_begin(ctx.h, None, None, None, 0, C.byref(up)) != 0
+    m = np.ones((48, 2), dtype=np.uint64)  # height not a power of two
+    rc, up = _upload_begin(ms, ctx, [m])
+    assert rc != 0
