@@ -114,10 +114,11 @@ __global__ void __launch_bounds__(kLeafThreads) k_hash_rows_staged(const __grid_
 
 // Wide rows (more than ~95 columns in total): staging whole rows would leave one warp per CTA hashing (32 rows x 2 KB at 256
 // columns), far too few to keep the ALU pipe busy. Here a CTA of 128 threads owns 128 rows and walks the row message in
-// segments of kSegWords words (4 BLAKE3 blocks): the segment of all 128 rows is staged with coalesced loads, every thread
-// compresses its row's 4 blocks and carries the chunk state (cv, chunk counter, subtree stack) in registers / local memory
-// to the next segment. 33 KB of shared memory per CTA, 6 CTAs = 24 hashing warps per SM.
-constexpr int kSegWords = 64;
+// segments of kSegWords words (2 BLAKE3 blocks): the segment of all 128 rows is staged with coalesced loads, every thread
+// compresses its row's 2 blocks and carries the chunk state (cv, chunk counter, subtree stack) in registers / local memory
+// to the next segment. 17 KB of shared memory per CTA: 8 CTAs = 32 hashing warps per SM (64-word segments: 24 warps,
+// 6.7 ms instead of 5.4 ms for 2^22 rows of 256 columns; 16-word segments: no further gain).
+constexpr int kSegWords = 32;
 __global__ void __launch_bounds__(kLeafThreads) k_hash_rows_stream(const __grid_constant__ LeafList mats, u32 nmats, u64 height, u32 total_words,
                                                                    u32* out) {
     __shared__ u32 tile[kLeafThreads][kSegWords + 1];
