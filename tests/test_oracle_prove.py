@@ -145,3 +145,18 @@ def test_quotient_value_tamper_is_ood_mismatch(oracle):
         return  # the prover noticed the quotient is not a polynomial (final FRI polynomial degree check)
     assert S.verify(claims, proof) in ("OodEvaluationMismatch", "InvalidOpeningArgument")
     S.close()
+
+
+def test_multi_circuit_system_balances_and_verifies(oracle):
+    """BASELINE configs[3] shape: K U32-add circuits of different heights sharing the byte table; the byte multiplicities of
+    all circuits are summed (multi_workload), so the lookup accumulator closes and the restated verifier accepts."""
+    import multi_stark_b200.system as mss
+    traces, claims = mss.multi_workload([6, 4, 5])
+    assert [t.shape for t in traces] == [(256, 1), (64, 14), (16, 14), (32, 14)] and claims.shape == (64 + 16 + 32, 4)
+    assert int(traces[0].sum()) == 12 * claims.shape[0]      # 12 byte lookups per addition
+    S = orc.OracleSystem(oracle, "multi:3", log_blowup=1, num_queries=8)
+    proof, _ = S.prove(traces, list(claims))
+    assert S.verify(list(claims), proof) == "Ok"
+    # dropping one circuit's claims unbalances the accumulator
+    assert S.verify(list(claims[:64]), proof) != "Ok"
+    S.close()
