@@ -154,6 +154,7 @@ HOST_SIGNATURES = {
     "msh_prover_preprocessed_commit": (C.c_int, [C.c_void_p, C.c_void_p]),
     "msh_prove": (C.c_int, [C.c_void_p, c_vpp, c_u64p, c_u64p, c_u64p, C.c_uint64, C.c_uint64, c_vpp, c_u64p, C.POINTER(C.c_double)]),
     "msh_bytes_free": (None, [C.c_void_p]),
+    "msh_last_transcript": (C.c_uint64, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]),
     "msh_challenger_create": (C.c_void_p, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "msh_challenger_free": (None, [C.c_void_p]),
     "msh_challenger_observe_digest": (None, [C.c_void_p, C.c_void_p]),

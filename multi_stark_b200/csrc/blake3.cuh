@@ -98,12 +98,13 @@ __device__ __forceinline__ void set_iv(u32 cv[8]) {
 }
 
 // out = BLAKE3(l || r): one 64-byte block, CHUNK_START | CHUNK_END | ROOT.
+template <bool kFmaAdds = false>
 __device__ __forceinline__ void hash_pair(const u32 l[8], const u32 r[8], u32 out[8]) {
     u32 m[16];
 #pragma unroll
     for (int i = 0; i < 8; i++) { m[i] = l[i]; m[8 + i] = r[i]; }
     set_iv(out);
-    compress<false>(out, m, 0, 0, 64, CHUNK_START | CHUNK_END | ROOT);
+    compress<kFmaAdds>(out, m, 0, 0, 64, CHUNK_START | CHUNK_END | ROOT);
 }
 
 }  // namespace b3

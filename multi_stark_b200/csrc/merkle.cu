@@ -273,15 +273,20 @@ __global__ void __launch_bounds__(256) k_merkle_subtree(SubtreeParams p) {
         const uint4* src = l == 0 ? p.in + cta * chunk * 2 : ((l & 1) ? bufA : bufB);
         uint4* dst = (l & 1) ? bufB : bufA;
         const u64 gbase = cta * nodes;
+        // Levels that keep every thread busy are throughput-bound on the ALU pipe: there the additions go to the FMA pipe as
+        // IMAD (blake3.cuh); the upper levels are a latency chain and keep the plain form with the shorter dependency chain.
+        const bool wide = nodes >= blockDim.x;
         for (u32 i = threadIdx.x; i < nodes; i += blockDim.x) {
             u32 a[8], b[8], d[8];
             ld_digest(src + 4 * i, a);
             ld_digest(src + 4 * i + 2, b);
-            b3::hash_pair(a, b, d);
+            if (wide) b3::hash_pair<true>(a, b, d);
+            else b3::hash_pair<false>(a, b, d);
             if (p.inject[l]) {
                 u32 x[8], d2[8];
                 ld_digest(p.inject[l] + 2 * (gbase + i), x);
-                b3::hash_pair(d, x, d2);
+                if (wide) b3::hash_pair<true>(d, x, d2);
+                else b3::hash_pair<false>(d, x, d2);
 #pragma unroll
                 for (int k = 0; k < 8; k++) d[k] = d2[k];
             }

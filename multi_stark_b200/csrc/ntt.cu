@@ -38,7 +38,22 @@ namespace msg {
 constexpr int kXt = 4;            // tile columns (64-byte row segments); two 512-thread CTAs per SM overlap their load /
                                   // compute / store phases, which one 1024-thread CTA with 16 columns cannot
 constexpr int kLogXt = 2;
-constexpr int kPitch = kXt + 1;   // u64 per tile row (+1 pad)
+// Tile rows are kXt u64 (8 words) wide with NO padding; the row index is XOR-swizzled so that the four tile rows a
+// half-warp touches in one 64-bit access (4 thread rows x kXt columns) always land in four different 8-word bank groups,
+// whichever round is running: rounds address rows that differ in one PAIR of index bits (0-1 for consecutive rows, 2-3 for
+// the stride-4 radix-4 round, 4-5 for the stride-16 radix-16 round, ...), and the swizzle folds every pair onto bits 0-1.
+// (The former "+1" pad, 10 words per row, gave a 4-way conflict in the stride-16 round: 16 * 10 words = 0 mod 32.)
+// The swizzle term sw2() is XOR-linear, and a round addresses rows row0 | mm (mm = slot << S0, a compile-time constant after
+// unrolling, disjoint from row0's bits), so swz(row0 | mm) = ((row0 ^ sw2(row0)) ^ x) + (mm & ~3) with x = (mm & 3) ^ sw2(mm) a
+// compile-time constant in 0..3: four base addresses per item, every access a base + immediate offset.
+__host__ __device__ constexpr u32 sw2(u32 row) { return ((row >> 2) ^ (row >> 4) ^ (row >> 6) ^ (row >> 8)) & 3u; }
+__device__ __forceinline__ u32 swz(u32 row) { return row ^ sw2(row); }
+// element index of tile row (row0 | mm), column q
+__device__ __forceinline__ u32 tile_at(u32 row0, u32 mm, u32 q) {
+    const u32 base = row0 ^ sw2(row0);
+    const u32 x = (mm & 3u) ^ sw2(mm);
+    return ((base ^ x) * kXt + q) + (mm & ~3u) * kXt;
+}
 constexpr int kMaxLogT = 10;      // tile points
 constexpr int kTwLog = 10;        // w_1024 table, full period
 
@@ -131,7 +146,8 @@ __host__ __device__ constexpr int round_bits(int tb, int k) {
 
 // One round of RB bits at bit offset S0 of a TB-bit tile. Slot m of item (blk, off) is tile row
 // (blk << (S0 + RB)) + off + (m << S0). DIF: DFT then slot m *= w^{off * rev(m)}; DIT: the mirror image.
-// ld(row) / st(row, value) move one element of this thread's column (registers <-> global or shared memory).
+// ld(row0, mm) / st(row0, mm, value) move the element of tile row row0 | mm of this thread's column (registers <-> global or
+// shared memory); mm = m << S0 is a compile-time constant after unrolling.
 template <int TB, int RB, int S0, bool INV, bool DIT, class Ld, class St>
 __device__ __forceinline__ void tile_round(const u64* __restrict__ tw, u32 trow, u32 nrows_thr, Ld ld, St st) {
     constexpr int R = 1 << RB;
@@ -141,7 +157,7 @@ __device__ __forceinline__ void tile_round(const u64* __restrict__ tw, u32 trow,
         const u32 row0 = (blk << (S0 + RB)) + off;
         u64 v[R];
 #pragma unroll
-        for (int m = 0; m < R; m++) v[m] = ld(row0 + ((u32)m << S0));
+        for (int m = 0; m < R; m++) v[m] = ld(row0, (u32)m << S0);
         if (DIT) {
             if (S0 > 0) {
 #pragma unroll
@@ -158,7 +174,7 @@ __device__ __forceinline__ void tile_round(const u64* __restrict__ tw, u32 trow,
             }
         }
 #pragma unroll
-        for (int m = 0; m < R; m++) st(row0 + ((u32)m << S0), v[m]);
+        for (int m = 0; m < R; m++) st(row0, (u32)m << S0, v[m]);
     }
 }
 
@@ -167,8 +183,8 @@ __device__ __forceinline__ void tile_round(const u64* __restrict__ tw, u32 trow,
 template <int TB, bool INV, bool DIT, class GLd, class GSt>
 __device__ __forceinline__ void tile_pass(u64* tile, const u64* __restrict__ tw, u32 q, u32 trow, u32 nrows_thr, GLd gld, GSt gst) {
     constexpr int B0 = round_bits(TB, 0), B1 = round_bits(TB, 1), B2 = round_bits(TB, 2);
-    auto sld = [&](u32 row) { return tile[(size_t)row * kPitch + q]; };
-    auto sst = [&](u32 row, u64 v) { tile[(size_t)row * kPitch + q] = v; };
+    auto sld = [&](u32 row0, u32 mm) { return tile[tile_at(row0, mm, q)]; };
+    auto sst = [&](u32 row0, u32 mm, u64 v) { tile[tile_at(row0, mm, q)] = v; };
     if constexpr (!DIT) {
         // round 0 works on the top bits
         if constexpr (B1 == 0) {
@@ -234,9 +250,10 @@ __global__ void __launch_bounds__(64 * kXt, 1024 / (64 * kXt)) k_ntt_strided(Str
     u64* __restrict__ dst = p.dst + col;
     const u64 I = p.I;
     const u64* __restrict__ twp = p.twp ? p.twp + (size_t)b * T : nullptr;
-    auto gld = [&](u32 row) -> u64 { return valid ? src[(u64)row * I] : 0ull; };
-    auto gst = [&](u32 row, u64 v) {
+    auto gld = [&](u32 row0, u32 mm) -> u64 { return valid ? src[(u64)(row0 + mm) * I] : 0ull; };
+    auto gst = [&](u32 row0, u32 mm, u64 v) {
         if (!valid) return;
+        const u32 row = row0 + mm;
         if (twp) v = mul(v, __ldg(twp + row));
         dst[(u64)row * I] = v;
     };
@@ -278,13 +295,74 @@ __global__ void __launch_bounds__(64 * kXt, 1024 / (64 * kXt)) k_ntt_block(Block
     const u64* __restrict__ twb = p.twb ? p.twb + (size_t)b * T : nullptr;
     u64* __restrict__ dst = p.dst + (u64)blockIdx.y * p.out_block_elems + b * w + c;
     const u64 dstride = p.S * w;
-    auto gld = [&](u32 t) -> u64 { return valid ? mul(src[(u64)t * w], __ldg(sc + t)) : 0ull; };
-    auto gst = [&](u32 s, u64 v) {
+    auto gld = [&](u32 t0, u32 mm) -> u64 { const u32 t = t0 + mm; return valid ? mul(src[(u64)t * w], __ldg(sc + t)) : 0ull; };
+    auto gst = [&](u32 s0, u32 mm, u64 v) {
         if (!valid) return;
+        const u32 s = s0 + mm;
         if (twb) v = mul(v, __ldg(twb + s));
         dst[(u64)gl::rev_bits(s, TB) * dstride] = v;
     };
     tile_pass<TB, false, true>(smem, p.tw, q, trow, nrows_thr, gld, gst);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused middle pass of the coset LDE: LAST inverse pass + FIRST forward pass of every coset in one kernel.
+// The last inverse pass (bits [0, tb), contiguous blocks of T rows) leaves tile position t holding the coefficient
+// j = rev_T(t) * S + rev(blk) -- exactly the tile the block pass of each coset starts from. So a CTA runs the inverse
+// DIF tile once, keeps the coefficients in a shared-memory tile A, and then for every coset beta scales them by
+// shift_beta^j / n, runs the DIT tile in a second (work) tile and scatters the row segments to output block beta.
+// The coefficients cross HBM never: one read of n*w for all B cosets instead of one write + B reads, and the
+// unnormalised inverse's last pass costs no launch of its own.
+// ------------------------------------------------------------------------------------------------
+struct MidParams {
+    const u64* src;     // evaluations (log_n <= tb) or the output of the earlier inverse passes; natural rows per T-block
+    u64* dst;
+    const u64* tw_inv;  // w_1024^{-i}
+    const u64* tw_fwd;  // w_1024^{i}
+    const u64* scale;   // [beta][b][t] = (shift_beta)^{rev_T(t)*S + b} / n
+    const u64* twb;     // [b][s] = w_n^{b*s}, or null when S == 1
+    u64 S;              // n / T
+    u64 out_block_elems;  // n * w
+    u32 log_n, w, n_cosets;
+};
+
+template <int TB>
+__global__ void __launch_bounds__(64 * kXt, 3) k_lde_mid(MidParams p) {
+    extern __shared__ u64 smem[];
+    constexpr u32 T = 1u << TB;
+    u64* A = smem;                 // coefficients of this tile (canonical), read by every coset
+    u64* W = smem + T * kXt;       // work tile of the forward rounds (unused when the tile is a single round)
+    const u32 q = threadIdx.x & (kXt - 1), trow = threadIdx.x >> kLogXt, nrows_thr = blockDim.x >> kLogXt;
+    const u32 hi_bits = p.log_n - TB;
+    const u32 w = p.w;
+    const u64 v = (u64)blockIdx.x * kXt + q;   // virtual column b * w + c
+    const bool valid = v < p.S * w;
+    const u64 b = valid ? v / w : 0;
+    const u32 c = valid ? (u32)(v % w) : 0;
+    const u64 blk = gl::rev_bits((u32)b, hi_bits);
+    const u64* __restrict__ src = p.src + blk * T * w + c;
+    // ---- inverse DIF tile: natural rows in, coefficient rev_T(t) at tile row t, left in A ----
+    {
+        auto gld = [&](u32 row0, u32 mm) -> u64 { return valid ? src[(u64)(row0 + mm) * w] : 0ull; };
+        auto ast = [&](u32 t0, u32 mm, u64 x) { A[tile_at(t0, mm, q)] = x; };
+        tile_pass<TB, true, false>(A, p.tw_inv, q, trow, nrows_thr, gld, ast);
+    }
+    __syncthreads();
+    const u64* __restrict__ twb = p.twb ? p.twb + (size_t)b * T : nullptr;
+    const u64 dstride = p.S * w;
+    for (u32 beta = 0; beta < p.n_cosets; beta++) {
+        const u64* __restrict__ sc = p.scale + ((size_t)beta * p.S + b) * T;
+        u64* __restrict__ dst = p.dst + (u64)beta * p.out_block_elems + b * w + c;
+        auto ald = [&](u32 t0, u32 mm) -> u64 { return mul(A[tile_at(t0, mm, q)], __ldg(sc + t0 + mm)); };
+        auto gst = [&](u32 s0, u32 mm, u64 x) {
+            if (!valid) return;
+            const u32 s = s0 + mm;
+            if (twb) x = mul(x, __ldg(twb + s));
+            dst[(u64)gl::rev_bits(s, TB) * dstride] = x;
+        };
+        tile_pass<TB, false, true>(W, p.tw_fwd, q, trow, nrows_thr, ald, gst);
+        __syncthreads();   // the next coset's first round overwrites W
+    }
 }
 
 // dst[beta][j][c] = src[j][c] * tab[beta](j)
@@ -347,7 +425,7 @@ static std::vector<u32> plan_passes(u32 log_n) {
     return tb;
 }
 
-static size_t tile_smem(u32 log_t) { return log_t <= 4 ? 0 : (size_t)(1u << log_t) * kPitch * sizeof(u64); }
+static size_t tile_smem(u32 log_t) { return log_t <= 4 ? 0 : (size_t)(1u << log_t) * kXt * sizeof(u64); }
 static u32 tile_threads(u32 log_t) {
     u32 rows = log_t >= 4 ? (1u << (log_t - 4)) : 1u;  // one thread row per radix-16 item
     u32 t = rows * kXt;
@@ -370,6 +448,13 @@ template <int TB>
 static void launch_block_tb(const BlockParams& p, dim3 grid, cudaStream_t st) {
     ensure_max_smem(k_ntt_block<TB>, (int)tile_smem(kMaxLogT));
     k_ntt_block<TB><<<grid, tile_threads(TB), tile_smem(TB), st>>>(p);
+}
+
+static size_t mid_smem(u32 log_t) { return (size_t)(1u << log_t) * kXt * sizeof(u64) * (log_t <= 4 ? 1 : 2); }
+template <int TB>
+static void launch_mid_tb(const MidParams& p, unsigned blocks, cudaStream_t st) {
+    ensure_max_smem(k_lde_mid<TB>, (int)mid_smem(kMaxLogT));
+    k_lde_mid<TB><<<blocks, tile_threads(TB), mid_smem(TB), st>>>(p);
 }
 
 #define MSG_TB_SWITCH(tb, CALL)                               \
@@ -486,11 +571,42 @@ void ntt_coset_lde(Ctx& c, const u64* src, u64* dst, u64* tmp, u64 n, u64 w, u32
             MSG_CUDA(cudaMemcpyAsync(dst + beta * w, src, w * 8, cudaMemcpyDeviceToDevice, c.stream));
         return;
     }
+    auto plan = plan_passes(log_n);
+    u32 tb = plan.back();
+    static const bool fused = !(getenv("MSGPU_LDE_UNFUSED") && getenv("MSGPU_LDE_UNFUSED")[0] == '1');
+    if (fused) {
+        // 1. inverse passes over the upper bits (unnormalised, natural -> bit-reversed in place); the last one is fused below
+        const u64* cur = src;
+        u32 hi = log_n;
+        for (size_t i = 0; i + 1 < plan.size(); i++) {
+            launch_strided(c, cur, tmp, log_n, 1, w, hi - plan[i], plan[i], true);
+            cur = tmp;
+            hi -= plan[i];
+        }
+        // 2. last inverse pass + first forward pass of every coset
+        MidParams p{};
+        p.src = cur;
+        p.dst = dst;
+        p.tw_inv = c.tw_full[1];
+        p.tw_fwd = c.tw_full[0];
+        p.scale = scale_table(c, log_n, tb, added_bits, shift);
+        p.log_n = log_n;
+        p.w = (u32)w;
+        p.n_cosets = 1u << added_bits;
+        p.S = n >> tb;
+        p.out_block_elems = n * w;
+        p.twb = p.S > 1 ? twb_table(c, log_n, tb) : nullptr;
+        u64 blocks = (p.S * w + kXt - 1) / kXt;
+        MSG_REQUIRE(blocks < (1ull << 31), "lde: grid too large");
+        {
+            KLaunch kl(c, "k_lde_mid");
+            MSG_TB_SWITCH(tb, launch_mid_tb<TBV>(p, (unsigned)blocks, c.stream));
+        }
+        MSG_CUDA(cudaGetLastError());
+    } else {
     // 1. inverse transform (unnormalised): coefficients in bit-reversed order
     ntt_dft_bitrev(c, src, tmp, n, w, true);
     // 2. first forward pass per coset from the bit-reversed coefficients
-    auto plan = plan_passes(log_n);
-    u32 tb = plan.back();
     BlockParams p{};
     p.src = tmp;
     p.dst = dst;
@@ -509,6 +625,7 @@ void ntt_coset_lde(Ctx& c, const u64* src, u64* dst, u64* tmp, u64 n, u64 w, u32
         MSG_TB_SWITCH(tb, launch_block_tb<TBV>(p, grid, c.stream));
     }
     MSG_CUDA(cudaGetLastError());
+    }
     // 3. remaining forward passes: every block rev_T(k1) of S rows is an independent size-S DFT
     u32 log_s = log_n - tb;
     if (log_s > 0) {

@@ -19,6 +19,7 @@ struct msh_system {
 };
 
 static thread_local std::string g_err;
+static thread_local TranscriptTrace g_trace;  // of the last msh_prove on this thread
 
 extern "C" {
 
@@ -166,6 +167,7 @@ int msh_prove(msh_prover* p, const uint64_t* const* traces, const uint64_t* heig
         cl.n = (size_t)n_claims;
         ProveTimings tm;
         Proof proof = p->prover->prove(cl, views, &tm);
+        g_trace = tm.trace;
         std::vector<u8> bytes = proof_to_bytes(proof);
         *proof_out = (uint8_t*)malloc(bytes.size());
         memcpy(*proof_out, bytes.data(), bytes.size());
@@ -186,6 +188,17 @@ int msh_prove(msh_prover* p, const uint64_t* const* traces, const uint64_t* heig
     }
 }
 void msh_bytes_free(uint8_t* b) { free(b); }
+// Test hook: the challenges of the last msh_prove on this thread (beta, gamma, alpha, zeta, alpha_pcs, FRI betas; 2 u64 each)
+// and its query indices. Returns the number of challenges; writes at most cap of them / cap_idx indices.
+uint64_t msh_last_transcript(uint64_t* challenges2, uint64_t cap, uint64_t* indices, uint64_t cap_idx, uint64_t* n_indices) {
+    for (size_t i = 0; i < g_trace.challenges.size() && i < cap; i++) {
+        challenges2[2 * i] = g_trace.challenges[i].c[0].v;
+        challenges2[2 * i + 1] = g_trace.challenges[i].c[1].v;
+    }
+    for (size_t i = 0; i < g_trace.query_indices.size() && i < cap_idx; i++) indices[i] = g_trace.query_indices[i];
+    if (n_indices) *n_indices = g_trace.query_indices.size();
+    return g_trace.challenges.size();
+}
 
 // ---- standalone PCS use (examples/pcs_example.rs): the transcript object and Pcs::open ------------------------------
 struct msh_challenger {

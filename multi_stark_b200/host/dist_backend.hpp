@@ -316,7 +316,7 @@ class DistOpenDevice : public OpenDevice {
                 proof.commit_phase_commits.push_back(d);
                 if (!ch.check_witness(pow_bits, w)) throw DistError("fri: the owner's proof-of-work witness does not verify");
                 proof.commit_pow_witnesses.push_back(w);
-                (void)ch.sample_ext();  // beta
+                betas.push_back(ch.sample_ext());
             }
             cur_len_ = final_len;
         }

@@ -38,8 +38,16 @@ struct OpenRound {
     std::vector<std::vector<Fp2>> points;  // [matrix][point]
 };
 
+// The challenges a proof's transcript produced, in order, for the tests that re-derive them with an independent restatement
+// of the challenger (tests/_pyverifier.py): beta, gamma, alpha, zeta (prover.hpp), then alpha_pcs and the FRI betas.
+struct TranscriptTrace {
+    std::vector<Fp2> challenges;
+    std::vector<u64> query_indices;
+};
+
 struct OpenDevice {
     virtual ~OpenDevice() {}
+    std::vector<Fp2> betas;  // the FRI folding challenges, recorded by commit_phase
     // [round][matrix][point][column]
     virtual std::vector<OpenedValuesForRound> evaluate() = 0;
     virtual void reduce(Fp2 alpha, unsigned& log_max_height) = 0;
@@ -57,6 +65,7 @@ struct OpenDevice {
             proof.commit_phase_commits.push_back(commit);
             proof.commit_pow_witnesses.push_back(ch.grind(pow_bits));
             Fp2 beta = ch.sample_ext();
+            betas.push_back(beta);
             fold(beta);
         }
     }
@@ -102,7 +111,7 @@ inline std::vector<Fp2> idft_ext(const std::vector<Fp2>& evals) {
 // TwoAdicFriPcs::open. `rounds_meta[r]` = log2 of the tallest LDE of round r.
 inline void pcs_open(OpenDevice& dev, const std::vector<OpenRound>& rounds, const CommitmentParameters& cp, const FriParameters& fp,
                      Challenger& ch, std::vector<OpenedValuesForRound>& opened, FriProof& proof,
-                     std::map<std::string, double>* tm = nullptr) {
+                     std::map<std::string, double>* tm = nullptr, TranscriptTrace* trace = nullptr) {
     auto t0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* name) {
         auto t1 = std::chrono::steady_clock::now();
@@ -125,6 +134,10 @@ inline void pcs_open(OpenDevice& dev, const std::vector<OpenRound>& rounds, cons
     proof = FriProof();
     const size_t stop_len = (size_t(1) << cp.log_blowup) << fp.log_final_poly_len;
     dev.commit_phase(ch, stop_len, fp.commit_proof_of_work_bits, proof);
+    if (trace) {
+        trace->challenges.push_back(alpha);
+        trace->challenges.insert(trace->challenges.end(), dev.betas.begin(), dev.betas.end());
+    }
     lap("fri/commit_phase");
     // final polynomial: undo the bit reversal, inverse DFT, keep final_poly_len coefficients
     std::vector<Fp2> folded = dev.read_current();
@@ -146,6 +159,7 @@ inline void pcs_open(OpenDevice& dev, const std::vector<OpenRound>& rounds, cons
     // query phase: sample all indices (no observation happens in between), then open in batches
     std::vector<size_t> indices(fp.num_queries);
     for (auto& i : indices) i = ch.sample_bits(log_max_height);
+    if (trace) trace->query_indices.assign(indices.begin(), indices.end());
     proof.query_proofs.assign(fp.num_queries, QueryProof());
     std::vector<unsigned> round_shifts;
     for (size_t r = 0; r < rounds.size(); r++) round_shifts.push_back(log_max_height - log2_exact(rounds[r].data->max_height()));

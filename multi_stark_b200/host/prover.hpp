@@ -53,6 +53,7 @@ struct ProverKey {  // src/system.rs:104-107
 
 struct ProveTimings {
     std::map<std::string, double> ms;
+    TranscriptTrace trace;  // beta, gamma, alpha, zeta, alpha_pcs, FRI betas; query indices
 };
 
 class Prover {
@@ -164,6 +165,7 @@ class Prover {
 
         // stark/fri_open
         Fp2 zeta = ch.sample_ext();
+        if (tm) tm->trace.challenges = {beta, gamma, alpha, zeta};
         std::vector<OpenRound> rounds(3);
         rounds[0].data = s1.get();
         rounds[1].data = s2.get();
@@ -190,7 +192,8 @@ class Prover {
         }
         std::unique_ptr<OpenDevice> dev = be_.open_begin(rounds);
         std::vector<OpenedValuesForRound> opened;
-        pcs_open(*dev, rounds, shape_.commitment, shape_.fri, ch, opened, proof.opening_proof, tm ? &tm->ms : nullptr);
+        pcs_open(*dev, rounds, shape_.commitment, shape_.fri, ch, opened, proof.opening_proof, tm ? &tm->ms : nullptr,
+                 tm ? &tm->trace : nullptr);
         dev.reset();
         proof.stage_1_opened_values = std::move(opened[0]);
         proof.stage_2_opened_values = std::move(opened[1]);

@@ -241,6 +241,16 @@ class Prover:
         self.last_stage_ms = dict(zip(STAGE_NAMES, ms))
         return data
 
+    def last_transcript(self):
+        """Test hook: (challenges [(c0, c1)...] = beta, gamma, alpha, zeta, alpha_pcs, FRI betas; query indices) of the last
+        prove() on this thread."""
+        ch = np.zeros(2 * 128, dtype=np.uint64)
+        idx = np.zeros(4096, dtype=np.uint64)
+        nidx = np.zeros(1, dtype=np.uint64)
+        n = int(self.H.msh_last_transcript(ch.ctypes.data_as(C.c_void_p), 128, idx.ctypes.data_as(C.c_void_p), 4096,
+                                           nidx.ctypes.data_as(C.c_void_p)))
+        return [(int(ch[2 * i]), int(ch[2 * i + 1])) for i in range(n)], [int(v) for v in idx[:int(nidx[0])]]
+
     def prove_precommitted(self, stage1_pdata, heights, claims=None):
         """prove() whose stage-1 commitment was made elsewhere (`msgpu_pdata_from_parts`: one wide matrix committed by column
         blocks over several GPUs). `stage1_pdata`: raw msgpu_pdata handle, adopted; heights[i]: trace rows of circuit i. Only

@@ -15,6 +15,7 @@ static std::vector<std::vector<Fp>> read_claims(const u64* claims, const u64* of
 }
 
 static thread_local std::string g_orc_err;
+static thread_local TranscriptTrace g_orc_trace;  // of the last orc_prove on this thread
 
 extern "C" {
 
@@ -37,6 +38,7 @@ int orc_prove(void* s, const u64* const* traces, const u64* heights, const u64* 
         for (auto& m : mats) ptrs.push_back(&m);
         ProveTimings tm;
         Proof proof = sys.get_prover().prove(read_claims(claims, offsets, n_claims), ptrs, &tm);
+        g_orc_trace = tm.trace;
         std::vector<u8> bytes = proof_to_bytes(proof);
         *proof_out = (u8*)malloc(bytes.size());
         memcpy(*proof_out, bytes.data(), bytes.size());
@@ -54,6 +56,16 @@ int orc_prove(void* s, const u64* const* traces, const u64* heights, const u64* 
     }
 }
 void orc_bytes_free(u8* p) { free(p); }
+// the challenges / query indices of the last orc_prove on this thread (same layout as msh_last_transcript)
+u64 orc_last_transcript(u64* challenges2, u64 cap, u64* indices, u64 cap_idx, u64* n_indices) {
+    for (size_t i = 0; i < g_orc_trace.challenges.size() && i < cap; i++) {
+        challenges2[2 * i] = g_orc_trace.challenges[i].c[0].v;
+        challenges2[2 * i + 1] = g_orc_trace.challenges[i].c[1].v;
+    }
+    for (size_t i = 0; i < g_orc_trace.query_indices.size() && i < cap_idx; i++) indices[i] = g_orc_trace.query_indices[i];
+    if (n_indices) *n_indices = g_orc_trace.query_indices.size();
+    return g_orc_trace.challenges.size();
+}
 
 // the preprocessed commitment (verifier key); returns 0 if the system has no preprocessed trace
 int orc_preprocessed_commit(void* s, u8* out32) {

@@ -67,6 +67,7 @@ def lib():
         "orc_prove": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), u64p, u64p, u64p, C.c_uint64, C.POINTER(C.c_void_p),
                                 C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
         "orc_bytes_free": (None, [C.c_void_p]),
+        "orc_last_transcript": (C.c_uint64, [u64p, C.c_uint64, u64p, C.c_uint64, u64p]),
         "orc_preprocessed_commit": (C.c_int, [C.c_void_p, u8p]),
         "orc_verify": (C.c_int, [C.c_void_p, u64p, u64p, C.c_uint64, u8p, C.c_uint64]),
         "orc_pcs_example_prove": (C.c_int, [C.POINTER(C.c_void_p), u64p, u64p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
@@ -197,6 +198,14 @@ class OracleSystem:
         data = C.string_at(out.value, ln.value)
         self.L.orc_bytes_free(out)
         return data, list(ms)
+
+    def last_transcript(self):
+        """(challenges [(c0, c1)...] = beta, gamma, alpha, zeta, alpha_pcs, FRI betas; query indices) of the last prove()."""
+        ch = np.zeros(2 * 128, dtype=np.uint64)
+        idx = np.zeros(4096, dtype=np.uint64)
+        nidx = np.zeros(1, dtype=np.uint64)
+        n = int(self.L.orc_last_transcript(ch, 128, idx, 4096, nidx))
+        return [(int(ch[2 * i]), int(ch[2 * i + 1])) for i in range(n)], [int(v) for v in idx[:int(nidx[0])]]
 
     def verify(self, claims, proof_bytes):
         flat, offs = flatten_claims(claims)
