@@ -299,6 +299,11 @@ int msgpu_blake3_hash(msgpu_ctx* ctx, const uint8_t* data, uint64_t len, uint8_t
 int msgpu_measure_int_peak(msgpu_ctx* ctx, double* out3);
 
 /* ---- test hooks --------------------------------------------------------------------------------- */
+/* The selector tables of the quotient kernel: `trace_domain.selectors_on_coset(quotient_domain)` (src/prover.rs:775; p3's
+ * UNNORMALISED Lagrange selectors, pinned in the reference by src/lookup.rs:697-756) at the points
+ * x_i = GENERATOR * w_{n q}^i, i < n * q, in natural order. HOST outputs of n * q values each. */
+int msgpu_selectors_on_coset(msgpu_ctx* ctx, uint32_t log_n, uint32_t log_q, uint64_t* is_first_row, uint64_t* is_last_row,
+                             uint64_t* inv_vanishing);
 /* raw 7-round BLAKE3 compression of a 16-word state and 16 message words (known-answer vector of
  * reference src/test_circuits/blake3.rs:2646-2746); host pointers */
 int msgpu_blake3_compress_raw(msgpu_ctx* ctx, const uint32_t* state16, const uint32_t* msg16, uint32_t* out16);

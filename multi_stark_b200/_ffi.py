@@ -94,6 +94,7 @@ SIGNATURES = {
     "msgpu_open_free": (None, [C.c_void_p]),
     "msgpu_measure_int_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "msgpu_blake3_compress_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "msgpu_selectors_on_coset": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 
@@ -137,6 +138,8 @@ _HOST = None
 HOST_SIGNATURES = {
     "msh_last_error": (C.c_char_p, []),
     "msh_system_create": (C.c_void_p, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "msh_system_create_from_graphs": (C.c_void_p, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                   C.c_uint32, C.c_uint32, C.c_uint32]),
     "msh_system_free": (None, [C.c_void_p]),
     "msh_system_num_circuits": (C.c_uint32, [C.c_void_p]),
     "msh_circuit_info": (None, [C.c_void_p, C.c_uint32, C.c_void_p]),

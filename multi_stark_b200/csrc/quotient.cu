@@ -957,4 +957,28 @@ int msgpu_shifted_quotient_slices(msgpu_ctx* h, const uint64_t* in, uint64_t nq,
     });
 }
 
+// Test hook: the selector tables the quotient kernel reads (`trace_domain.selectors_on_coset(quotient_domain)`,
+// src/prover.rs:775), in NATURAL order of the quotient coset: point i is x_i = GENERATOR * w_{nq}^i.
+int msgpu_selectors_on_coset(msgpu_ctx* h, uint32_t log_n, uint32_t log_q, uint64_t* is_first_row, uint64_t* is_last_row,
+                             uint64_t* inv_vanishing) {
+    return guard([&] {
+        Ctx& c = h->c;
+        MSG_REQUIRE(log_n + log_q <= msh::GL_TWO_ADICITY && is_first_row && is_last_row && inv_vanishing, "selectors: bad argument");
+        SelCache sc = selectors(c, log_n, log_q);
+        const u32 log_nq = log_n + log_q;
+        const u64 nq = 1ull << log_nq, q = 1ull << log_q;
+        std::vector<u64> first(nq), last(nq), izh(q);
+        MSG_CUDA(cudaMemcpyAsync(first.data(), sc.first, nq * 8, cudaMemcpyDeviceToHost, c.stream));
+        MSG_CUDA(cudaMemcpyAsync(last.data(), sc.last, nq * 8, cudaMemcpyDeviceToHost, c.stream));
+        MSG_CUDA(cudaMemcpyAsync(izh.data(), sc.inv_zh, q * 8, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+        for (u64 i = 0; i < nq; i++) {  // the tables are kept in stored (bit-reversed) order
+            u64 sidx = msh::reverse_bits_len(i, log_nq);
+            is_first_row[i] = first[sidx];
+            is_last_row[i] = last[sidx];
+            inv_vanishing[i] = izh[i & (q - 1)];
+        }
+    });
+}
+
 }  // extern "C"

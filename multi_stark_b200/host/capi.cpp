@@ -2,6 +2,7 @@
 // prover.hpp -- the prove() driver over the libmsgpu C ABI). Python (tests, bench.py) binds these with ctypes.
 #include "system.hpp"
 #include "program.hpp"
+#include "system_from_graphs.hpp"
 #include "gpu_backend.hpp"
 #include "dist_backend.hpp"
 #include <chrono>
@@ -38,6 +39,35 @@ msh_system* msh_system_create(const char* kind, uint32_t log_blowup, uint32_t lo
         fp.query_proof_of_work_bits = query_pow_bits;
         auto sys = std::make_unique<msh_system>();
         sys->shape = SystemShape::build(cp, fp, named_system_inputs(kind));
+        for (auto& c : sys->shape.circuits) {
+            auto d = std::make_unique<GraphDesc>();
+            d->build(c.graph, c.preprocessed_width, c.main_width, c.stage_2_width);
+            sys->descs.push_back(std::move(d));
+        }
+        return sys.release();
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+// System::new for circuits the caller compiled itself (src/system.rs:115-203 without the named-benchmark shortcut): one
+// msgpu_graph_desc per circuit in canonical order; preprocessed[i] = HOST pointer to pre_heights[i] x descs[i].pre_width values
+// or NULL. The descriptors are copied. Everything msh_prove / msh_dist_prover_create accept works on the result.
+msh_system* msh_system_create_from_graphs(const msgpu_graph_desc* descs, uint32_t n_circuits, const uint64_t* const* preprocessed,
+                                          const uint64_t* pre_heights, uint32_t log_blowup, uint32_t log_final_poly_len,
+                                          uint32_t max_log_arity, uint32_t num_queries, uint32_t commit_pow_bits,
+                                          uint32_t query_pow_bits) {
+    try {
+        CommitmentParameters cp;
+        cp.log_blowup = log_blowup;
+        FriParameters fp;
+        fp.log_final_poly_len = log_final_poly_len;
+        fp.max_log_arity = max_log_arity;
+        fp.num_queries = num_queries;
+        fp.commit_proof_of_work_bits = commit_pow_bits;
+        fp.query_proof_of_work_bits = query_pow_bits;
+        auto sys = std::make_unique<msh_system>();
+        sys->shape = system_from_descs(cp, fp, descs, n_circuits, preprocessed, pre_heights);
         for (auto& c : sys->shape.circuits) {
             auto d = std::make_unique<GraphDesc>();
             d->build(c.graph, c.preprocessed_width, c.main_width, c.stage_2_width);

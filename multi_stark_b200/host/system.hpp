@@ -74,6 +74,42 @@ struct SystemShape {
         return s;
     }
 
+    // The same from circuits that are ALREADY compiled (System::new's per-circuit tail, src/system.rs:146-179, without the
+    // compile() call): the caller holds its own ConstraintGraph per circuit.
+    struct CompiledInput {
+        ConstraintGraph graph;
+        size_t main_width = 0;
+        bool has_preprocessed = false;
+        Matrix preprocessed;
+    };
+    static SystemShape build_compiled(const CommitmentParameters& cp, const FriParameters& fp, std::vector<CompiledInput> inputs) {
+        SystemShape s;
+        s.commitment = cp;
+        s.fri = fp;
+        const size_t d = ExtensionParams().degree;
+        for (size_t i = 0; i < inputs.size(); i++) {
+            CompiledInput& in = inputs[i];
+            Circuit c;
+            c.graph = std::move(in.graph);
+            c.num_lookups = c.graph.lookups.size();
+            c.has_preprocessed = in.has_preprocessed;
+            c.preprocessed_width = in.has_preprocessed ? in.preprocessed.width : 0;
+            c.preprocessed_height = in.has_preprocessed ? in.preprocessed.height() : 0;
+            c.stage_2_width = std::max<size_t>(c.num_lookups, 1) * d;
+            c.num_publics = 4 * d;
+            c.constraint_count = c.graph.zeros.size() + std::max<size_t>(c.num_lookups, 1) * d;
+            c.max_constraint_degree = std::max(c.graph.max_constraint_degree, logup_max_degree(c.graph));
+            c.main_width = in.main_width;
+            c.preprocessed = std::move(in.preprocessed);
+            if (c.quotient_degree() > s.max_quotient_degree())
+                throw std::runtime_error("circuit " + std::to_string(i) + ": constraint degree needs a quotient degree the PCS "
+                                         "cannot serve; increase log_blowup or lower the constraint degree");
+            s.preprocessed_indices.push_back(c.has_preprocessed ? (int)s.num_preprocessed++ : -1);
+            s.circuits.push_back(std::move(c));
+        }
+        return s;
+    }
+
     // src/system.rs:211-222
     void observe_shape(Challenger& ch) const {
         ch.observe_usize(circuits.size());

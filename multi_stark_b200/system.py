@@ -12,17 +12,81 @@ INFO_FIELDS = ["main_width", "pre_width", "pre_height", "num_lookups", "stage2_w
                "max_constraint_degree", "quotient_degree", "n_nodes", "n_zeros", "lookup_prefix_len", "preprocessed_index"]
 
 
+class GraphDescC(C.Structure):
+    """`msgpu_graph_desc` (include/msgpu.h)."""
+    _fields_ = [("n_nodes", C.c_uint32), ("op", C.c_void_p), ("a", C.c_void_p), ("b", C.c_void_p), ("imm", C.c_void_p),
+                ("n_zeros", C.c_uint32), ("zeros", C.c_void_p), ("n_lookups", C.c_uint32), ("lookup_mult", C.c_void_p),
+                ("lookup_arg_off", C.c_void_p), ("lookup_args", C.c_void_p), ("lookup_prefix_len", C.c_uint32),
+                ("pre_width", C.c_uint32), ("main_width", C.c_uint32), ("stage2_width", C.c_uint32)]
+
+
+OPS = {"const": 0, "var": 1, "public": 2, "first": 3, "last": 4, "trans": 5, "add": 6, "sub": 7, "mul": 8, "neg": 9}
+
+
+def graph_descs(graphs):
+    """Compiled circuits -> (ctypes array of msgpu_graph_desc, keep-alive list). A graph is a dict with
+    nodes: [("const", v) | ("var", source, offset, index) | ("public", i) | ("first",) | ("last",) | ("trans",) |
+            ("add" | "sub" | "mul", a, b) | ("neg", a)]  (the reference's `Node`, src/graph.rs:35-46),
+    zeros: sorted root ids, lookups: [(multiplicity id, [argument ids])], lookup_prefix_len, main_width, pre_width."""
+    arr = (GraphDescC * len(graphs))()
+    keep = []
+    for i, g in enumerate(graphs):
+        n = len(g["nodes"])
+        op = np.zeros(max(n, 1), dtype=np.uint8)
+        a = np.zeros(max(n, 1), dtype=np.uint32)
+        b = np.zeros(max(n, 1), dtype=np.uint32)
+        imm = np.zeros(max(n, 1), dtype=np.uint64)
+        for k, nd in enumerate(g["nodes"]):
+            op[k] = OPS[nd[0]]
+            if nd[0] == "const":
+                imm[k] = nd[1]
+            elif nd[0] == "var":
+                a[k], b[k] = nd[1] | (nd[2] << 2), nd[3]
+            elif nd[0] in ("public", "neg"):
+                a[k] = nd[1]
+            elif nd[0] in ("add", "sub", "mul"):
+                a[k], b[k] = nd[1], nd[2]
+        zeros = np.array(list(g["zeros"]) or [0], dtype=np.uint32)
+        lm = np.array([m for m, _ in g["lookups"]] or [0], dtype=np.uint32)
+        off = np.zeros(len(g["lookups"]) + 1, dtype=np.uint32)
+        args = []
+        for j, (_, ar) in enumerate(g["lookups"]):
+            args += list(ar)
+            off[j + 1] = len(args)
+        la = np.array(args or [0], dtype=np.uint32)
+        keep += [op, a, b, imm, zeros, lm, off, la]
+        d = arr[i]
+        d.n_nodes, d.op, d.a, d.b, d.imm = n, op.ctypes.data, a.ctypes.data, b.ctypes.data, imm.ctypes.data
+        d.n_zeros, d.zeros = len(g["zeros"]), zeros.ctypes.data
+        d.n_lookups, d.lookup_mult, d.lookup_arg_off, d.lookup_args = len(g["lookups"]), lm.ctypes.data, off.ctypes.data, la.ctypes.data
+        d.lookup_prefix_len = g["lookup_prefix_len"]
+        d.pre_width, d.main_width = g.get("pre_width", 0), g["main_width"]
+        d.stage2_width = max(len(g["lookups"]), 1) * 2
+    return arr, keep
+
+
 class System:
-    """A named system (see named_system_inputs in host/system.hpp): "u32_add", "mixed", "fib", "wide:W"."""
+    """The reference's `System` (src/system.rs:52-203) on the host side: a named benchmark system (named_system_inputs in
+    host/system.hpp: "u32_add", "mixed", "fib", "wide:W", "multi:K") or, with `System.from_graphs`, any circuits the caller
+    compiled itself."""
 
     def __init__(self, kind, log_blowup=1, log_final_poly_len=0, max_log_arity=1, num_queries=100, commit_pow_bits=0,
-                 query_pow_bits=0):
+                 query_pow_bits=0, _graphs=None, _preprocessed=None):
         self.H = _ffi.host_lib()
         self.kind = kind
         self.params = dict(log_blowup=log_blowup, log_final_poly_len=log_final_poly_len, max_log_arity=max_log_arity,
                            num_queries=num_queries, commit_pow_bits=commit_pow_bits, query_pow_bits=query_pow_bits)
-        self.h = self.H.msh_system_create(kind.encode(), log_blowup, log_final_poly_len, max_log_arity, num_queries,
-                                          commit_pow_bits, query_pow_bits)
+        if _graphs is None:
+            self.h = self.H.msh_system_create(kind.encode(), log_blowup, log_final_poly_len, max_log_arity, num_queries,
+                                              commit_pow_bits, query_pow_bits)
+        else:
+            arr, keep = graph_descs(_graphs)
+            pre = [None if p is None else np.ascontiguousarray(p, dtype=np.uint64) for p in (_preprocessed or [None] * len(_graphs))]
+            ptrs = (C.c_void_p * len(_graphs))(*[p.ctypes.data if p is not None else None for p in pre])
+            hs = (C.c_uint64 * len(_graphs))(*[p.shape[0] if p is not None else 0 for p in pre])
+            self.h = self.H.msh_system_create_from_graphs(C.cast(arr, C.c_void_p), len(_graphs), C.cast(ptrs, C.c_void_p),
+                                                          C.cast(hs, C.c_void_p), log_blowup, log_final_poly_len, max_log_arity,
+                                                          num_queries, commit_pow_bits, query_pow_bits)
         if not self.h:
             raise ValueError((self.H.msh_last_error() or b"").decode())
         self.num_circuits = int(self.H.msh_system_num_circuits(self.h))
@@ -34,6 +98,12 @@ class System:
             if info["preprocessed_index"] == 2**64 - 1:
                 info["preprocessed_index"] = None
             self.circuits.append(info)
+
+    @classmethod
+    def from_graphs(cls, graphs, preprocessed=None, **params):
+        """`msh_system_create_from_graphs`: graphs as described at graph_descs(); preprocessed[i] = (height x pre_width) array
+        or None."""
+        return cls("graphs", _graphs=graphs, _preprocessed=preprocessed, **params)
 
     def preprocessed(self, i):
         c = self.circuits[i]

@@ -1,6 +1,7 @@
 // ORACLE C entry points, part 2 (test infrastructure, not product code): systems, stage-2 traces, quotient
 // values. Loaded with ctypes by tests/, __graft_entry__.smoke() and bench.py's CPU legs ONLY.
 #include "orc_system.hpp"
+#include "../multi_stark_b200/host/system_from_graphs.hpp"
 #include <cstring>
 #include <memory>
 
@@ -27,6 +28,26 @@ void* orc_system_create(const char* kind, u32 log_blowup, u32 log_final_poly_len
         fp.query_proof_of_work_bits = query_pow_bits;
         auto s = std::make_unique<OrcSystem>();
         s->shape = SystemShape::build(cp, fp, named_system_inputs(kind));
+        return s.release();
+    } catch (const std::exception&) {
+        return nullptr;
+    }
+}
+// the oracle's System from compiled circuits (same descriptors as msh_system_create_from_graphs)
+void* orc_system_create_from_graphs(const msgpu_graph_desc* descs, u32 n, const u64* const* preprocessed, const u64* pre_heights,
+                                    u32 log_blowup, u32 log_final_poly_len, u32 max_log_arity, u32 num_queries, u32 commit_pow_bits,
+                                    u32 query_pow_bits) {
+    try {
+        CommitmentParameters cp;
+        cp.log_blowup = log_blowup;
+        FriParameters fp;
+        fp.log_final_poly_len = log_final_poly_len;
+        fp.max_log_arity = max_log_arity;
+        fp.num_queries = num_queries;
+        fp.commit_proof_of_work_bits = commit_pow_bits;
+        fp.query_proof_of_work_bits = query_pow_bits;
+        auto s = std::make_unique<OrcSystem>();
+        s->shape = system_from_descs(cp, fp, descs, n, (const uint64_t* const*)preprocessed, (const uint64_t*)pre_heights);
         return s.release();
     } catch (const std::exception&) {
         return nullptr;

@@ -52,6 +52,8 @@ def lib():
         "orc_mmcs_verify": (C.c_int, [u8p, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u8p, C.c_uint64]),
         "orc_mmcs_free": (None, [C.c_void_p]),
         "orc_system_create": (C.c_void_p, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+        "orc_system_create_from_graphs": (C.c_void_p, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                       C.c_uint32, C.c_uint32, C.c_uint32]),
         "orc_system_free": (None, [C.c_void_p]),
         "orc_graph_num_nodes": (C.c_uint64, [C.c_void_p, C.c_uint32]),
         "orc_graph_nodes": (None, [C.c_void_p, C.c_uint32, u8p, u32p, u32p, u64p, u32p]),
@@ -177,10 +179,20 @@ class OracleSystem:
     """The oracle's System: CPU prover (src/prover.rs) and restated verifier (src/verifier.rs)."""
 
     def __init__(self, L, kind, log_blowup=1, log_final_poly_len=0, max_log_arity=1, num_queries=100, commit_pow_bits=0,
-                 query_pow_bits=0):
+                 query_pow_bits=0, graphs=None, preprocessed=None):
         self.L = L
-        self.h = L.orc_system_create(kind.encode(), log_blowup, log_final_poly_len, max_log_arity, num_queries,
-                                     commit_pow_bits, query_pow_bits)
+        if graphs is None:
+            self.h = L.orc_system_create(kind.encode(), log_blowup, log_final_poly_len, max_log_arity, num_queries,
+                                         commit_pow_bits, query_pow_bits)
+        else:  # compiled circuits, same descriptors as multi_stark_b200.System.from_graphs
+            from multi_stark_b200.system import graph_descs
+            arr, keep = graph_descs(graphs)
+            pre = [None if p is None else np.ascontiguousarray(p, dtype=np.uint64) for p in (preprocessed or [None] * len(graphs))]
+            ptrs = (C.c_void_p * len(graphs))(*[p.ctypes.data if p is not None else None for p in pre])
+            hs = (C.c_uint64 * len(graphs))(*[p.shape[0] if p is not None else 0 for p in pre])
+            self.h = L.orc_system_create_from_graphs(C.cast(arr, C.c_void_p), len(graphs), C.cast(ptrs, C.c_void_p),
+                                                     C.cast(hs, C.c_void_p), log_blowup, log_final_poly_len, max_log_arity,
+                                                     num_queries, commit_pow_bits, query_pow_bits)
         assert self.h, "orc_system_create failed"
 
     def prove(self, traces, claims):

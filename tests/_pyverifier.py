@@ -807,3 +807,9 @@ def verify(circuits, params, pre_commit, claims, proof, out=None):
             return "OodEvaluationMismatch"
         acc = next_acc
     return "Ok"
+
+
+def graph_dict(c):
+    """A compiled circuit in the form multi_stark_b200.System.from_graphs / msgpu_graph_desc take."""
+    return dict(nodes=list(c.graph.nodes), zeros=list(c.graph.zeros), lookups=[(m, list(a)) for m, a in c.graph.lookups],
+                lookup_prefix_len=c.graph.lookup_prefix_len, main_width=c.main_width, pre_width=c.pre_width)

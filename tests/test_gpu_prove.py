@@ -146,3 +146,57 @@ def test_invalid_witness_is_an_error_not_a_crash(gpu):
     with pytest.raises(ms.MsgpuError):
         prover.prove([bad], [])
     prover.close()
+
+
+@pytest.mark.parametrize("log_rows,lb,fpl,nq,pow_bits", [(4, 1, 0, 20, 0), (8, 2, 1, 25, 0), (10, 1, 0, 30, 3), (12, 1, 0, 100, 0)])
+def test_independent_python_verifier_accepts_device_proofs(gpu, log_rows, lb, fpl, nq, pow_bits):
+    """tests/_pyverifier.py shares nothing with the host layer or the oracle (own challenger, own graph compiler, own MMCS / FRI
+    / STARK verifier from the reference text): it must accept the device proof, and every challenge the device prover's
+    transcript produced must equal the one the Python transcript re-derives from the proof's commitments."""
+    from tests import _pyverifier as pv
+    ms, ctx = gpu
+    kw = dict(log_blowup=lb, log_final_poly_len=fpl, num_queries=nq, commit_pow_bits=pow_bits, query_pow_bits=pow_bits)
+    system = ms.System("u32_add", **kw)
+    prover = ms.Prover(ctx, system)
+    traces, claims = workload(ms, "u32_add", log_rows)
+    proof = prover.prove(traces, claims)
+    challenges, indices = prover.last_transcript()
+    prm = dict(kw, max_log_arity=1)
+    out = {}
+    cl = [list(map(int, c)) for c in claims]
+    assert pv.verify(pv.named_system("u32_add"), prm, prover.preprocessed_commit(), cl, _proof.parse(proof), out) == "Ok"
+    mine = [out["beta"], out["gamma"], out["alpha"], out["zeta"], out["alpha_pcs"]] + out["fri_betas"]
+    assert [(e.a, e.b) for e in mine] == challenges
+    assert out["query_indices"] == indices
+    prover.close()
+
+
+def test_system_from_descriptors_proves_the_same_bytes(gpu):
+    """msh_system_create_from_graphs: the U32-add system assembled from descriptors that the independent Python compiler made
+    produces, through msh_prove, the proof bytes of the named system; and a circuit that exists only as a descriptor proves
+    and is accepted by the Python verifier."""
+    from tests import _pyverifier as pv
+    ms, ctx = gpu
+    kw = dict(log_blowup=1, num_queries=20)
+    graphs = [pv.graph_dict(c) for c in pv.named_system("u32_add")]
+    pre = [np.arange(256, dtype=np.uint64).reshape(256, 1), None]
+    named, generic = ms.System("u32_add", **kw), ms.System.from_graphs(graphs, pre, **kw)
+    traces, claims = workload(ms, "u32_add", 9)
+    pa, pb = ms.Prover(ctx, named), ms.Prover(ctx, generic)
+    assert pa.prove(traces, claims) == pb.prove(traces, claims)
+    pa.close()
+    pb.close()
+    E = pv.Expr
+    m = E.main
+    circ = pv.Circuit(3, [], [m(2) - (m(0) * m(1) + E.const(3)), E("trans") * (E.main_next(0) - m(0) - E.const(1))])
+    n = 1 << 10
+    rng = np.random.default_rng(3)
+    a = np.arange(5, 5 + n, dtype=np.uint64)
+    b = rng.integers(0, P, size=n, dtype=np.uint64)
+    c = np.array([(int(x) * int(y) + 3) % P for x, y in zip(a, b)], dtype=np.uint64)
+    custom = ms.System.from_graphs([pv.graph_dict(circ)], **kw)
+    pr = ms.Prover(ctx, custom)
+    proof = pr.prove([np.stack([a, b, c], axis=1)], [])
+    assert pv.verify([circ], dict(kw, log_final_poly_len=0, max_log_arity=1, commit_pow_bits=0, query_pow_bits=0), None, [],
+                     _proof.parse(proof)) == "Ok"
+    pr.close()
