@@ -148,14 +148,24 @@ __host__ __device__ constexpr int round_bits(int tb, int k) {
 // (blk << (S0 + RB)) + off + (m << S0). DIF: DFT then slot m *= w^{off * rev(m)}; DIT: the mirror image.
 // ld(row0, mm) / st(row0, mm, value) move the element of tile row row0 | mm of this thread's column (registers <-> global or
 // shared memory); mm = m << S0 is a compile-time constant after unrolling.
+// post (the LAST round only): table of the pass's output multipliers (inter-pass twiddles), indexed by tile row, or null.
+// Its loads are issued for the whole item BEFORE the butterflies (radix <= 4: 8 registers) or right after them, never between
+// the stores: written as "load, multiply, store" per element the compiler keeps that order (the stores may alias the table as
+// far as it knows) and every element waits a full L2 round trip on its own -- 22 % of all stall samples of the fused LDE
+// kernel (profiles/ncu_lde_mid_r2_v1.txt).
 template <int TB, int RB, int S0, bool INV, bool DIT, class Ld, class St>
-__device__ __forceinline__ void tile_round(const u64* __restrict__ tw, u32 trow, u32 nrows_thr, Ld ld, St st) {
+__device__ __forceinline__ void tile_round(const u64* __restrict__ tw, u32 trow, u32 nrows_thr, Ld ld, St st, const u64* __restrict__ post_tab = nullptr) {
     constexpr int R = 1 << RB;
     constexpr u32 items = 1u << (TB - RB);
+    constexpr bool kEarlyPost = R <= 4;
     for (u32 g = trow; g < items; g += nrows_thr) {
         const u32 off = g & ((1u << S0) - 1), blk = g >> S0;
         const u32 row0 = (blk << (S0 + RB)) + off;
-        u64 v[R];
+        u64 v[R], pt[R];
+        if (kEarlyPost && post_tab) {
+#pragma unroll
+            for (int m = 0; m < R; m++) pt[m] = __ldg(post_tab + row0 + ((u32)m << S0));
+        }
 #pragma unroll
         for (int m = 0; m < R; m++) v[m] = ld(row0, (u32)m << S0);
         if (DIT) {
@@ -173,6 +183,14 @@ __device__ __forceinline__ void tile_round(const u64* __restrict__ tw, u32 trow,
                     v[m] = mul(v[m], __ldg(tw + ((off * (u32)rev_small(m, RB)) << (kTwLog - S0 - RB))));
             }
         }
+        if (post_tab) {
+            if (!kEarlyPost) {
+#pragma unroll
+                for (int m = 0; m < R; m++) pt[m] = __ldg(post_tab + row0 + ((u32)m << S0));
+            }
+#pragma unroll
+            for (int m = 0; m < R; m++) v[m] = mul(v[m], pt[m]);
+        }
 #pragma unroll
         for (int m = 0; m < R; m++) st(row0, (u32)m << S0, v[m]);
     }
@@ -181,39 +199,40 @@ __device__ __forceinline__ void tile_round(const u64* __restrict__ tw, u32 trow,
 // All rounds of a TB-bit tile for this thread's column q. gld(row) reads the input element of tile row `row`,
 // gst(row, v) consumes the output element. DIF: natural rows in, bit-reversed rows out. DIT: the converse.
 template <int TB, bool INV, bool DIT, class GLd, class GSt>
-__device__ __forceinline__ void tile_pass(u64* tile, const u64* __restrict__ tw, u32 q, u32 trow, u32 nrows_thr, GLd gld, GSt gst) {
+__device__ __forceinline__ void tile_pass(u64* tile, const u64* __restrict__ tw, u32 q, u32 trow, u32 nrows_thr, GLd gld, GSt gst,
+                                          const u64* __restrict__ post = nullptr) {
     constexpr int B0 = round_bits(TB, 0), B1 = round_bits(TB, 1), B2 = round_bits(TB, 2);
     auto sld = [&](u32 row0, u32 mm) { return tile[tile_at(row0, mm, q)]; };
     auto sst = [&](u32 row0, u32 mm, u64 v) { tile[tile_at(row0, mm, q)] = v; };
     if constexpr (!DIT) {
         // round 0 works on the top bits
         if constexpr (B1 == 0) {
-            tile_round<TB, B0, TB - B0, INV, false>(tw, trow, nrows_thr, gld, gst);
+            tile_round<TB, B0, TB - B0, INV, false>(tw, trow, nrows_thr, gld, gst, post);
         } else if constexpr (B2 == 0) {
             tile_round<TB, B0, TB - B0, INV, false>(tw, trow, nrows_thr, gld, sst);
             __syncthreads();
-            tile_round<TB, B1, 0, INV, false>(tw, trow, nrows_thr, sld, gst);
+            tile_round<TB, B1, 0, INV, false>(tw, trow, nrows_thr, sld, gst, post);
         } else {
             tile_round<TB, B0, TB - B0, INV, false>(tw, trow, nrows_thr, gld, sst);
             __syncthreads();
             tile_round<TB, B1, B2, INV, false>(tw, trow, nrows_thr, sld, sst);
             __syncthreads();
-            tile_round<TB, B2, 0, INV, false>(tw, trow, nrows_thr, sld, gst);
+            tile_round<TB, B2, 0, INV, false>(tw, trow, nrows_thr, sld, gst, post);
         }
     } else {
         // round 0 works on the low bits
         if constexpr (B1 == 0) {
-            tile_round<TB, B0, 0, INV, true>(tw, trow, nrows_thr, gld, gst);
+            tile_round<TB, B0, 0, INV, true>(tw, trow, nrows_thr, gld, gst, post);
         } else if constexpr (B2 == 0) {
             tile_round<TB, B0, 0, INV, true>(tw, trow, nrows_thr, gld, sst);
             __syncthreads();
-            tile_round<TB, B1, B0, INV, true>(tw, trow, nrows_thr, sld, gst);
+            tile_round<TB, B1, B0, INV, true>(tw, trow, nrows_thr, sld, gst, post);
         } else {
             tile_round<TB, B0, 0, INV, true>(tw, trow, nrows_thr, gld, sst);
             __syncthreads();
             tile_round<TB, B1, B0, INV, true>(tw, trow, nrows_thr, sld, sst);
             __syncthreads();
-            tile_round<TB, B2, B0 + B1, INV, true>(tw, trow, nrows_thr, sld, gst);
+            tile_round<TB, B2, B0 + B1, INV, true>(tw, trow, nrows_thr, sld, gst, post);
         }
     }
 }
@@ -252,12 +271,9 @@ __global__ void __launch_bounds__(64 * kXt, 1024 / (64 * kXt)) k_ntt_strided(Str
     const u64* __restrict__ twp = p.twp ? p.twp + (size_t)b * T : nullptr;
     auto gld = [&](u32 row0, u32 mm) -> u64 { return valid ? src[(u64)(row0 + mm) * I] : 0ull; };
     auto gst = [&](u32 row0, u32 mm, u64 v) {
-        if (!valid) return;
-        const u32 row = row0 + mm;
-        if (twp) v = mul(v, __ldg(twp + row));
-        dst[(u64)row * I] = v;
+        if (valid) dst[(u64)(row0 + mm) * I] = v;
     };
-    tile_pass<TB, INV, false>(smem, p.tw, q, trow, nrows_thr, gld, gst);
+    tile_pass<TB, INV, false>(smem, p.tw, q, trow, nrows_thr, gld, gst, twp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -297,12 +313,9 @@ __global__ void __launch_bounds__(64 * kXt, 1024 / (64 * kXt)) k_ntt_block(Block
     const u64 dstride = p.S * w;
     auto gld = [&](u32 t0, u32 mm) -> u64 { const u32 t = t0 + mm; return valid ? mul(src[(u64)t * w], __ldg(sc + t)) : 0ull; };
     auto gst = [&](u32 s0, u32 mm, u64 v) {
-        if (!valid) return;
-        const u32 s = s0 + mm;
-        if (twb) v = mul(v, __ldg(twb + s));
-        dst[(u64)gl::rev_bits(s, TB) * dstride] = v;
+        if (valid) dst[(u64)gl::rev_bits(s0 + mm, TB) * dstride] = v;
     };
-    tile_pass<TB, false, true>(smem, p.tw, q, trow, nrows_thr, gld, gst);
+    tile_pass<TB, false, true>(smem, p.tw, q, trow, nrows_thr, gld, gst, twb);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -355,12 +368,9 @@ __global__ void __launch_bounds__(64 * kXt, 3) k_lde_mid(MidParams p) {
         u64* __restrict__ dst = p.dst + (u64)beta * p.out_block_elems + b * w + c;
         auto ald = [&](u32 t0, u32 mm) -> u64 { return mul(A[tile_at(t0, mm, q)], __ldg(sc + t0 + mm)); };
         auto gst = [&](u32 s0, u32 mm, u64 x) {
-            if (!valid) return;
-            const u32 s = s0 + mm;
-            if (twb) x = mul(x, __ldg(twb + s));
-            dst[(u64)gl::rev_bits(s, TB) * dstride] = x;
+            if (valid) dst[(u64)gl::rev_bits(s0 + mm, TB) * dstride] = x;
         };
-        tile_pass<TB, false, true>(W, p.tw_fwd, q, trow, nrows_thr, ald, gst);
+        tile_pass<TB, false, true>(W, p.tw_fwd, q, trow, nrows_thr, ald, gst, twb);
         __syncthreads();   // the next coset's first round overwrites W
     }
 }

@@ -14,6 +14,7 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may use this file.
 #pragma once
 #include "../multi_stark_b200/host/goldilocks.hpp"
+#include "cpu_simd.hpp"
 #include <map>
 #include <mutex>
 #include <memory>
@@ -43,50 +44,65 @@ static inline void dif_layer_block(Fp* m, size_t width, size_t base, size_t half
         Fp t = tw[j * tw_stride];
         Fp* a = m + (base + j) * width;
         Fp* b = m + (base + j + half) * width;
-        for (size_t c = 0; c < width; c++) {
-            Fp x = a[c], y = b[c];
-            a[c] = x + y;
-            b[c] = (x - y) * t;
-        }
+        if (t.v == 1) simd::dif_butterfly_row_notw((u64*)a, (u64*)b, width);
+        else simd::dif_butterfly_row((u64*)a, (u64*)b, t.v, width);
+    }
+}
+
+// Size-n DIF of a cache-resident block of rows (no threading inside): natural rows in, bit-reversed rows out.
+// tw = twiddle table of a transform of size n * tw_scale (w^i, i < n * tw_scale / 2).
+static inline void dif_block_inplace(Fp* m, size_t n, size_t width, const Fp* tw, size_t tw_scale) {
+    for (size_t blk = n; blk >= 2; blk >>= 1) {
+        size_t half = blk >> 1, stride = (n / blk) * tw_scale;
+        for (size_t base = 0; base < n; base += blk) dif_layer_block(m, width, base, half, tw, stride);
     }
 }
 
 // In-place forward DFT of every column; output left in BIT-REVERSED row order
 // (row rev(k) holds dft_k) -- i.e. `dft.dft_batch(m).bit_reverse_rows()` (src/prover.rs:650,716).
+// Transforms that do not fit the cache run as TWO passes over memory (the four-step split p3-dft's Radix2DitParallel makes
+// with its mid-way bit reversal): n = T * S; pass 1 gathers, for every x < S, the T rows x, x + S, x + 2S, ... into a
+// thread-local buffer, transforms them (size T, bit-reversed out), multiplies row r by w_n^{x * rev_T(r)} and scatters them
+// back; pass 2 finishes every contiguous block of S rows on its own. One layer at a time over a 100 MB matrix is bound by
+// DRAM bandwidth, not by the butterflies.
 inline void dft_batch_bitrev_inplace(Fp* m, size_t n, size_t width) {
     if (n <= 1) return;
     unsigned log_n = log2_strict(n);
     const std::vector<Fp>& tw = twiddles(log_n);
-    // Layers whose blocks exceed the cache-sized chunk are streamed over the whole matrix; the
-    // remaining layers are finished chunk by chunk so each chunk stays cache resident.
-    size_t chunk_rows = 1;
-    while (chunk_rows < n && chunk_rows * 2 * width * sizeof(Fp) <= (size_t(1) << 18)) chunk_rows *= 2;
-    size_t block = n;
-    for (; block > chunk_rows; block >>= 1) {
-        size_t half = block >> 1, stride = n / block;
-        long long nbf = (long long)(n / 2);
-#pragma omp parallel for schedule(static)
-        for (long long b = 0; b < nbf; b++) {
-            size_t blk = (size_t)b / half, j = (size_t)b % half;
-            Fp t = tw[j * stride];
-            Fp* a = m + (blk * block + j) * width;
-            Fp* bb = a + half * width;
-            for (size_t c = 0; c < width; c++) {
-                Fp x = a[c], y = bb[c];
-                a[c] = x + y;
-                bb[c] = (x - y) * t;
+    const size_t row_bytes = width * sizeof(Fp), cache = size_t(1) << 19;
+    if (n * row_bytes <= cache || log_n < 6) {
+        dif_block_inplace(m, n, width, tw.data(), 1);
+        return;
+    }
+    unsigned log_s = 1;
+    while (log_s + 1 < log_n && (size_t(2) << log_s) * row_bytes <= cache) log_s++;
+    if (log_n - log_s > log_s + 2 && (n >> log_s) * row_bytes > 4 * cache) log_s = log_n / 2;  // very tall: balance the passes
+    const size_t S = size_t(1) << log_s, T = n >> log_s;
+    const unsigned log_t = log_n - log_s;
+    const size_t half_n = n >> 1;
+#pragma omp parallel
+    {
+        std::vector<Fp> buf(T * width);
+#pragma omp for schedule(static)
+        for (long long xx = 0; xx < (long long)S; xx++) {
+            const size_t x = (size_t)xx;
+            for (size_t j = 0; j < T; j++) std::copy(m + (j * S + x) * width, m + (j * S + x + 1) * width, buf.data() + j * width);
+            dif_block_inplace(buf.data(), T, width, tw.data(), S);  // size-T twiddles are w_n^{i * S}
+            for (size_t r = 0; r < T; r++) {
+                Fp* dst = m + (r * S + x) * width;
+                const Fp* src = buf.data() + r * width;
+                size_t e = (x * reverse_bits_len(r, log_t)) & (n - 1);  // w_n^e, w_n^{n/2} = -1
+                if (e == 0) { std::copy(src, src + width, dst); continue; }
+                Fp t = e < half_n ? tw[e] : -tw[e - half_n];
+                simd::scale_row((u64*)dst, (const u64*)src, t.v, width);
             }
         }
     }
-    long long nchunks = (long long)(n / block);
-    size_t top = block;
+    if (S * row_bytes <= 2 * cache) {
 #pragma omp parallel for schedule(static)
-    for (long long ch = 0; ch < nchunks; ch++) {
-        for (size_t blk = top; blk >= 2; blk >>= 1) {
-            size_t half = blk >> 1, stride = n / blk;
-            for (size_t base = (size_t)ch * top; base < (size_t)(ch + 1) * top; base += blk)
-                dif_layer_block(m, width, base, half, tw.data(), stride);
-        }
+        for (long long r = 0; r < (long long)T; r++) dif_block_inplace(m + (size_t)r * S * width, S, width, tw.data(), T);
+    } else {  // still too large for the cache: recurse (three or more passes), one block at a time with the threads inside
+        for (size_t r = 0; r < T; r++) dft_batch_bitrev_inplace(m + r * S * width, S, width);
     }
 }
 
@@ -123,9 +139,7 @@ inline Matrix idft_batch(Matrix m) {
 #pragma omp parallel for schedule(static)
     for (long long j = 0; j < nn; j++) {
         size_t src = reverse_bits_len((n - (size_t)j) & (n - 1), log_n);
-        const Fp* s = m.row(src);
-        Fp* d = out.row(j);
-        for (size_t c = 0; c < w; c++) d[c] = s[c] * n_inv;
+        simd::scale_row((u64*)out.row(j), (const u64*)m.row(src), n_inv.v, w);
     }
     return out;
 }
@@ -140,7 +154,7 @@ inline void scale_rows_by_powers(Matrix& m, Fp shift) {
         Fp weight = shift.pow((u64)ch * CH);
         for (size_t r = (size_t)ch * CH; r < std::min(n, (size_t)(ch + 1) * CH); r++) {
             Fp* row = m.row(r);
-            for (size_t c = 0; c < w; c++) row[c] *= weight;
+            simd::scale_row_inplace((u64*)row, weight.v, w);
             weight *= shift;
         }
     }
@@ -169,10 +183,28 @@ inline Matrix lde_from_shifted_coefficients(Matrix coeffs, unsigned added_bits) 
 
 // What `TwoAdicFriPcs::commit` stores per matrix (src/prover.rs:681-692):
 // coset_lde_batch(evals, log_blowup, shift).bit_reverse_rows(): stored[i] = P(shift * w_{nB}^{rev(i)}).
+// = idft -> * shift^j -> zero-pad -> dft, with the inverse's reordering, the 1/n and the shift powers written straight into
+// the zero-padded matrix (one pass, no intermediate copies).
 inline Matrix coset_lde_batch_bitrev(Matrix evals, unsigned added_bits, Fp shift) {
-    Matrix c = idft_batch(std::move(evals));
-    scale_rows_by_powers(c, shift);
-    return lde_from_shifted_coefficients(std::move(c), added_bits);
+    size_t n = evals.height(), w = evals.width;
+    if (n == 0) return evals;
+    unsigned log_n = log2_strict(n);
+    dft_batch_bitrev_inplace(evals.values.data(), n, w);
+    Matrix out(n << added_bits, w);  // rows >= n stay zero
+    Fp n_inv = Fp((u64)n).inverse();
+    const size_t CH = 512;
+    long long nch = (long long)((n + CH - 1) / CH);
+#pragma omp parallel for schedule(static)
+    for (long long ch = 0; ch < nch; ch++) {
+        Fp weight = shift.pow((u64)ch * CH) * n_inv;  // idft(f)_j = n^-1 dft(f)_{(n-j) mod n}, then * shift^j
+        for (size_t j = (size_t)ch * CH; j < std::min(n, (size_t)(ch + 1) * CH); j++) {
+            size_t src = reverse_bits_len((n - j) & (n - 1), log_n);
+            simd::scale_row((u64*)out.row(j), (const u64*)evals.row(src), weight.v, w);
+            weight *= shift;
+        }
+    }
+    dft_batch_bitrev_inplace(out.values.data(), n << added_bits, w);
+    return out;
 }
 
 // `shifted_quotient_slices` (src/prover.rs:631-679): from the quotient's evaluations on the coset

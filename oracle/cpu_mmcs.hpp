@@ -16,6 +16,7 @@
 #pragma once
 #include "../multi_stark_b200/host/goldilocks.hpp"
 #include "../multi_stark_b200/host/blake3_host.hpp"
+#include "cpu_simd.hpp"
 #include <numeric>
 #include <stdexcept>
 
@@ -42,6 +43,44 @@ inline Digest hash_rows(const std::vector<MatView>& mats, size_t r) {
         }
     }
     return blake3_hash(buf);
+}
+// leaf digests of rows [r0, r0 + n), n <= simd::kLanes, one row per SIMD lane (rows of up to 1024 bytes = one BLAKE3 chunk;
+// wider rows take the scalar multi-chunk path)
+inline void hash_rows_many(const std::vector<MatView>& mats, size_t r0, int n, Digest* out) {
+    size_t total = 0;
+    for (auto& m : mats) total += m.width;
+    if (total * 8 > 1024 || n < 2) {
+        for (int l = 0; l < n; l++) out[l] = hash_rows(mats, r0 + l);
+        return;
+    }
+    // canonical u64 values are their own little-endian bytes on this (little-endian) host: concatenate the rows
+    std::vector<uint8_t> buf((size_t)simd::kLanes * total * 8 + 64);
+    const uint8_t* msgs[simd::kLanes];
+    for (int l = 0; l < n; l++) {
+        uint8_t* dst = buf.data() + (size_t)l * total * 8;
+        msgs[l] = dst;
+        for (auto& m : mats) {
+            memcpy(dst, m.row(r0 + l), m.width * 8);
+            dst += m.width * 8;
+        }
+    }
+    simd::b3_hash_lanes_one_chunk(msgs, n, total * 8, out);
+}
+// next[i] = compress(prev[2i], prev[2i+1]) for i in [i0, i0 + n), n <= simd::kLanes
+inline void compress_many(const Digest* prev, size_t i0, int n, Digest* out) {
+    const uint8_t* msgs[simd::kLanes];
+    for (int l = 0; l < n; l++) msgs[l] = prev[2 * (i0 + l)].data();  // 64 contiguous bytes: two adjacent digests
+    simd::b3_hash_lanes_one_chunk(msgs, n, 64, out);
+}
+inline void compress_pairs_many(const Digest* l, const Digest* r, int n, Digest* out) {
+    uint8_t buf[simd::kLanes][64];
+    const uint8_t* msgs[simd::kLanes];
+    for (int k = 0; k < n; k++) {
+        memcpy(buf[k], l[k].data(), 32);
+        memcpy(buf[k] + 32, r[k].data(), 32);
+        msgs[k] = buf[k];
+    }
+    simd::b3_hash_lanes_one_chunk(msgs, n, 64, out);
 }
 inline Digest hash_values(const Fp* vals, size_t n) {
     MatView m{vals, 1, n};
@@ -78,7 +117,8 @@ inline MerkleTree merkle_commit(const std::vector<MatView>& leaves) {
     {
         long long nn = (long long)max_h;
 #pragma omp parallel for schedule(static)
-        for (long long i = 0; i < nn; i++) layer[i] = hash_rows(group, (size_t)i);
+        for (long long i = 0; i < nn; i += simd::kLanes)
+            hash_rows_many(group, (size_t)i, (int)std::min<long long>(simd::kLanes, nn - i), &layer[i]);
     }
     t.digest_layers.push_back(std::move(layer));
     while (t.digest_layers.back().size() > 1) {
@@ -90,10 +130,17 @@ inline MerkleTree merkle_commit(const std::vector<MatView>& leaves) {
         long long nn = (long long)next_len;
         bool inject = !group.empty();
 #pragma omp parallel for schedule(static)
-        for (long long i = 0; i < nn; i++) {
-            Digest d = compress2(prev[2 * i], prev[2 * i + 1]);
-            if (inject) d = compress2(d, hash_rows(group, (size_t)i));
-            next[i] = d;
+        for (long long i = 0; i < nn; i += simd::kLanes) {
+            const int cnt = (int)std::min<long long>(simd::kLanes, nn - i);
+            Digest d[simd::kLanes];
+            compress_many(prev.data(), (size_t)i, cnt, d);
+            if (inject) {
+                Digest leaf[simd::kLanes];
+                hash_rows_many(group, (size_t)i, cnt, leaf);
+                compress_pairs_many(d, leaf, cnt, &next[i]);
+            } else {
+                for (int k = 0; k < cnt; k++) next[i + k] = d[k];
+            }
         }
         t.digest_layers.push_back(std::move(next));
     }

@@ -11,11 +11,15 @@ using namespace orc;
 
 static Matrix to_matrix(const u64* in, u64 rows, u64 cols) {
     Matrix m(rows, cols);
-    for (size_t i = 0; i < rows * cols; i++) m.values[i] = Fp(in[i]);
+    const long long total = (long long)(rows * cols);
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < total; i++) m.values[i] = Fp(in[i]);
     return m;
 }
 static void from_matrix(const Matrix& m, u64* out) {
-    for (size_t i = 0; i < m.values.size(); i++) out[i] = m.values[i].v;
+    const long long total = (long long)m.values.size();
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < total; i++) out[i] = m.values[i].v;
 }
 
 extern "C" {

@@ -26,6 +26,7 @@ def lib():
     L = C.CDLL(path)
     sig = {
         "orc_num_threads": (C.c_int, []),
+        "orc_simd_level": (C.c_int, []),
         "orc_set_num_threads": (None, [C.c_int]),
         "orc_fp_mul": (C.c_uint64, [C.c_uint64, C.c_uint64]),
         "orc_fp_inv": (C.c_uint64, [C.c_uint64]),
