@@ -36,8 +36,22 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """One builder at a time: under torchrun every rank imports the package at once; without the lock N ranks would run nvcc
+    into the same objects and a rank could load a half-written .so. Outputs are written under a temporary name and renamed."""
     if not force and not needs_build():
         return LIB
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():  # another process built it while we waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     os.makedirs(OBJ, exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose else []
 
@@ -53,10 +67,12 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    os.replace(tmp, LIB)
     build_host()
     return LIB
 
@@ -67,11 +83,13 @@ HOST_LIB = os.path.join(HERE, "libmshost.so")
 def build_host():
     """libmshost.so: the host-side protocol layer (C++17, no CUDA) over the libmsgpu C ABI."""
     src = sorted(os.path.join(HERE, "host", f) for f in os.listdir(os.path.join(HERE, "host")) if f.endswith(".cpp"))
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-o", HOST_LIB, *src,
+    tmp = HOST_LIB + ".tmp.%d" % os.getpid()
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-o", tmp, *src,
            "-L" + HERE, "-lmsgpu", "-Wl,-rpath,$ORIGIN"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("host library build failed:\n%s\n%s" % (r.stdout, r.stderr))
+    os.replace(tmp, HOST_LIB)
     return HOST_LIB
 
 

@@ -546,6 +546,9 @@ int msgpu_commit_local_dev(msgpu_ctx* h, uint64_t* const* mats, const uint64_t* 
             throw;
         }
         for (auto& m : pd->mats) m.owned = true;
+        // The class digests are handed to the caller's transport next (an NCCL send ordered against ITS stream, not this
+        // context's): they must be complete when this call returns, as in the local_only branch of msgpu_commit_upload.
+        c.sync();
         *out = pd;
     });
 }

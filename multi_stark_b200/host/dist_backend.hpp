@@ -117,7 +117,8 @@ struct DistMatrix {
 // Pcs::commit / commit_ldes over the ranks. Adopts `dev` buffers when inputs_are_ldes.
 // `prebuilt_local`: the local part already built from `mats` (msgpu_commit_upload with local_only = 1), adopted.
 inline std::shared_ptr<DistPcsHandle> dist_commit(msgpu_ctx* ctx, const CommView& comm, const std::vector<DistMatrix>& mats, uint32_t log_blowup,
-                                                  bool inputs_are_ldes, Digest& root, msgpu_pdata* prebuilt_local = nullptr) {
+                                                  bool inputs_are_ldes, Digest& root, msgpu_pdata* prebuilt_local = nullptr,
+                                                  bool* ldes_adopted = nullptr) {
     auto h = std::make_shared<DistPcsHandle>();
     h->local = prebuilt_local;  // adopted first: released with the handle on every error path
     std::vector<uint64_t*> ptrs;
@@ -138,6 +139,9 @@ inline std::shared_ptr<DistPcsHandle> dist_commit(msgpu_ctx* ctx, const CommView
     auto cls = class_owners(h->shapes, h->owner);
     h->tree_owner = cls.begin()->second;
     if (!prebuilt_local && !ptrs.empty()) gpu_check(msgpu_commit_local_dev(ctx, ptrs.data(), hs.data(), ws.data(), ptrs.size(), log_blowup, inputs_are_ldes ? 1 : 0, &h->local));
+    // from here on the handle owns the LDE buffers it was given (released with it on every later error path): the caller
+    // must not free them again -- the arena knows blocks by address only, and a released address may already be live elsewhere
+    if (ldes_adopted) *ldes_adopted = inputs_are_ldes && h->local != nullptr;
     // class digests -> tree owner
     std::vector<uint64_t> class_h;
     std::vector<const uint8_t*> class_ptr;
@@ -605,6 +609,7 @@ class DistGpuBackend : public GpuBackend {
         uint32_t lb = (uint32_t)shape_.log_blowup();
         std::vector<DistMatrix> mats;
         std::vector<uint64_t*> ldes;
+        bool adopted = false;
         try {
             for (auto& j : jobs) {
                 DistMatrix dm{(size_t)1 << (j.log_degree + lb), (size_t)2 << j.log_quotient_degree, owner_[j.circuit], nullptr};
@@ -623,11 +628,10 @@ class DistGpuBackend : public GpuBackend {
                 }
                 mats.push_back(dm);
             }
-            return dist_commit(ctx_, comm_, mats, lb, true, root);  // adopts the LDE buffers
+            return dist_commit(ctx_, comm_, mats, lb, true, root, nullptr, &adopted);  // adopts the LDE buffers
         } catch (...) {
-            // LDE buffers the commitment has not adopted yet are still ours; the arena refuses (without harm) the ones it
-            // has already released with the handle
-            for (auto* d : ldes) msgpu_free(ctx_, d);
+            if (!adopted)  // ownership was never transferred: the buffers are still ours
+                for (auto* d : ldes) msgpu_free(ctx_, d);
             throw;
         }
     }

@@ -326,6 +326,11 @@ class GpuBackend : public ProverBackend {
         std::vector<uint64_t*> s2;
         std::vector<uint64_t> hs, ws;
         intermediate.clear();
+        struct FreeAll {  // the stage-2 traces are scratch: released on every path, including a throwing msgpu_stage2_trace
+            msgpu_ctx* ctx;
+            std::vector<uint64_t*>& v;
+            ~FreeAll() { for (auto* d : v) msgpu_free(ctx, d); }
+        } guard{ctx_, s2};
         for (size_t p = 0; p < active_.size(); p++) {
             const Circuit& c = shape_.circuits[active_[p]];
             uint64_t rows = trace_rows_[p];
@@ -340,10 +345,8 @@ class GpuBackend : public ProverBackend {
             ws.push_back(c.stage_2_width);
         }
         msgpu_pdata* pd = nullptr;
-        int rc = msgpu_commit_dev(ctx_, (const uint64_t* const*)s2.data(), hs.data(), ws.data(), s2.size(), (uint32_t)shape_.log_blowup(), &pd,
-                                  root.data());
-        for (auto* d : s2) msgpu_free(ctx_, d);
-        gpu_check(rc);
+        gpu_check(msgpu_commit_dev(ctx_, (const uint64_t* const*)s2.data(), hs.data(), ws.data(), s2.size(), (uint32_t)shape_.log_blowup(), &pd,
+                                   root.data()));
         // the natural-order traces are not needed any more
         for (auto* d : trace_dev_) msgpu_free(ctx_, d);
         trace_dev_.clear();

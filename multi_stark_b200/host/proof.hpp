@@ -8,6 +8,8 @@
 // 0.5.1, which is not vendored in the reference: field ORDER here follows SURVEY Appendix A.6 and is
 // PARITY UNPINNED (no golden proof bytes exist in the reference tree).
 #pragma once
+#include <cstdlib>
+#include <string>
 #include "challenger.hpp"
 #include <optional>
 
@@ -69,13 +71,36 @@ class ByteWriter {
     void vec(const std::vector<T>& v, F&& f) { u64_(v.size()); for (auto& x : v) f(x); }
 };
 
+// ---- the one place that knows how a `Commitment` (src/types.rs:87) is laid out on the wire ------------------------------------
+// The reference's commitments are p3-merkle-tree 0.5.1's (`Mmcs::new(.., cap_height)`, src/types.rs:199-207), whose serde
+// shape is NOT verifiable in this tree (Plonky3 is an un-vendored git dependency and there is no cargo here):
+//   Raw32  the 32 digest bytes as a fixed array (`Hash<F, u8, 32>`: serde arrays carry no length)            -- the default
+//   CapVec a Merkle cap `Vec<[u8; 32]>`: u64 length prefix (2^cap_height = 1) followed by the digest bytes
+// Every commitment in `Proof::to_bytes` -- the three trace commitments and the FRI commit-phase commitments -- goes through
+// write_commitment / read_commitment, so `integration/golden_dump.rs` run against real Plonky3 settles it with one setting
+// (MSH_COMMITMENT_WIRE=cap or set_commitment_wire). The transcript observes the digest bytes either way
+// (`challenger.observe(commit)`, src/prover.rs:356).
+enum class CommitmentWire { Raw32, CapVec };
+inline CommitmentWire& commitment_wire_setting() {
+    static CommitmentWire w = [] {
+        const char* e = getenv("MSH_COMMITMENT_WIRE");
+        return (e && std::string(e) == "cap") ? CommitmentWire::CapVec : CommitmentWire::Raw32;
+    }();
+    return w;
+}
+inline void set_commitment_wire(CommitmentWire w) { commitment_wire_setting() = w; }
+inline void write_commitment(ByteWriter& w, const Digest& d) {
+    if (commitment_wire_setting() == CommitmentWire::CapVec) w.u64_(1);
+    w.digest(d);
+}
+
 inline void write_opened_round(ByteWriter& w, const OpenedValuesForRound& r) {
     w.vec(r, [&](const std::vector<std::vector<Fp2>>& m) {
         w.vec(m, [&](const std::vector<Fp2>& p) { w.vec(p, [&](const Fp2& v) { w.fp2(v); }); });
     });
 }
 inline void write_fri_proof(ByteWriter& w, const FriProof& f) {
-    w.vec(f.commit_phase_commits, [&](const Digest& d) { w.digest(d); });
+    w.vec(f.commit_phase_commits, [&](const Digest& d) { write_commitment(w, d); });
     w.vec(f.commit_pow_witnesses, [&](Fp v) { w.fp(v); });
     w.vec(f.query_proofs, [&](const QueryProof& q) {
         w.vec(q.input_proof, [&](const BatchOpening& b) {
@@ -95,9 +120,9 @@ inline std::vector<u8> proof_to_bytes(const Proof& p) {
     ByteWriter w;
     w.u64_(p.active.size());
     for (bool b : p.active) w.u8_(b ? 1 : 0);
-    w.digest(p.stage_1_trace);
-    w.digest(p.stage_2_trace);
-    w.digest(p.quotient_chunks);
+    write_commitment(w, p.stage_1_trace);
+    write_commitment(w, p.stage_2_trace);
+    write_commitment(w, p.quotient_chunks);
     w.vec(p.intermediate_accumulators, [&](const Fp2& v) { w.fp2(v); });
     w.vec(p.log_degrees, [&](u8 v) { w.u8_(v); });
     write_fri_proof(w, p.opening_proof);
@@ -124,6 +149,10 @@ class ByteReader {
   private:
     const u8 *p_, *end_;
 };
+inline Digest read_commitment(ByteReader& r) {
+    if (commitment_wire_setting() == CommitmentWire::CapVec && r.u64_() != 1) r.ok = false;  // cap_height 0: one digest
+    return r.digest();
+}
 inline OpenedValuesForRound read_opened_round(ByteReader& r) {
     OpenedValuesForRound out(r.len());
     for (auto& m : out) { m.resize(r.len()); for (auto& p : m) { p.resize(r.len()); for (auto& v : p) v = r.fp2(); } }
@@ -131,7 +160,7 @@ inline OpenedValuesForRound read_opened_round(ByteReader& r) {
 }
 inline void read_fri_proof(ByteReader& r, FriProof& f) {
     f.commit_phase_commits.resize(r.len());
-    for (auto& d : f.commit_phase_commits) d = r.digest();
+    for (auto& d : f.commit_phase_commits) d = read_commitment(r);
     f.commit_pow_witnesses.resize(r.len());
     for (auto& v : f.commit_pow_witnesses) v = r.fp();
     f.query_proofs.resize(r.len());
@@ -169,38 +198,13 @@ inline bool proof_from_bytes(const u8* data, size_t n, Proof& p) {
     ByteReader r(data, n);
     p.active.resize(r.len());
     for (size_t i = 0; i < p.active.size(); i++) { u8 b = r.u8_(); if (b > 1) r.ok = false; p.active[i] = b == 1; }
-    p.stage_1_trace = r.digest(); p.stage_2_trace = r.digest(); p.quotient_chunks = r.digest();
+    p.stage_1_trace = read_commitment(r); p.stage_2_trace = read_commitment(r); p.quotient_chunks = read_commitment(r);
     p.intermediate_accumulators.resize(r.len());
     for (auto& v : p.intermediate_accumulators) v = r.fp2();
     p.log_degrees.resize(r.len());
     for (auto& v : p.log_degrees) v = r.u8_();
-    FriProof& f = p.opening_proof;
-    f.commit_phase_commits.resize(r.len());
-    for (auto& d : f.commit_phase_commits) d = r.digest();
-    f.commit_pow_witnesses.resize(r.len());
-    for (auto& v : f.commit_pow_witnesses) v = r.fp();
-    f.query_proofs.resize(r.len());
-    for (auto& q : f.query_proofs) {
-        q.input_proof.resize(r.len());
-        for (auto& b : q.input_proof) {
-            b.opened_values.resize(r.len());
-            for (auto& row : b.opened_values) { row.resize(r.len()); for (auto& v : row) v = r.fp(); }
-            b.opening_proof.resize(r.len());
-            for (auto& d : b.opening_proof) d = r.digest();
-        }
-        q.commit_phase_openings.resize(r.len());
-        for (auto& s : q.commit_phase_openings) {
-            s.log_arity = r.u8_();
-            s.sibling_values.resize(r.len());
-            for (auto& v : s.sibling_values) v = r.fp2();
-            s.opening_proof.resize(r.len());
-            for (auto& d : s.opening_proof) d = r.digest();
-        }
-        if (!r.ok) return false;
-    }
-    f.final_poly.resize(r.len());
-    for (auto& v : f.final_poly) v = r.fp2();
-    f.query_pow_witness = r.fp();
+    read_fri_proof(r, p.opening_proof);
+    if (!r.ok) return false;
     p.quotient_opened_values = read_opened_round(r);
     u8 tag = r.u8_();
     if (tag > 1) r.ok = false;

@@ -8,9 +8,17 @@ Vec<CommitPhaseProofStep{log_arity, sibling_values, opening_proof}> }` (SURVEY A
 import struct
 
 
+CAP_WIRE = False  # True: commitments as a Merkle cap Vec<[u8; 32]> (u64 length 1 + digest), see host/proof.hpp
+
+
 class R:
     def __init__(self, b):
         self.b, self.o = b, 0
+
+    def commitment(self):
+        if CAP_WIRE:
+            assert self.u64() == 1
+        return self.digest()
 
     def u8(self):
         v = self.b[self.o]
@@ -43,11 +51,11 @@ def parse(data):
     r = R(data)
     p = {}
     p["active"] = r.vec(r.u8)
-    p["stage_1_trace"], p["stage_2_trace"], p["quotient_chunks"] = r.digest(), r.digest(), r.digest()
+    p["stage_1_trace"], p["stage_2_trace"], p["quotient_chunks"] = r.commitment(), r.commitment(), r.commitment()
     p["intermediate_accumulators"] = r.vec(r.ext)
     p["log_degrees"] = r.vec(r.u8)
     f = {}
-    f["commit_phase_commits"] = r.vec(r.digest)
+    f["commit_phase_commits"] = r.vec(r.commitment)
     f["commit_pow_witnesses"] = r.vec(r.u64)
 
     def query():
@@ -85,6 +93,11 @@ class W:
     def digest(self, d):
         self.out += d
 
+    def commitment(self, d):
+        if CAP_WIRE:
+            self.u64(1)
+        self.out += d
+
     def vec(self, v, f):
         self.u64(len(v))
         for x in v:
@@ -98,13 +111,13 @@ def _w_opened_round(w, rnd):
 def serialize(p):
     w = W()
     w.vec(p["active"], w.u8)
-    w.digest(p["stage_1_trace"])
-    w.digest(p["stage_2_trace"])
-    w.digest(p["quotient_chunks"])
+    w.commitment(p["stage_1_trace"])
+    w.commitment(p["stage_2_trace"])
+    w.commitment(p["quotient_chunks"])
     w.vec(p["intermediate_accumulators"], w.ext)
     w.vec(p["log_degrees"], w.u8)
     f = p["opening_proof"]
-    w.vec(f["commit_phase_commits"], w.digest)
+    w.vec(f["commit_phase_commits"], w.commitment)
     w.vec(f["commit_pow_witnesses"], w.u64)
 
     def query(q):

@@ -160,3 +160,29 @@ def test_multi_circuit_system_balances_and_verifies(oracle):
     # dropping one circuit's claims unbalances the accumulator
     assert S.verify(list(claims[:64]), proof) != "Ok"
     S.close()
+
+
+def test_commitment_wire_switch_is_one_setting():
+    """the serde shape of p3's `Commitment` at the pinned rev cannot be checked here. Every commitment in
+    Proof::to_bytes goes through write_commitment / read_commitment (host/proof.hpp); MSH_COMMITMENT_WIRE=cap switches all of them
+    to the Merkle-cap form (u64 length 1 + digest) and nothing else in the bytes moves."""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); from tests import _oracle as orc; import multi_stark_b200.system as mss; "
+            "L = orc.lib(); S = orc.OracleSystem(L, 'u32_add', log_blowup=1, num_queries=8); "
+            "b, a, c = mss.u32_add_workload(16); p, _ = S.prove([b, a], list(c)); "
+            "assert S.verify(list(c), p) == 'Ok'; sys.stdout.write(p.hex())") % orc.ROOT
+    raw = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, MSH_COMMITMENT_WIRE="raw"))
+    cap = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, MSH_COMMITMENT_WIRE="cap"))
+    assert raw.returncode == 0 and cap.returncode == 0, raw.stderr + cap.stderr
+    praw, pcap = bytes.fromhex(raw.stdout), bytes.fromhex(cap.stdout)
+    a = _proof.parse(praw)
+    _proof.CAP_WIRE = True
+    try:
+        b = _proof.parse(pcap)
+        assert _proof.serialize(b) == pcap
+    finally:
+        _proof.CAP_WIRE = False
+    assert a == b
+    assert len(pcap) == len(praw) + 8 * (3 + len(a["opening_proof"]["commit_phase_commits"]))
