@@ -280,6 +280,13 @@ int msgpu_open_add_input(msgpu_open* op, uint64_t len, uint64_t** dev_ptr);
 int msgpu_fri_current_len(msgpu_open* op, uint64_t* len);
 int msgpu_fri_commit_round(msgpu_open* op, uint8_t* root32);
 int msgpu_fri_fold(msgpu_open* op, const uint64_t* beta2);
+/* The whole commit phase with the TRANSCRIPT ON THE DEVICE, for commit_proof_of_work_bits = 0 (p3-fri `commit_phase`, reference
+ * call site src/prover.rs:580): per round commit -> observe(root) -> sample beta -> fold, until the vector is stop_len long,
+ * without a host round trip. input_buffer = the challenger's pending input bytes at entry (`HashChallenger` state, 1..960
+ * bytes: after the alpha sample it is the 32-byte digest of the last flush). roots_out (32 bytes per round) and betas_out
+ * (2 u64 per round) let the caller replay the same steps on its own challenger (and check them); max_rounds = their capacity. */
+int msgpu_fri_commit_phase(msgpu_open* op, const uint8_t* input_buffer, uint64_t input_len, uint64_t stop_len, uint64_t max_rounds,
+                           uint8_t* roots_out, uint64_t* betas_out, uint64_t* n_rounds);
 int msgpu_fri_read_current(msgpu_open* op, uint64_t* out);
 uint64_t msgpu_fri_num_layers(const msgpu_open* op);
 const msgpu_pdata* msgpu_fri_layer_pdata(const msgpu_open* op, uint64_t layer);

@@ -89,6 +89,7 @@ SIGNATURES = {
     "msgpu_fri_commit_round": (C.c_int, [C.c_void_p, C.c_void_p]),
     "msgpu_fri_fold": (C.c_int, [C.c_void_p, C.c_void_p]),
     "msgpu_fri_read_current": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "msgpu_fri_commit_phase": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "msgpu_fri_num_layers": (C.c_uint64, [C.c_void_p]),
     "msgpu_fri_layer_pdata": (C.c_void_p, [C.c_void_p, C.c_uint64]),
     "msgpu_open_free": (None, [C.c_void_p]),

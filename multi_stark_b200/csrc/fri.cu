@@ -149,17 +149,25 @@ __global__ void __launch_bounds__(256) k_bary_partial(BaryParams p) {
 }
 
 // sums[e] = sum over the CTAs of partial[cta][e], e over (column, slot): the host then sees W * (npts + 1) extension values
-// per matrix instead of one set per CTA (at 2^16 rows the host-side sum over 592 CTAs cost more than the kernels)
+// per matrix instead of one set per CTA (at 2^16 rows the host-side sum over 592 CTAs cost more than the kernels).
+// One warp per element: the lanes stride over the CTAs and combine with shuffles (a single thread walking ~900 partials is a
+// 900-deep chain of dependent loads: 0.30 ms per proof at 2^20 rows).
 __global__ void __launch_bounds__(128) k_bary_sum(const u64* partial, u32 ctas, u32 n, u64* sums) {
-    const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (e >= n) return;
     gl::e2 s = gl::e2_make(0, 0);
-    for (u32 b = 0; b < ctas; b++) {
+    for (u32 b = lane; b < ctas; b += 32) {
         const u64* o = partial + ((size_t)b * n + e) * 2;
         s = gl::e2_add(s, gl::e2_make(o[0], o[1]));
     }
-    sums[2 * (size_t)e] = s.a;
-    sums[2 * (size_t)e + 1] = s.b;
+    for (int d = 16; d >= 1; d >>= 1) {
+        u64 oa = __shfl_xor_sync(0xffffffffu, s.a, d), ob = __shfl_xor_sync(0xffffffffu, s.b, d);
+        s = gl::e2_add(s, gl::e2_make(oa, ob));
+    }
+    if (lane == 0) {
+        sums[2 * (size_t)e] = s.a;
+        sums[2 * (size_t)e + 1] = s.b;
+    }
 }
 
 // ro[i] += sum_p aoff_p * (yred_p - Mred_i) * invden_p[i],  Mred_i = sum_c alpha^c M[i][c]
@@ -229,11 +237,74 @@ __global__ void __launch_bounds__(kRedThreads) k_reduce_openings(ReduceParams p)
     p.ro[2 * i + 1] = acc.b;
 }
 
+// ---- the commit phase's transcript on the device ---------------------------------------------------------------------------
+// One FRI round of the reference's challenger (`DeterministicPow<SerializingChallenger64<Goldilocks, HashChallenger<u8, Blake3,
+// 32>>>`, src/types.rs:28-81) when commit_proof_of_work_bits = 0 (`grind(0)` touches nothing):
+//     observe(root): input = input || root, output buffer cleared        sample_algebra_element(): flush = BLAKE3(input),
+//     input := digest, output := digest; bytes are popped from the END, 8 per u64 (first popped = least significant),
+//     rejection-sampled below p, coordinate 0 first; when the four candidates of a digest run out the next flush hashes the
+//     32-byte input again.
+// The input buffer is the 32-byte digest of the previous flush (state) in every round but the first, whose buffer (`prefix`, at
+// most 960 bytes: one BLAKE3 chunk with the root) the host hands over. The host replays the same steps on its own challenger
+// afterwards (host/gpu_backend.hpp) and compares every beta.
+struct FriChal {
+    gl::e2 half_beta, beta_sq, beta;
+};
+__device__ __forceinline__ u32 bswap32(u32 x) { return __byte_perm(x, 0, 0x0123); }
+__device__ __noinline__ void fri_challenge_step(const uint8_t* prefix, u32 prefix_len, u32* state, const u32* root, FriChal* out,
+                                                u32* root_out) {
+    const u32 plen = prefix ? prefix_len : 32u, total = plen + 32u;
+    const uint8_t* pre = prefix ? prefix : reinterpret_cast<const uint8_t*>(state);
+    const uint8_t* rb = reinterpret_cast<const uint8_t*>(root);
+    u32 cv[8];
+    b3::set_iv(cv);
+    const u32 nblocks = (total + 63u) / 64u;
+    for (u32 b = 0; b < nblocks; b++) {
+        u32 m[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            u32 w = 0;
+            for (int k = 0; k < 4; k++) {
+                const u32 pos = b * 64u + 4u * i + k;
+                u32 byte = pos < plen ? pre[pos] : pos < total ? rb[pos - plen] : 0u;
+                w |= byte << (8 * k);
+            }
+            m[i] = w;
+        }
+        const u32 blen = min(64u, total - b * 64u);
+        const u32 flags = (b == 0 ? b3::CHUNK_START : 0u) | (b + 1 == nblocks ? (b3::CHUNK_END | b3::ROOT) : 0u);
+        b3::compress<false>(cv, m, 0, 0, blen, flags);
+    }
+    u64 coord[2];
+    int got = 0;
+    for (;;) {
+        for (int cnd = 0; cnd < 4 && got < 2; cnd++) {
+            const u64 v = ((u64)bswap32(cv[6 - 2 * cnd]) << 32) | bswap32(cv[7 - 2 * cnd]);
+            if (v < GLD_P) coord[got++] = v;
+        }
+        if (got == 2) break;
+        u32 m[16] = {cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], cv[6], cv[7], 0, 0, 0, 0, 0, 0, 0, 0};
+        b3::set_iv(cv);
+        b3::compress<false>(cv, m, 0, 0, 32, b3::CHUNK_START | b3::CHUNK_END | b3::ROOT);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) { state[i] = cv[i]; root_out[i] = root[i]; }
+    const gl::e2 beta = gl::e2_make(coord[0], coord[1]);
+    out->beta = beta;
+    out->half_beta = gl::e2_make(gl::halve(beta.a), gl::halve(beta.b));
+    out->beta_sq = gl::e2_mul(beta, beta);
+}
+__global__ void k_fri_challenge(const uint8_t* prefix, u32 prefix_len, u32* state, const u32* root, FriChal* out, u32* root_out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) fri_challenge_step(prefix, prefix_len, state, root, out, root_out);
+}
+
 // out[i] = (lo + hi)/2 + (beta/2) * g^{-rev(i)} * (lo - hi)  [+ beta^2 * roll[i]],  (lo, hi) = in[2i], in[2i+1]
+// `chal` (device) overrides the by-value challenge when the transcript runs on the device.
 __global__ void __launch_bounds__(256) k_fri_fold(const u64* in, u64* out, u64 half_len, u32 log_half, gl::e2 half_beta,
-                                                  gl::PowTable ginv_tab, const u64* roll, gl::e2 beta_sq) {
+                                                  gl::PowTable ginv_tab, const u64* roll, gl::e2 beta_sq, const FriChal* chal) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= half_len) return;
+    if (chal) { half_beta = chal->half_beta; beta_sq = chal->beta_sq; }
     gl::e2 lo = gl::e2_make(in[4 * i], in[4 * i + 1]), hi = gl::e2_make(in[4 * i + 2], in[4 * i + 3]);
     gl::e2 s = gl::e2_add(lo, hi), d = gl::e2_sub(lo, hi);
     s = gl::e2_make(gl::halve(s.a), gl::halve(s.b));
@@ -259,14 +330,18 @@ struct FoldCommitParams {
     gl::e2 half_beta, beta_sq;
     gl::PowTable ginv_tab;
     u32 half_len, log_half, n_layers;
+    const FriChal* chal;      // device-side transcript: this round's challenge (overrides half_beta / beta_sq), or null
+    u32* fs_state;            // device-side transcript: challenger state, advanced with the new root when chal_next != null
+    FriChal* chal_next;       // where the NEXT round's challenge goes
+    u32* root_out;            // 8 words: copy of the new root for the host
 };
-__device__ __forceinline__ gl::e2 fold_one(const FoldCommitParams& p, u32 i) {
+__device__ __forceinline__ gl::e2 fold_one(const FoldCommitParams& p, gl::e2 half_beta, gl::e2 beta_sq, u32 i) {
     gl::e2 lo = gl::e2_make(p.in[4 * i], p.in[4 * i + 1]), hi = gl::e2_make(p.in[4 * i + 2], p.in[4 * i + 3]);
     gl::e2 s = gl::e2_add(lo, hi), d = gl::e2_sub(lo, hi);
     s = gl::e2_make(gl::halve(s.a), gl::halve(s.b));
     u64 gp = gl::pow_lookup(p.ginv_tab, gl::rev_bits(i, p.log_half));
-    gl::e2 r = gl::e2_add(s, gl::e2_mul_base(gl::e2_mul(p.half_beta, d), gp));
-    if (p.roll) r = gl::e2_add(r, gl::e2_mul(p.beta_sq, gl::e2_make(p.roll[2 * i], p.roll[2 * i + 1])));
+    gl::e2 r = gl::e2_add(s, gl::e2_mul_base(gl::e2_mul(half_beta, d), gp));
+    if (p.roll) r = gl::e2_add(r, gl::e2_mul(beta_sq, gl::e2_make(p.roll[2 * i], p.roll[2 * i + 1])));
     return r;
 }
 __global__ void __launch_bounds__(256) k_fri_fold_commit(const __grid_constant__ FoldCommitParams p) {
@@ -274,8 +349,9 @@ __global__ void __launch_bounds__(256) k_fri_fold_commit(const __grid_constant__
     const u32 rows = p.half_len >> 1;
     uint4* bufA = sm_f;             // rows digests
     uint4* bufB = sm_f + 2 * rows;  // rows / 2 digests
+    const gl::e2 hb = p.chal ? p.chal->half_beta : p.half_beta, bsq = p.chal ? p.chal->beta_sq : p.beta_sq;
     for (u32 j = threadIdx.x; j < rows; j += blockDim.x) {
-        gl::e2 a = fold_one(p, 2 * j), b = fold_one(p, 2 * j + 1);
+        gl::e2 a = fold_one(p, hb, bsq, 2 * j), b = fold_one(p, hb, bsq, 2 * j + 1);
         p.out[4 * j] = a.a; p.out[4 * j + 1] = a.b; p.out[4 * j + 2] = b.a; p.out[4 * j + 3] = b.b;
         u32 m[16] = {(u32)a.a, (u32)(a.a >> 32), (u32)a.b, (u32)(a.b >> 32), (u32)b.a, (u32)(b.a >> 32), (u32)b.b, (u32)(b.b >> 32),
                      0, 0, 0, 0, 0, 0, 0, 0};
@@ -301,6 +377,10 @@ __global__ void __launch_bounds__(256) k_fri_fold_commit(const __grid_constant__
         }
         __syncthreads();
     }
+    // device-side transcript: observe the new root, sample the next round's beta (thread 0 wrote the root itself)
+    if (p.chal_next && threadIdx.x == 0)
+        fri_challenge_step(nullptr, 0, p.fs_state, reinterpret_cast<const u32*>(p.digests + 2 * p.layer_off[p.n_layers - 1]), p.chal_next,
+                           p.root_out);
 }
 
 }  // namespace msg
@@ -335,6 +415,7 @@ struct msgpu_open {
     bool cur_committed = false;
     std::vector<msgpu_pdata*> layers;
     msgpu_pdata* pending = nullptr;  // layer over `cur` built ahead by the fused fold (owns cur); adopted by the next commit_round
+    bool pending_has_chal = false;   // the fused fold that built `pending` also ran the transcript step for its root
 };
 
 namespace msg {
@@ -437,7 +518,7 @@ static void evaluate_all(Ctx& c, msgpu_open* op) {
                     {
                         const u32 n = bp.wc * (npts + 1);
                         KLaunch kl(c, "k_bary_sum");
-                        k_bary_sum<<<(n + 127) / 128, 128, 0, c.stream>>>(pd.d_partial, ctas, n, d_sums.u() + pd.sums_off);
+                        k_bary_sum<<<(n * 32 + 127) / 128, 128, 0, c.stream>>>(pd.d_partial, ctas, n, d_sums.u() + pd.sums_off);
                     }
                     MSG_CUDA(cudaGetLastError());
                     pend.push_back(std::move(pd));
@@ -531,6 +612,76 @@ static void reduce_all(Ctx& c, msgpu_open* op, msh::Fp2 alpha) {
     op->cur = op->inputs[0].ptr;
     op->cur_len = op->inputs[0].len;
     op->next_input = 1;
+    op->cur_committed = false;
+}
+
+
+// One fold of the committed vector. The challenge comes from the host (`beta`) or from device memory (`chal`). With
+// fuse_commit and a folded length in [2, kFusedFoldMax] the folded vector is committed by the same launch (op->pending) and,
+// when next_state / next_chal are given, the transcript step for that commitment runs in it too.
+static void fri_fold_impl(msgpu_open* op, const msh::Fp2* beta, const FriChal* chal, bool fuse_commit, u32* next_state,
+                          FriChal* next_chal, u32* next_root_out) {
+    Ctx& c = *op->ctx;
+    StageScope ss(c, "fri");
+    u64 half = op->cur_len / 2;
+    u32 log_half = ilog2(half);
+    msh::Fp2 hb, bsq;
+    if (beta) { hb = beta->halve(); bsq = beta->square(); }
+    const u64* roll = nullptr;
+    if (op->next_input < op->inputs.size() && op->inputs[op->next_input].len == half) roll = op->inputs[op->next_input].ptr;
+    u64* out = (u64*)c.alloc(half * 16);
+    gl::PowTable tab = c.pow_table(msh::two_adic_generator(log_half + 1).inverse().v, 1, log_half + 1).view();
+    if (fuse_commit && half >= 2 && half <= kFusedFoldMax) {
+        // fold + Merkle commitment of the folded vector (rows of 2 extension elements) in one launch
+        msgpu_pdata* pd = new msgpu_pdata();
+        pd->ctx = &c;
+        const u64 rows = half / 2;
+        try {
+            mmcs_layout_layers(c, pd, rows);
+        } catch (...) {
+            delete pd;
+            c.free(out);
+            throw;
+        }
+        pd->mats.push_back(msgpu_pdata::Mat{out, rows, 4, true});
+        pd->total_width = 4;
+        FoldCommitParams fp{};
+        fp.in = op->cur;
+        fp.out = out;
+        fp.roll = roll;
+        fp.digests = (uint4*)pd->digests;
+        fp.n_layers = (u32)pd->layer_off.size();
+        for (size_t l = 0; l < pd->layer_off.size(); l++) fp.layer_off[l] = pd->layer_off[l];
+        fp.half_beta = gl::e2{hb.c[0].v, hb.c[1].v};
+        fp.beta_sq = gl::e2{bsq.c[0].v, bsq.c[1].v};
+        fp.ginv_tab = tab;
+        fp.half_len = (u32)half;
+        fp.log_half = log_half;
+        fp.chal = chal;
+        fp.fs_state = next_state;
+        fp.chal_next = next_chal;
+        fp.root_out = next_root_out;
+        ensure_max_smem(k_fri_fold_commit, (int)(kFusedFoldMax / 2 * 48));
+        {
+            KLaunch kl(c, "k_fri_fold_commit");
+            k_fri_fold_commit<<<1, 256, (size_t)rows * 48, c.stream>>>(fp);
+        }
+        MSG_CUDA(cudaGetLastError());
+        if (!chal) MSG_CUDA(cudaMemcpyAsync(pd->root, pd->digests + pd->layer_off.back() * 32, 32, cudaMemcpyDeviceToHost, c.stream));
+        op->pending = pd;
+        op->pending_has_chal = next_chal != nullptr;
+    } else {
+        KLaunch kl(c, "k_fri_fold");
+        k_fri_fold<<<(unsigned)((half + 255) / 256), 256, 0, c.stream>>>(op->cur, out, half, log_half, gl::e2{hb.c[0].v, hb.c[1].v}, tab,
+                                                                         roll, gl::e2{bsq.c[0].v, bsq.c[1].v}, chal);
+    }
+    MSG_CUDA(cudaGetLastError());
+    if (roll) {
+        c.free(op->inputs[op->next_input].ptr);
+        op->next_input++;
+    }
+    op->cur = out;
+    op->cur_len = half;
     op->cur_committed = false;
 }
 
@@ -665,64 +816,75 @@ int msgpu_fri_commit_round(msgpu_open* op, uint8_t* root32) {
 
 int msgpu_fri_fold(msgpu_open* op, const uint64_t* beta2) {
     return guard([&] {
+        MSG_REQUIRE(op->cur && op->cur_committed, "fri_fold: commit the current vector first");
+        msh::Fp2 beta{msh::Fp(beta2[0]), msh::Fp(beta2[1])};
+        fri_fold_impl(op, &beta, nullptr, true, nullptr, nullptr, nullptr);
+    });
+}
+
+// The whole commit phase without a host round trip (commit_proof_of_work_bits = 0): per round commit the vector (the root
+// stays on the device), k_fri_challenge derives beta from (challenger state, root), the fold reads it from device memory.
+// Rounds of at most kFusedFoldMax elements are ONE launch each (fold + leaf hash + node layers + the next transcript step).
+// One synchronisation at the end brings back every root and beta.
+int msgpu_fri_commit_phase(msgpu_open* op, const uint8_t* input_buffer, uint64_t input_len, uint64_t stop_len, uint64_t max_rounds,
+                           uint8_t* roots_out, uint64_t* betas_out, uint64_t* n_rounds) {
+    return guard([&] {
         Ctx& c = *op->ctx;
         StageScope ss(c, "fri");
-        MSG_REQUIRE(op->cur && op->cur_committed, "fri_fold: commit the current vector first");
-        u64 half = op->cur_len / 2;
-        u32 log_half = ilog2(half);
-        msh::Fp2 beta{msh::Fp(beta2[0]), msh::Fp(beta2[1])};
-        msh::Fp2 hb = beta.halve(), bsq = beta.square();
-        const u64* roll = nullptr;
-        if (op->next_input < op->inputs.size() && op->inputs[op->next_input].len == half) roll = op->inputs[op->next_input].ptr;
-        u64* out = (u64*)c.alloc(half * 16);
-        gl::PowTable tab = c.pow_table(msh::two_adic_generator(log_half + 1).inverse().v, 1, log_half + 1).view();
-        if (half >= 2 && half <= kFusedFoldMax) {
-            // fold + Merkle commitment of the folded vector (rows of 2 extension elements) in one launch
-            msgpu_pdata* pd = new msgpu_pdata();
-            pd->ctx = &c;
-            const u64 rows = half / 2;
-            try {
-                mmcs_layout_layers(c, pd, rows);
-            } catch (...) {
-                delete pd;
-                c.free(out);
-                throw;
+        MSG_REQUIRE(op->cur && !op->cur_committed && !op->pending, "fri_commit_phase: nothing to commit");
+        MSG_REQUIRE(input_buffer && input_len >= 1 && input_len <= 960, "fri_commit_phase: the challenger's input buffer must be 1..960 bytes");
+        MSG_REQUIRE(is_pow2(stop_len) && stop_len >= 1 && roots_out && betas_out && n_rounds, "fri_commit_phase: bad argument");
+        u64 rounds = 0;
+        for (u64 l = op->cur_len; l > stop_len; l >>= 1) rounds++;
+        MSG_REQUIRE(rounds <= max_rounds, "fri_commit_phase: output buffers too small");
+        *n_rounds = rounds;
+        if (rounds == 0) return;
+        // device transcript state: [state 32 B][roots 32 B x rounds][FriChal x rounds][prefix]
+        const size_t off_roots = 32, off_chal = off_roots + 32 * rounds, off_prefix = off_chal + sizeof(FriChal) * rounds;
+        DevBuf fs(c, off_prefix + ((input_len + 15) & ~(size_t)15));
+        uint8_t* base = (uint8_t*)fs.p;
+        u32* d_state = (u32*)base;
+        u32* d_roots = (u32*)(base + off_roots);
+        FriChal* d_chal = (FriChal*)(base + off_chal);
+        uint8_t* d_prefix = base + off_prefix;
+        MSG_CUDA(cudaMemcpyAsync(d_prefix, input_buffer, input_len, cudaMemcpyHostToDevice, c.stream));
+        for (u64 k = 0; k < rounds; k++) {
+            // commit the current vector (unless the fused fold of the previous round already did, transcript step included)
+            msgpu_pdata* pd;
+            bool have_chal = false;
+            if (op->pending) {
+                pd = op->pending;
+                op->pending = nullptr;
+                have_chal = op->pending_has_chal;
+                op->pending_has_chal = false;
+            } else {
+                pd = new msgpu_pdata();
+                pd->ctx = &c;
+                pd->mats.push_back(msgpu_pdata::Mat{op->cur, op->cur_len / 2, 4, true});  // ExtensionMmcs rows of 2 elements
             }
-            pd->mats.push_back(msgpu_pdata::Mat{out, rows, 4, true});
-            pd->total_width = 4;
-            FoldCommitParams fp{};
-            fp.in = op->cur;
-            fp.out = out;
-            fp.roll = roll;
-            fp.digests = (uint4*)pd->digests;
-            fp.n_layers = (u32)pd->layer_off.size();
-            for (size_t l = 0; l < pd->layer_off.size(); l++) fp.layer_off[l] = pd->layer_off[l];
-            fp.half_beta = gl::e2{hb.c[0].v, hb.c[1].v};
-            fp.beta_sq = gl::e2{bsq.c[0].v, bsq.c[1].v};
-            fp.ginv_tab = tab;
-            fp.half_len = (u32)half;
-            fp.log_half = log_half;
-            ensure_max_smem(k_fri_fold_commit, (int)(kFusedFoldMax / 2 * 48));
-            {
-                KLaunch kl(c, "k_fri_fold_commit");
-                k_fri_fold_commit<<<1, 256, (size_t)rows * 48, c.stream>>>(fp);
+            op->cur_committed = true;
+            op->layers.push_back(pd);
+            if (!pd->digests) mmcs_build_async(c, pd);
+            if (!have_chal) {
+                KLaunch kl(c, "k_fri_challenge");
+                k_fri_challenge<<<1, 32, 0, c.stream>>>(k == 0 ? d_prefix : nullptr, (u32)input_len, d_state,
+                                                       (const u32*)(pd->digests + pd->layer_off.back() * 32), d_chal + k, d_roots + 8 * k);
+                MSG_CUDA(cudaGetLastError());
             }
-            MSG_CUDA(cudaGetLastError());
-            MSG_CUDA(cudaMemcpyAsync(pd->root, pd->digests + pd->layer_off.back() * 32, 32, cudaMemcpyDeviceToHost, c.stream));
-            op->pending = pd;
-        } else {
-            KLaunch kl(c, "k_fri_fold");
-            k_fri_fold<<<(unsigned)((half + 255) / 256), 256, 0, c.stream>>>(op->cur, out, half, log_half, gl::e2{hb.c[0].v, hb.c[1].v},
-                                                                             tab, roll, gl::e2{bsq.c[0].v, bsq.c[1].v});
+            const bool last = k + 1 == rounds;
+            fri_fold_impl(op, nullptr, d_chal + k, !last, last ? nullptr : d_state, last ? nullptr : d_chal + k + 1,
+                          last ? nullptr : d_roots + 8 * (k + 1));
         }
-        MSG_CUDA(cudaGetLastError());
-        if (roll) {
-            c.free(op->inputs[op->next_input].ptr);
-            op->next_input++;
+        std::vector<uint8_t> host(32 * rounds + sizeof(FriChal) * rounds);
+        MSG_CUDA(cudaMemcpyAsync(host.data(), d_roots, host.size(), cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+        memcpy(roots_out, host.data(), 32 * rounds);
+        const FriChal* hc = (const FriChal*)(host.data() + 32 * rounds);
+        for (u64 k = 0; k < rounds; k++) {
+            betas_out[2 * k] = hc[k].beta.a;
+            betas_out[2 * k + 1] = hc[k].beta.b;
+            memcpy(op->layers[op->layers.size() - rounds + k]->root, roots_out + 32 * k, 32);
         }
-        op->cur = out;
-        op->cur_len = half;
-        op->cur_committed = false;
     });
 }
 

@@ -90,6 +90,12 @@ static void build_nodes(Ctx& c, msgpu_pdata* pd, const std::vector<std::pair<u64
 }
 
 void mmcs_build(Ctx& c, msgpu_pdata* pd) {
+    mmcs_build_async(c, pd);
+    MSG_CUDA(cudaMemcpyAsync(pd->root, pd->digests + pd->layer_off.back() * 32, 32, cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+}
+
+void mmcs_build_async(Ctx& c, msgpu_pdata* pd) {
     StageScope stage_scope(c, "merkle");
     MSG_REQUIRE(!pd->mats.empty(), "commit: no matrices given");
     u64 max_h = 0;
@@ -105,8 +111,6 @@ void mmcs_build(Ctx& c, msgpu_pdata* pd) {
         throw;
     }
     for (size_t k = 1; k < cls.size(); k++) c.free(cls[k].second);
-    MSG_CUDA(cudaMemcpyAsync(pd->root, pd->digests + pd->layer_off.back() * 32, 32, cudaMemcpyDeviceToHost, c.stream));
-    c.sync();
 }
 
 void mmcs_build_local(Ctx& c, msgpu_pdata* pd) {

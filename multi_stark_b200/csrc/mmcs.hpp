@@ -26,6 +26,9 @@ struct msgpu_pdata {
 namespace msg {
 // Builds the tree over pd->mats (already filled in). Writes pd->root (synchronises the stream).
 void mmcs_build(Ctx& c, msgpu_pdata* pd);
+// The same without the root read-back: everything is enqueued on the stream, the root is the last digest of pd->digests
+// (pd->root is NOT filled in). For the device-side FRI commit phase, which never waits for the host between rounds.
+void mmcs_build_async(Ctx& c, msgpu_pdata* pd);
 void mmcs_open_batch(Ctx& c, const msgpu_pdata* pd, const u64* indices_host, u64 n_idx, u64* opened_host,
                      uint8_t* proof_host);
 // Mmcs::open_batch of several trees in one launch: tree k is opened at indices[q] >> shifts[k]

@@ -3,6 +3,8 @@
 // stages; the host sees roots, opened values, the final polynomial and the query openings only.
 #pragma once
 #include "prover.hpp"
+#include <cstdlib>
+#include <cstring>
 #include "program.hpp"
 #include "../../include/msgpu.h"
 
@@ -119,6 +121,30 @@ class GpuOpenDevice : public OpenDevice {
     void fold(Fp2 beta) override {
         uint64_t b[2] = {beta.c[0].v, beta.c[1].v};
         gpu_check(msgpu_fri_fold(op_, b));
+    }
+    // p3-fri `commit_phase` with the transcript on the device (no root read-back per round) when there is no proof of work
+    // to grind; the host challenger replays the rounds afterwards and every beta is compared.
+    void commit_phase(Challenger& ch, size_t stop_len, size_t pow_bits, FriProof& proof) override {
+        const std::vector<u8>& buf = ch.input_buffer();
+        static const bool host_loop = getenv("MSGPU_FRI_HOST_LOOP") != nullptr;
+        if (pow_bits != 0 || buf.empty() || buf.size() > 960 || host_loop || current_len() <= stop_len) {
+            OpenDevice::commit_phase(ch, stop_len, pow_bits, proof);
+            return;
+        }
+        uint8_t roots[64 * 32];
+        uint64_t bt[64 * 2], n = 0;
+        gpu_check(msgpu_fri_commit_phase(op_, buf.data(), buf.size(), stop_len, 64, roots, bt, &n));
+        for (uint64_t k = 0; k < n; k++) {
+            Digest commit;
+            memcpy(commit.data(), roots + 32 * k, 32);
+            ch.observe(commit);
+            proof.commit_phase_commits.push_back(commit);
+            proof.commit_pow_witnesses.push_back(ch.grind(0));
+            Fp2 beta = ch.sample_ext();
+            if (beta.c[0].v != bt[2 * k] || beta.c[1].v != bt[2 * k + 1])
+                throw GpuError("fri: the device transcript and the host challenger disagree on a folding challenge");
+            betas.push_back(beta);
+        }
     }
     std::vector<Fp2> read_current() override {
         size_t len = current_len();

@@ -62,8 +62,13 @@ struct Proof {
 class ByteWriter {
   public:
     std::vector<u8> out;
+    ByteWriter() { out.reserve(size_t(1) << 20); }  // a proof is ~1 MB: one allocation, appended 8 bytes at a time
     void u8_(u8 v) { out.push_back(v); }
-    void u64_(u64 v) { for (int b = 0; b < 8; b++) out.push_back((u8)(v >> (8 * b))); }
+    void u64_(u64 v) {
+        u8 le[8];
+        for (int b = 0; b < 8; b++) le[b] = (u8)(v >> (8 * b));
+        out.insert(out.end(), le, le + 8);
+    }
     void fp(Fp v) { u64_(v.v); }
     void fp2(const Fp2& v) { fp(v.c[0]); fp(v.c[1]); }
     void digest(const Digest& d) { out.insert(out.end(), d.begin(), d.end()); }

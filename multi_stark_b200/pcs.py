@@ -278,6 +278,29 @@ class GpuPcs:
                                   root.ctypes.data_as(C.c_void_p)))
         return root, ProverData(self.ctx, h, root)
 
+    def upload_begin(self, evaluations):
+        """`msgpu_upload_begin`: start the host-to-device copies of the matrices on the context's copy stream and return at
+        once; pass the handle to commit_upload. The host arrays (pinned memory for a real overlap) must stay alive until then.
+        Calling upload_begin for commitment k + 1 BEFORE commit_upload of commitment k puts the next transfer under this
+        commitment's kernels."""
+        mats = [_as_matrix(m) for m in evaluations]
+        ptrs, hs, ws = _mat_args(mats)
+        up = C.c_void_p()
+        check(self.L.msgpu_upload_begin(self.ctx.h, ptrs, hs, ws, len(mats), C.byref(up)))
+        return (up, mats)
+
+    def commit_upload(self, handle, verify_canonical=True):
+        """`msgpu_commit_upload`: Pcs::commit of the matrices handed to upload_begin. Returns (root, ProverData)."""
+        up, _keep = handle
+        h = C.c_void_p()
+        root = np.zeros(32, dtype=np.uint8)
+        check(self.L.msgpu_commit_upload(up, self.log_blowup, 1 if verify_canonical else 0, None, 0, C.byref(h),
+                                         root.ctypes.data_as(C.c_void_p)))
+        return root, ProverData(self.ctx, h, root)
+
+    def upload_free(self, handle):
+        self.L.msgpu_upload_free(handle[0])
+
     def commit_dev(self, ptrs_shapes):
         """Same with device-resident inputs: list of (device_ptr, rows, cols)."""
         n = len(ptrs_shapes)
