@@ -33,45 +33,88 @@ P = 2**64 - 2**32 + 1
 # carry, 1] from two xorshift32 streams; byte table multiplicities. Stage-2 (lookup accumulator)
 # columns are synthetic field elements of the stage-2 shape (26 / 2 base columns).
 # ------------------------------------------------------------------------------------------------
-def xorshift_stream(seed, n):
-    out = np.empty(n, dtype=np.uint32)
+def _xs_step(x):
+    x ^= (x << 13) & 0xFFFFFFFF
+    x ^= x >> 17
+    x ^= (x << 5) & 0xFFFFFFFF
+    return x
+
+
+def xorshift_stream(seed, n, block=4096):
+    """The xorshift32 stream of benches/multi_stark.rs:180-187. x_{i+1} = T x_i is linear over GF(2): the first `block` values
+    are generated one by one, then whole blocks at once with T^block applied through four byte-indexed tables."""
+    block = min(block, n)
+    first = np.empty(block, dtype=np.uint32)
     x = seed
-    for i in range(n):
-        x ^= (x << 13) & 0xFFFFFFFF
-        x ^= x >> 17
-        x ^= (x << 5) & 0xFFFFFFFF
-        out[i] = x
+    for i in range(block):
+        x = _xs_step(x)
+        first[i] = x
+    if block == n:
+        return first
+
+    def apply(M, v):
+        r = 0
+        for j in range(32):
+            if (v >> j) & 1:
+                r ^= M[j]
+        return r
+    base = [_xs_step(1 << j) for j in range(32)]  # columns of T
+    R, e = None, block
+    while e:
+        if e & 1:
+            R = base if R is None else [apply(base, c) for c in R]
+        base = [apply(base, c) for c in base]
+        e >>= 1
+    tabs = []
+    for k in range(4):
+        t = np.zeros(256, dtype=np.uint32)
+        for v in range(256):
+            r = 0
+            for bit in range(8):
+                if (v >> bit) & 1:
+                    r ^= R[8 * k + bit]
+            t[v] = r
+        tabs.append(t)
+    out = np.empty(n, dtype=np.uint32)
+    out[:block] = first
+    cur, pos = first, block
+    while pos < n:
+        cur = tabs[0][cur & 0xFF] ^ tabs[1][(cur >> 8) & 0xFF] ^ tabs[2][(cur >> 16) & 0xFF] ^ tabs[3][cur >> 24]
+        m = min(block, n - pos)
+        out[pos:pos + m] = cur[:m]
+        pos += m
     return out
 
 
-def u32_add_workload(log_rows, seed=0):
+def u32_add_traces(log_rows):
+    """benches/multi_stark.rs:171-238 in numpy (no product library: the reference arm uses this too): the byte table's
+    multiplicity trace (256 x 1), the U32-add trace (n x 14) and the claims [1, x, y, z] (n x 4)."""
     n = 1 << log_rows
-    cache = os.path.join("/tmp", "msb200_u32add_%d.npz" % log_rows)
-    if os.path.exists(cache):
-        z = np.load(cache)
-        x, y = z["x"], z["y"]
-    else:
-        x = xorshift_stream(0xDEADBEEF, n)
-        y = xorshift_stream(0xCAFEBABE, n)
-        try:
-            np.savez(cache, x=x, y=y)
-        except OSError:
-            pass
+    x = xorshift_stream(0xDEADBEEF, n)
+    y = xorshift_stream(0xCAFEBABE, n)
     zsum = x.astype(np.uint64) + y.astype(np.uint64)
     z = (zsum & 0xFFFFFFFF).astype(np.uint32)
-    carry = (zsum >> 32).astype(np.uint64)
     main = np.empty((n, 14), dtype=np.uint64)
     for k, v in enumerate((x, y, z)):
         for b in range(4):
             main[:, 4 * k + b] = (v >> (8 * b)) & 0xFF
-    main[:, 12] = carry
+    main[:, 12] = zsum >> 32
     main[:, 13] = 1
     mult = np.bincount(main[:, :12].astype(np.int64).reshape(-1), minlength=256).astype(np.uint64)
-    byte_main = mult.reshape(256, 1)
+    claims = np.empty((n, 4), dtype=np.uint64)
+    claims[:, 0] = 1
+    claims[:, 1], claims[:, 2], claims[:, 3] = x, y, z
+    return mult.reshape(256, 1), main, claims
+
+
+def u32_add_workload(log_rows, seed=0):
+    """The two commit calls of prove(): stage 1 (byte table multiplicities, U32-add trace) then stage 2 (synthetic field
+    elements of the stage-2 shapes: 2 / 26 base columns), matrices in circuit order."""
+    n = 1 << log_rows
+    byte_main, main, _ = u32_add_traces(log_rows)
     rng = np.random.default_rng(seed + 1)
     s2_main = rng.integers(0, P, size=(n, 26), dtype=np.uint64)
     s2_byte = rng.integers(0, P, size=(256, 2), dtype=np.uint64)
-    # the two commit calls of prove(): stage 1 then stage 2, matrices in circuit order
     return [[byte_main, main], [s2_byte, s2_main]]
 
 
@@ -175,9 +218,12 @@ def measured_peaks():
 
 # ------------------------------------------------------------------------------------------------
 def load_oracle():
-    """CPU restatement of the reference path (oracle/): ONLY for the cpu_baseline / --impl reference legs."""
+    """CPU restatement of the reference path (oracle/): ONLY for the cpu_baseline / --impl reference legs. Uses every host
+    core whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
     from tests import _oracle
-    return _oracle, _oracle.lib()
+    L = _oracle.lib()
+    L.orc_set_num_threads(os.cpu_count() or 1)
+    return _oracle, L
 
 
 def cpu_commit_time(stages, log_blowup, reps=1):
@@ -203,6 +249,10 @@ def sample_stages(stages, log_sample):
     return [[m if m.shape[0] <= n else m[:n] for m in st] for st in stages]
 
 
+CPU_NOTE = ("oracle/: C++/OpenMP restatement of the reference path with AVX-512/AVX2 Goldilocks row kernels, 16-lane BLAKE3 and a "
+            "cache-blocked two-pass DFT; NOT the Rust reference binary (no cargo here, Plonky3 un-vendored); the stage-2, quotient "
+            "and opening stages of its prove() are scalar + OpenMP")
+
 
 def prove_params(args):
     """BASELINE configs[0]/[1]: log_blowup as given, 100 queries, final poly len 1, binary folding, PoW 0/0 (deterministic)."""
@@ -211,30 +261,51 @@ def prove_params(args):
 
 
 def cpu_prove_time(args, log_rows, reps=1):
-    """The oracle's CPU prover (restatement of src/prover.rs:289-603 over restated Plonky3 semantics) on all host cores."""
-    import multi_stark_b200.system as mss
+    """The oracle's CPU prover (restatement of src/prover.rs:289-603 over restated Plonky3 semantics) on all host cores, on the
+    numpy-generated workload (no product library involved)."""
     orc, L = load_oracle()
     S = orc.OracleSystem(L, "u32_add", **prove_params(args))
-    byte, add, claims = mss.u32_add_workload(1 << log_rows)
+    byte, add, claims = u32_add_traces(log_rows)
+    claims_list = list(claims)
     best, stages = None, None
     for _ in range(reps):
         t0 = time.perf_counter()
-        proof, ms_stages = S.prove([byte, add], claims)
+        proof, ms_stages = S.prove([byte, add], claims_list)
         dt = (time.perf_counter() - t0) * 1e3
         if best is None or dt < best:
             best, stages = dt, ms_stages
-    ok = S.verify(claims, proof)
+    ok = S.verify(claims_list, proof)
     S.close()
     names = ["stark/stage1_commit", "stark/claims", "stark/stage2_commit", "stark/quotient", "stark/fri_open", "stark/prove"]
-    return {"rows": 1 << log_rows, "ms": best, "stages_ms": dict(zip(names, stages)), "cores": int(L.orc_num_threads()),
-            "kind": "port", "verified": ok == "Ok", "proof_bytes": len(proof)}
+    # `ms` = the prover's own clock (sum of its stages), like the GPU leg's stages; `wall_ms` adds the ctypes marshalling
+    return {"rows": 1 << log_rows, "ms": float(stages[5]), "wall_ms": best, "stages_ms": dict(zip(names, stages)),
+            "cores": int(L.orc_num_threads()), "simd_level": int(L.orc_simd_level()), "kind": "port", "verified": ok == "Ok",
+            "proof_bytes": len(proof), "digest": __import__("hashlib").sha256(proof).hexdigest()}
 
 
-def gpu_prove_leg(args, ms, ctx, steps, warmup, verify):
+def prove_stage_bytes(log_rows, log_blowup):
+    """SURVEY 8(d) algorithmic bytes of the prove() stages after the trace commitments, for the U32-add system (byte table:
+    n = 256, widths pre 1 / main 1 / stage-2 2, q = 1; U32-add: n = 2^log_rows, widths 14 / 26, q = 1; D = 2)."""
+    B = 1 << log_blowup
+    out = {"quotient": 0, "open": 0, "fri": 0}
+    heights = set()
+    for n, wp, w1, w2, q in ((256, 1, 1, 2, 1), (1 << log_rows, 0, 14, 26, 1)):
+        nq, W = n * q, wp + w1 + w2 + 2 * q
+        out["quotient"] += 8 * nq * (wp + w1 + w2) + 16 * nq          # quotient evaluation
+        out["quotient"] += 16 * nq + 8 * n * 2 * q * (1 + B)           # quotient DFT / slices + LDE
+        out["open"] += 8 * n * W                                       # barycentric sums over the first n rows
+        out["open"] += 8 * n * B * W                                   # reduced openings: every LDE read once
+        heights.add(n * B)
+    out["open"] += 16 * sum(heights)
+    out["fri"] = 96 * max(heights)                                     # sum_k 48 * nB / 2^k
+    return out
+
+
+def gpu_prove_leg(args, ms, ctx, log_rows, steps, warmup, verify, peak=None):
     """prove() end to end through the public API: HOST (pinned) traces and claims in, Proof::to_bytes out."""
     system = ms.System("u32_add", **prove_params(args))
     prover = ms.Prover(ctx, system)  # System::new: programs + preprocessed commitment (setup, untimed like Criterion's setup)
-    byte, add, claims = ms.u32_add_workload(1 << args.log_rows)
+    byte, add, claims = u32_add_traces(log_rows)
     rk = int(os.environ.get("RANK", "0"))
     if rk:  # every rank proves its own instance: the same additions in a rotated row order
         add, claims = np.roll(add, rk, axis=0), np.roll(claims, rk, axis=0)
@@ -250,15 +321,31 @@ def gpu_prove_leg(args, ms, ctx, steps, warmup, verify):
         for k, v in prover.last_stage_ms.items():
             stage_acc.setdefault(k, []).append(v)
     launches = (ctx.launches - l0) // max(steps, 1)
-    out = {"rows": 1 << args.log_rows, "ms": float(np.median(times)), "ms_min": float(np.min(times)), "steps": steps,
+    out = {"rows": 1 << log_rows, "ms": float(np.median(times)), "ms_min": float(np.min(times)), "steps": steps,
            "stages_ms": {k: float(np.median(v)) for k, v in stage_acc.items()}, "proof_bytes": len(proof),
            "digest": __import__("hashlib").sha256(proof).hexdigest(),
            "h2d_bytes": int(byte.nbytes + add.nbytes + claims.nbytes), "gpu_launches": int(launches),
            "timing": "host wall clock around the call (host buffers in, proof bytes out)"}
+    # per-launch CUDA events of one more proof: device time per stage, and the HBM roofline of the stages SURVEY 8(d) gives
+    # algorithmic bytes for (quotient, opening = barycentric + reduced openings, FRI folds)
+    ctx.profile_begin()
+    prover.prove([byte, add], claims)
+    dev = {}
+    for rec in ctx.profile_end():
+        dev[rec["stage"] or "other"] = dev.get(rec["stage"] or "other", 0.0) + rec["ms"]
+    out["device_ms_by_stage"] = {k: round(v, 4) for k, v in sorted(dev.items())}
+    out["device_ms"] = float(sum(dev.values()))
+    if peak:
+        alg = prove_stage_bytes(log_rows, args.log_blowup)
+        out["stage_roofline"] = [{"stage": st, "ms": dev[st], "algorithmic_bytes": alg[st],
+                                  "achieved_gbs": alg[st] / (dev[st] / 1e3) / 1e9, "frac": alg[st] / (dev[st] / 1e3) / 1e9 / peak,
+                                  "note": "fri = folds + layer commitments (BLAKE3): integer-bound, bytes are the folds' only"
+                                  if st == "fri" else "HBM fraction of measured copy bandwidth"}
+                                 for st in ("quotient", "open", "fri") if dev.get(st)]
     if verify:
         orc, L = load_oracle()
         S = orc.OracleSystem(L, "u32_add", **prove_params(args))
-        out["verified"] = S.verify(claims, proof) == "Ok"
+        out["verified"] = S.verify(list(claims), proof) == "Ok"
         S.close()
     prover.close()
     return out
@@ -308,6 +395,8 @@ def sharded_prove_leg(args, ms, msd, ctx, rank, world, steps=4):
 
 
 def run_reference(args):
+    """The reference arm: the CPU restatement of the SAME step (both trace commitments of configs[1] at the full 2^log_rows
+    rows) on every host core, plus its prove() at the same rows and at 2^big rows. Imports nothing of the product."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -324,18 +413,23 @@ def run_reference(args):
     elems = committed_elements(sample, args.log_blowup)
     ms = 1e3 * float(np.mean(times))
     value = elems / (ms / 1e3) / 1e9
-    desc = "first 2^%d of 2^%d rows of each trace matrix, %d steps" % (log_sample, args.log_rows, args.steps)
-    prove = None if args.no_prove else cpu_prove_time(args, min(args.log_rows, args.cpu_prove_log_rows))
+    desc = ("the full step: both trace commitments at 2^%d rows, %d steps" % (args.log_rows, args.steps) if log_sample == args.log_rows
+            else "first 2^%d of 2^%d rows of each trace matrix, %d steps" % (log_sample, args.log_rows, args.steps))
+    prove = prove_big = None
+    if not args.no_prove:
+        prove = cpu_prove_time(args, min(args.log_rows, args.cpu_prove_log_rows))
+        if args.big_log_rows > args.log_rows:
+            prove_big = cpu_prove_time(args, args.big_log_rows)
+    orc, L = load_oracle()
     print(json.dumps({
         "impl": "reference", "metric": "lde_merkle_gelem_per_s", "value": value, "unit": "Gelem/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": "Gelem/s", "cores": threads, "kind": "port", "sample": desc,
-                         "note": "C++/OpenMP restatement of the reference path (oracle/); the Rust reference cannot be "
-                                 "built here (no cargo, Plonky3 un-vendored)"},
+                         "simd_level": int(L.orc_simd_level()), "baseline_is_reference_binary": False, "note": CPU_NOTE},
         "e2e": {"value": value, "unit": "Gelem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "prove": prove,
+        "prove": prove, "prove_big": prove_big,
     }))
 
 
@@ -355,9 +449,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-rows", type=int, default=20)
     ap.add_argument("--log-blowup", type=int, default=1)
-    ap.add_argument("--cpu-log-rows", type=int, default=18, help="rows of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-log-rows", type=int, default=20, help="rows of the CPU-baseline commit (default: the full 2^20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-prove-log-rows", type=int, default=16, help="rows of the CPU prove() baseline")
+    ap.add_argument("--cpu-prove-log-rows", type=int, default=20, help="rows of the CPU prove() baseline (default: the GPU leg's)")
+    ap.add_argument("--big-log-rows", type=int, default=22, help="second prove() leg, GPU and CPU (north_star: 2^22 rows); 0 = off")
     ap.add_argument("--no-prove", action="store_true", help="skip the prove() leg")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -402,13 +497,33 @@ def main():
             pd.free()
         return roots
 
-    def step_e2e():
+    def step_e2e_serial():
         roots = []
         for st in pinned_np:
             root, pd = pcs.commit(st)
             roots.append(bytes(root))
             pd.free()
         return roots
+
+    # The same commitments through the two-step host-pointer ABI (msgpu_upload_begin / msgpu_commit_upload): the upload of
+    # commitment k + 1 is enqueued on the copy stream BEFORE the kernels of commitment k, so in steady state PCIe and the SMs
+    # work at the same time (a prover streams its next trace in while the current one is extended).
+    pend = {"up": None}
+
+    def step_e2e():
+        roots = []
+        for i, st in enumerate(pinned_np):
+            up = pend["up"] if pend["up"] is not None else pcs.upload_begin(st)
+            pend["up"] = pcs.upload_begin(pinned_np[(i + 1) % len(pinned_np)])
+            root, pd = pcs.commit_upload(up)
+            roots.append(bytes(root))
+            pd.free()
+        return roots
+
+    def e2e_drain():
+        if pend["up"] is not None:
+            pcs.upload_free(pend["up"])
+            pend["up"] = None
 
     def barrier():
         if world > 1:
@@ -437,7 +552,8 @@ def main():
         r_res = step_resident()
     for _ in range(2):
         r_e2e = step_e2e()
-    assert r_res == r_e2e, "resident and host-pointer paths disagree"
+    e2e_drain()
+    assert r_res == r_e2e == step_e2e_serial(), "resident and host-pointer paths disagree"
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -446,6 +562,9 @@ def main():
         step_resident()
     ms_res, launches, prof, _ = timed(step_resident, args.steps, profile=True)
     ms_e2e, _, _, _ = timed(step_e2e, args.steps)
+    e2e_drain()
+    ms_e2e_serial, _, _, _ = timed(step_e2e_serial, max(3, args.steps // 2))
+    ms_e2e_serial *= args.steps / max(3, args.steps // 2)
     t_s = time.perf_counter()
     while len(sampler.lines) < 8 and time.perf_counter() - t_s < 2.0:  # same kernels, untimed: enough samples under load
         step_resident()
@@ -488,7 +607,9 @@ def main():
                                   "frac_of_mixed_peak": rate / ipk["mixed"]}
                 st["dram_traffic_bytes_per_step"] = c["dram_bytes_per_step"]
         traffic = dom.get("dram_traffic_bytes_per_step")
-        roofline = {"bound": "hbm", "kernel": "%s stage (%d launches/step)" % (dom["stage"], dom["launches_per_step"]),
+        top = max((k for k in kernels if k["stage"] == dom["stage"]), key=lambda k: k["ms_per_step"])
+        roofline = {"bound": "hbm", "stage": "%s (%d launches/step)" % (dom["stage"], dom["launches_per_step"]),
+                    "kernel": "%s (%d launches/step, %.3f ms/step)" % (top["kernel"], top["launches_per_step"], top["ms_per_step"]),
                     "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
                     "traffic": traffic / dom["launches_per_step"] if traffic else None,
                     "traffic_note": "dram read+write bytes per launch (ncu, %s); achieved/frac use ALGORITHMIC bytes per launch" % counters_file,
@@ -507,39 +628,58 @@ def main():
         log_sample = min(args.log_rows, args.cpu_log_rows)
         sample = sample_stages(stages, log_sample)
         dt, threads = cpu_commit_time(sample, B, reps=2)
-        cpu = {"value": committed_elements(sample, B) / dt / 1e9, "unit": "Gelem/s", "cores": threads, "kind": "port",
-               "sample": "first 2^%d of 2^%d rows of each trace matrix, best of 2" % (log_sample, args.log_rows)}
-        # parity spot check of the timed path against the oracle on the sample
         orc, L = load_oracle()
-        for st_full, st in zip(stages, sample):
+        cpu = {"value": committed_elements(sample, B) / dt / 1e9, "unit": "Gelem/s", "cores": threads, "kind": "port",
+               "simd_level": int(L.orc_simd_level()), "baseline_is_reference_binary": False, "note": CPU_NOTE,
+               "sample": ("the full step (both trace commitments at 2^%d rows), best of 2" % args.log_rows) if log_sample == args.log_rows
+               else "first 2^%d of 2^%d rows of each trace matrix, best of 2" % (log_sample, args.log_rows)}
+        # parity spot check of the timed path against the oracle on the same matrices
+        for st in sample:
             want, h = orc.pcs_commit(L, st, B)
             L.orc_mmcs_free(h)
             got, pd = pcs.commit(st)
             pd.free()
             assert bytes(got) == want, "GPU root differs from the oracle"
 
-    prove = None
+    prove = prove_big = None
     if not args.no_prove:
         barrier()
-        prove = gpu_prove_leg(args, ms, ctx, steps=max(3, min(args.steps, 10)), warmup=2, verify=(rank == 0))
+        prove = gpu_prove_leg(args, ms, ctx, args.log_rows, steps=max(3, min(args.steps, 10)), warmup=2, verify=(rank == 0), peak=peak)
         if world > 1:
             prove["ms_max_over_ranks"] = msd.max_over_ranks(prove["ms"])
             prove["proofs_per_s_all_ranks"] = world * 1e3 / prove["ms_max_over_ranks"]
             prove["proof_digests"] = [d.hex()[:16] for d in msd.gather_digests([bytes.fromhex(prove["digest"])])]
         if cpu is not None:
             prove["cpu"] = cpu_prove_time(args, min(args.log_rows, args.cpu_prove_log_rows))
+            if prove["cpu"]["rows"] == prove["rows"]:
+                prove["identical_to_cpu_proof"] = prove["cpu"]["digest"] == prove["digest"]
+                prove["speedup_vs_cpu_port"] = prove["cpu"]["ms"] / prove["ms"]
         barrier()
+        # north_star: prove() at 2^22 rows against the host-core parallel CPU prover, both measured here
+        if world == 1 and args.big_log_rows > args.log_rows:
+            prove_big = gpu_prove_leg(args, ms, ctx, args.big_log_rows, steps=3, warmup=1, verify=(rank == 0), peak=peak)
+            if cpu is not None:
+                prove_big["cpu"] = cpu_prove_time(args, args.big_log_rows)
+                prove_big["identical_to_cpu_proof"] = prove_big["cpu"]["digest"] == prove_big["digest"]
+                prove_big["speedup_vs_cpu_port"] = prove_big["cpu"]["ms"] / prove_big["ms"]
         if world > 1:
             prove["sharded"] = sharded_prove_leg(args, ms, msd, ctx, rank, world)
 
     if rank == 0:
+        if roofline is not None and prove is not None and prove.get("stage_roofline"):
+            roofline["prove_stages"] = prove["stage_roofline"]
         print(json.dumps({
             "metric": "lde_merkle_gelem_per_s", "value": value, "unit": "Gelem/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": "Gelem/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "call": "msgpu_upload_begin + msgpu_commit_upload on pinned host matrices, the next commitment's upload enqueued "
+                            "before this one's kernels",
+                    "serial": {"value": world * elems / (ms_e2e_serial / args.steps / 1e3) / 1e9, "ms_per_step": ms_e2e_serial / args.steps,
+                               "call": "msgpu_commit (upload, then kernels, then root; no overlap between calls)"}},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "prove": prove,
+            "prove_big": prove_big,
         }))
     ctx.close()
     if world > 1:

@@ -292,6 +292,37 @@ uint64_t msgpu_fri_num_layers(const msgpu_open* op);
 const msgpu_pdata* msgpu_fri_layer_pdata(const msgpu_open* op, uint64_t layer);
 void msgpu_open_free(msgpu_open* op);
 
+/* ---- ONE proof over ROW SHARDS of every matrix (SURVEY 8e carried past the commitment) ---------------------------------------
+ * Rank d of N holds stored rows [d H / N, (d + 1) H / N) of every committed LDE (all columns); see
+ * multi_stark_b200/host/rowshard_backend.hpp for the protocol around these calls.
+ * msgpu_pack_column_blocks_dev: rows x width row-major (device) -> n_blocks contiguous matrices rows x (c1[b] - c0[b]) laid out
+ *   back to back in dst (the send buffer of the all-to-all that turns natural-order ROW blocks into COLUMN blocks).
+ * msgpu_interleave_column_blocks_dev: the inverse for the receive side: n_blocks matrices of `rows` rows back to back in src ->
+ *   one row-major rows x sum(widths) matrix.
+ * msgpu_quotient_values_shard / msgpu_quotient_finish: `quotient_values` on the rows a rank holds (the NEXT rows come from the
+ *   shard one trace step further) and the tail of the quotient stage on the rank that gathered the values.
+ * msgpu_open_begin_shard .. msgpu_open_finish_values: Pcs::open where every rank evaluates / reduces the rows it holds; the
+ *   barycentric sums are added over the ranks by the caller, the reduced-opening shards are added into the FRI owner's vectors
+ *   (msgpu_open_input_dev + msgpu_ext_add_dev). modes[r]: 0 = round held here in full, 1 = row shard `shard` of `n_shards`
+ *   (the prover data holds the shard), 2 = held elsewhere (msgpu_pdata_placeholder carries the global shapes). */
+int msgpu_pack_column_blocks_dev(msgpu_ctx* ctx, const uint64_t* src, uint64_t rows, uint64_t width, uint64_t n_blocks,
+                                 const uint64_t* c0, const uint64_t* c1, uint64_t* dst);
+int msgpu_interleave_column_blocks_dev(msgpu_ctx* ctx, const uint64_t* src, uint64_t rows, uint64_t n_blocks, const uint64_t* widths,
+                                       uint64_t* dst);
+int msgpu_quotient_values_shard(msgpu_ctx* ctx, const msgpu_program* prog, const uint64_t* const* cur3, const uint64_t* const* next3,
+                                uint64_t row0, uint64_t n_local, uint64_t next_row0, uint32_t log_n, uint32_t log_quotient_degree,
+                                const uint64_t* publics8, const uint64_t* alpha2, uint64_t* out_dev);
+int msgpu_quotient_finish(msgpu_ctx* ctx, const uint64_t* values_stored_dev, uint32_t log_n, uint32_t log_quotient_degree,
+                          uint32_t log_blowup, uint64_t** lde_out_dev);
+int msgpu_open_begin_shard(msgpu_ctx* ctx, uint64_t n_rounds, const msgpu_pdata* const* pds, const uint32_t* modes, uint32_t shard,
+                           uint32_t n_shards, int fri_owner, const uint64_t* n_points, const uint64_t* points, uint32_t log_blowup,
+                           msgpu_open** out, uint64_t* n_values, uint64_t* n_sums);
+int msgpu_open_sums(msgpu_open* op, uint64_t* out);
+int msgpu_open_finish_values(msgpu_open* op, const uint64_t* total_sums);
+int msgpu_pdata_placeholder(msgpu_ctx* ctx, uint64_t n_mats, const uint64_t* heights, const uint64_t* widths, msgpu_pdata** out);
+int msgpu_ext_add_dev(msgpu_ctx* ctx, uint64_t* dst, const uint64_t* src, uint64_t n_ext);
+int msgpu_ext_add_scalar_dev(msgpu_ctx* ctx, uint64_t* v, uint64_t n_ext, const uint64_t* c2);
+
 /* ---- transcript helper ---------------------------------------------------------------------------
  * Unkeyed BLAKE3-256 of a HOST byte string, hashed on the device (chunk chaining values in parallel, then the
  * binary parent tree). The reference's challenger is `HashChallenger<u8, Blake3, 32>` (src/types.rs:28-29); its

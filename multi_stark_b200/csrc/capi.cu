@@ -594,6 +594,22 @@ int msgpu_pdata_digests(const msgpu_pdata* pd, uint8_t** dev_ptr, uint64_t* n_di
         *n_digests = 2 * pd->max_height - 1;
     });
 }
+int msgpu_pack_column_blocks_dev(msgpu_ctx* h, const uint64_t* src, uint64_t rows, uint64_t width, uint64_t n_blocks, const uint64_t* c0,
+                                 const uint64_t* c1, uint64_t* dst) {
+    return guard([&] {
+        MSG_REQUIRE(src && dst && c0 && c1, "pack_column_blocks: null argument");
+        StageScope ss(h->c, "exchange");
+        pack_column_blocks(h->c, (const u64*)src, rows, width, std::vector<u64>(c0, c0 + n_blocks), std::vector<u64>(c1, c1 + n_blocks), (u64*)dst);
+    });
+}
+int msgpu_interleave_column_blocks_dev(msgpu_ctx* h, const uint64_t* src, uint64_t rows, uint64_t n_blocks, const uint64_t* widths,
+                                       uint64_t* dst) {
+    return guard([&] {
+        MSG_REQUIRE(src && dst && widths, "interleave_column_blocks: null argument");
+        StageScope ss(h->c, "exchange");
+        interleave_column_blocks(h->c, (const u64*)src, rows, std::vector<u64>(widths, widths + n_blocks), (u64*)dst);
+    });
+}
 int msgpu_pdata_from_parts(msgpu_ctx* h, uint64_t n_blocks, const uint64_t* const* blocks, const uint64_t* widths, uint64_t lde_height,
                            uint64_t n_parts, const uint8_t* const* part_digests, msgpu_pdata** out, uint8_t* root32) {
     return guard([&] {

@@ -34,8 +34,9 @@ __device__ __forceinline__ gl::e2 e2_inverse_d(gl::e2 x) {
 
 // invden[i] = 1 / (z - x_i), x_i = GENERATOR * w_H^{rev(i)}  (the LDE domain in stored order)
 constexpr int kInvPerThread = 8;
-__global__ void __launch_bounds__(256) k_inv_denoms(u64* invden, u32 log_h, gl::e2 z, gl::PowTable xtab) {
-    const u64 H = 1ull << log_h;
+// Row shards: invden[i] belongs to stored row row0 + i, i < len (unsharded: row0 = 0, len = 2^log_h).
+__global__ void __launch_bounds__(256) k_inv_denoms(u64* invden, u32 log_h, gl::e2 z, gl::PowTable xtab, u64 row0, u64 len) {
+    const u64 H = len;
     u64 i0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * kInvPerThread;
     if (i0 >= H) return;
     // fully unrolled with constant indices: the batch lives in registers (a dynamically indexed array is local memory)
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(256) k_inv_denoms(u64* invden, u32 log_h, gl::
         pref[k] = acc;
         va[k] = 0;
         if (k < cnt) {
-            u64 x = gl::pow_lookup(xtab, gl::rev_bits((u32)(i0 + k), log_h));
+            u64 x = gl::pow_lookup(xtab, gl::rev_bits((u32)(row0 + i0 + k), log_h));
             va[k] = gl::sub(z.a, x);
             acc = gl::e2_mul(acc, gl::e2_make(va[k], z.b));
         }
@@ -176,7 +177,8 @@ struct ReduceParams {
     const u64* apow;  // w x 2
     const u64* invden[kMaxPts];
     u64* ro;
-    u64 H;
+    u64 H;        // local rows of M
+    u64 ro_off;   // ro index of local row 0 (the FRI owner of a sharded opening keeps the full-length vector)
     u64 aoff[kMaxPts][2], yred[kMaxPts][2];
     u32 w, npts, tile_rows;
 };
@@ -225,16 +227,29 @@ __global__ void __launch_bounds__(kRedThreads) k_reduce_openings(ReduceParams p)
         m1 = gl::add(m1, o1);
     }
     if (!live || lane != 0) return;
-    const u64 i = row0 + r;
-    gl::e2 acc = gl::e2_make(p.ro[2 * i], p.ro[2 * i + 1]);
+    const u64 i = row0 + r, io = p.ro_off + i;
+    gl::e2 acc = gl::e2_make(p.ro[2 * io], p.ro[2 * io + 1]);
     for (u32 k = 0; k < p.npts; k++) {
         gl::e2 diff = gl::e2_make(gl::sub(p.yred[k][0], m0), gl::sub(p.yred[k][1], m1));
         gl::e2 d = gl::e2_make(p.invden[k][2 * i], p.invden[k][2 * i + 1]);
         gl::e2 t = gl::e2_mul(gl::e2_mul(gl::e2_make(p.aoff[k][0], p.aoff[k][1]), diff), d);
         acc = gl::e2_add(acc, t);
     }
-    p.ro[2 * i] = acc.a;
-    p.ro[2 * i + 1] = acc.b;
+    p.ro[2 * io] = acc.a;
+    p.ro[2 * io + 1] = acc.b;
+}
+
+// dst[i] += src[i] over n extension elements (shards of reduced openings added into the FRI owner's vector)
+__global__ void __launch_bounds__(256) k_ext_add(u64* dst, const u64* src, u64 n) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n) return;
+    dst[i] = gl::add(dst[i], src[i]);
+}
+// v[i] += c over n extension elements (the running-sum offset of a row block of a stage-2 trace)
+__global__ void __launch_bounds__(256) k_ext_add_scalar(u64* v, u64 n, gl::e2 cst) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n) return;
+    v[i] = gl::add(v[i], (i & 1) ? cst.b : cst.a);
 }
 
 // ---- the commit phase's transcript on the device ---------------------------------------------------------------------------
@@ -388,19 +403,32 @@ __global__ void __launch_bounds__(256) k_fri_fold_commit(const __grid_constant__
 struct msgpu_open {
     struct Mat {
         const u64* ptr;
-        u64 height, width;
+        u64 height, width;   // GLOBAL LDE height
         u32 log_h;
         std::vector<msh::Fp2> points;
         std::vector<std::vector<msh::Fp2>> values;  // [point][column]
+        // row shards (msgpu_open_begin_shard): this rank holds stored rows [row0, row0 + rows) of the matrix at `ptr`;
+        // rows = 0: the matrix lives elsewhere (shapes only). Unsharded: row0 = 0, rows = height.
+        u64 row0 = 0, rows = 0;
     };
     msg::Ctx* ctx = nullptr;
     u32 log_blowup = 0;
+    bool sharded = false, fri_owner = true;
     std::vector<std::vector<Mat>> rounds;
     struct InvDen {
         msh::Fp2 z;
         u32 log_h;
         u64* ptr;
+        u64 row0 = 0, len = 0;
     };
+    // sharded evaluation: the barycentric sums of the local rows, to be summed over the ranks before the values exist
+    struct PendingSum {
+        size_t round, mat, sums_off;
+        u32 npts, c0, wc;
+        size_t p0;
+    };
+    std::vector<PendingSum> pending_sums;
+    std::vector<u64> raw_sums;
     std::vector<InvDen> invdens;
     u64 n_values = 0;
     // FRI
@@ -424,9 +452,14 @@ static gl::PowTable lde_x_table(Ctx& c, u32 log_h) {
     return c.pow_table(msh::two_adic_generator(log_h).v, msh::GL_GENERATOR, log_h).view();
 }
 
-static u64* find_invden(msgpu_open* op, const msh::Fp2& z, u32 log_h) {
-    for (auto& d : op->invdens)
-        if (d.z == z && d.log_h >= log_h) return d.ptr;
+// Unsharded: one array per point at the largest height opened there serves every shorter matrix (its first rows are the
+// shorter domain). Sharded: one array per (point, height, row range), since a shard of a shorter matrix is not a prefix.
+static u64* find_invden(msgpu_open* op, const msh::Fp2& z, const msgpu_open::Mat& m) {
+    for (auto& d : op->invdens) {
+        if (!(d.z == z)) continue;
+        if (!op->sharded && d.log_h >= m.log_h) return d.ptr;
+        if (op->sharded && d.log_h == m.log_h && d.row0 == m.row0 && d.len == m.rows) return d.ptr;
+    }
     throw Error(-3, "open: missing inverse denominators");
 }
 
@@ -441,50 +474,75 @@ static void open_destroy(msgpu_open* op) {
     delete op;
 }
 
+// values from the barycentric sums (S1, S2 per column and point): y = (z * S2 - S1) * (z^h - g^h) / (h * g^h), g = GENERATOR
+static void finish_values(msgpu_open* op, const u64* sums) {
+    for (auto& ps : op->pending_sums) {
+        auto& m = op->rounds[ps.round][ps.mat];
+        u32 log_h = m.log_h - op->log_blowup;
+        msh::Fp shift_pow = msh::Fp(msh::GL_GENERATOR).exp_power_of_2(log_h);
+        msh::Fp denom_inv = (shift_pow * msh::Fp((msh::u64)1 << log_h)).inverse();
+        const u32 nslots = ps.npts + 1;
+        msh::Fp2 scale[kMaxPts];
+        for (u32 k = 0; k < ps.npts; k++) scale[k] = (m.points[ps.p0 + k].exp_power_of_2(log_h) - shift_pow) * denom_inv;
+        const u64* hs = sums + ps.sums_off;
+        for (u32 cc = 0; cc < ps.wc; cc++) {
+            msh::Fp s1 = msh::Fp(hs[((size_t)cc * nslots) * 2]);
+            for (u32 k = 0; k < ps.npts; k++) {
+                size_t o = ((size_t)cc * nslots + k + 1) * 2;
+                msh::Fp2 s2 = msh::Fp2(msh::Fp((msh::u64)hs[o]), msh::Fp((msh::u64)hs[o + 1]));
+                m.values[ps.p0 + k][ps.c0 + cc] = (m.points[ps.p0 + k] * s2 - s1) * scale[k];
+            }
+        }
+    }
+    op->pending_sums.clear();
+}
+
 static void evaluate_all(Ctx& c, msgpu_open* op) {
     StageScope ss(c, "open");
-    // 1. inverse denominators per distinct point, at the largest LDE height opened there
+    // 1. inverse denominators per distinct point: unsharded at the largest LDE height opened there; sharded per
+    //    (point, height, row range) of the rows this rank holds
     for (auto& round : op->rounds)
-        for (auto& m : round)
+        for (auto& m : round) {
+            if (m.rows == 0) continue;
             for (auto& z : m.points) {
                 bool found = false;
-                for (auto& d : op->invdens)
-                    if (d.z == z) { d.log_h = std::max(d.log_h, m.log_h); found = true; }
-                if (!found) op->invdens.push_back(msgpu_open::InvDen{z, m.log_h, nullptr});
+                for (auto& d : op->invdens) {
+                    if (!(d.z == z)) continue;
+                    if (!op->sharded) { d.log_h = std::max(d.log_h, m.log_h); d.len = 1ull << d.log_h; found = true; }
+                    else if (d.log_h == m.log_h && d.row0 == m.row0 && d.len == m.rows) found = true;
+                }
+                if (!found) op->invdens.push_back(msgpu_open::InvDen{z, m.log_h, nullptr, m.row0, m.rows});
             }
+        }
     for (auto& d : op->invdens) {
-        u64 H = 1ull << d.log_h;
-        d.ptr = (u64*)c.alloc(H * 16);
-        u64 threads = (H + kInvPerThread - 1) / kInvPerThread;
+        d.ptr = (u64*)c.alloc(d.len * 16);
+        u64 threads = (d.len + kInvPerThread - 1) / kInvPerThread;
         {
             KLaunch kl(c, "k_inv_denoms");
             k_inv_denoms<<<(unsigned)((threads + 255) / 256), 256, 0, c.stream>>>(d.ptr, d.log_h, gl::e2{d.z.c[0].v, d.z.c[1].v},
-                                                                                lde_x_table(c, d.log_h));
+                                                                                lde_x_table(c, d.log_h), d.row0, d.len);
         }
         MSG_CUDA(cudaGetLastError());
     }
-    // 2. barycentric sums per matrix (all of its points in one pass over the low coset)
-    struct Pending {
-        msgpu_open::Mat* m;
-        u64* d_partial;
-        size_t sums_off;  // u64 offset of this launch's (column, slot) sums inside the shared sums buffer
-        u32 ctas, npts, c0, wc;
-        size_t p0;
-    };
-    std::vector<Pending> pend;
+    // 2. barycentric sums per matrix (all of its points in one pass over the low coset = the first height >> log_blowup stored
+    //    rows; a shard contributes the part of them it holds)
+    std::vector<u64*> partials;
     size_t sums_total = 0;
     for (auto& round : op->rounds)
         for (auto& m : round)
             for (size_t p0 = 0; p0 < m.points.size(); p0 += kMaxPts)
                 sums_total += m.width * (std::min<size_t>(kMaxPts, m.points.size() - p0) + 1) * 2;
     DevBuf d_sums(c, std::max<size_t>(sums_total, 1) * 8);
+    MSG_CUDA(cudaMemsetAsync(d_sums.p, 0, std::max<size_t>(sums_total, 1) * 8, c.stream));
     size_t sums_off = 0;
-    for (auto& round : op->rounds)
-        for (auto& m : round) {
+    op->pending_sums.clear();
+    for (size_t ri = 0; ri < op->rounds.size(); ri++)
+        for (size_t mi = 0; mi < op->rounds[ri].size(); mi++) {
+            auto& m = op->rounds[ri][mi];
             m.values.assign(m.points.size(), std::vector<msh::Fp2>(m.width));
             if (m.width == 0) continue;
-            u64 h = m.height >> op->log_blowup;
-            u32 log_h = m.log_h - op->log_blowup;
+            const u64 h_all = m.height >> op->log_blowup;
+            const u64 h = m.row0 >= h_all ? 0 : std::min<u64>(m.rows, h_all - m.row0);  // local rows inside the low coset
             for (size_t p0 = 0; p0 < m.points.size(); p0 += kMaxPts) {
                 u32 npts = (u32)std::min<size_t>(kMaxPts, m.points.size() - p0);
                 for (u32 c0 = 0; c0 < m.width; c0 += 256) {
@@ -492,17 +550,20 @@ static void evaluate_all(Ctx& c, msgpu_open* op) {
                     bp.M = m.ptr;
                     bp.h = h;
                     bp.w = (u32)m.width;
-                                    bp.c0 = c0;
+                    bp.c0 = c0;
                     bp.wc = (u32)std::min<u64>(256, m.width - c0);
                     bp.rows_per_step = 256 / bp.wc;
-                    for (u32 k = 0; k < npts; k++) bp.invden[k] = find_invden(op, m.points[p0 + k], m.log_h);
+                    op->pending_sums.push_back(msgpu_open::PendingSum{ri, mi, sums_off, npts, c0, bp.wc, p0});
+                    const size_t my_off = sums_off;
+                    sums_off += (size_t)bp.wc * (npts + 1) * 2;
+                    if (h == 0) continue;  // nothing of the low coset here: the sums stay zero
+                    for (u32 k = 0; k < npts; k++) bp.invden[k] = find_invden(op, m.points[p0 + k], m);
                     bp.tile_rows = (u32)std::min<u64>(256, std::max<u64>(8, 4096 / bp.wc));
                     u64 want = (h + bp.tile_rows - 1) / bp.tile_rows;
                     u32 ctas = (u32)std::min<u64>(want, (u64)c.sm_count * 6);
-                    Pending pd{&m, nullptr, sums_off, ctas, npts, c0, bp.wc, p0};
-                    sums_off += (size_t)bp.wc * (npts + 1) * 2;
-                    pd.d_partial = (u64*)c.alloc((size_t)ctas * bp.wc * (npts + 1) * 16);
-                    bp.partial = pd.d_partial;
+                    u64* d_partial = (u64*)c.alloc((size_t)ctas * bp.wc * (npts + 1) * 16);
+                    partials.push_back(d_partial);
+                    bp.partial = d_partial;
                     size_t smem = std::max((size_t)bp.rows_per_step * bp.wc * (npts + 1) * 16,
                                            (size_t)bp.tile_rows * (bp.wc * 8 + npts * 16));
                     {
@@ -518,36 +579,19 @@ static void evaluate_all(Ctx& c, msgpu_open* op) {
                     {
                         const u32 n = bp.wc * (npts + 1);
                         KLaunch kl(c, "k_bary_sum");
-                        k_bary_sum<<<(n * 32 + 127) / 128, 128, 0, c.stream>>>(pd.d_partial, ctas, n, d_sums.u() + pd.sums_off);
+                        k_bary_sum<<<(n * 32 + 127) / 128, 128, 0, c.stream>>>(d_partial, ctas, n, d_sums.u() + my_off);
                     }
                     MSG_CUDA(cudaGetLastError());
-                    pend.push_back(std::move(pd));
                 }
             }
         }
-    std::vector<u64> h_sums(std::max<size_t>(sums_total, 1));
-    if (sums_total) MSG_CUDA(cudaMemcpyAsync(h_sums.data(), d_sums.p, sums_total * 8, cudaMemcpyDeviceToHost, c.stream));  // ONE read-back
+    op->raw_sums.assign(std::max<size_t>(sums_total, 1), 0);
+    if (sums_total) MSG_CUDA(cudaMemcpyAsync(op->raw_sums.data(), d_sums.p, sums_total * 8, cudaMemcpyDeviceToHost, c.stream));  // ONE read-back
     c.sync();
-    for (auto& pd : pend) {
-        c.free(pd.d_partial);
-        auto& m = *pd.m;
-        u32 log_h = m.log_h - op->log_blowup;
-        // y = (z * S2 - S1) * (z^h - g^h) / (h * g^h),  g = GENERATOR
-        msh::Fp shift_pow = msh::Fp(msh::GL_GENERATOR).exp_power_of_2(log_h);
-        msh::Fp denom_inv = (shift_pow * msh::Fp((msh::u64)1 << log_h)).inverse();
-        const u32 nslots = pd.npts + 1;
-        msh::Fp2 scale[kMaxPts];
-        for (u32 k = 0; k < pd.npts; k++) scale[k] = (m.points[pd.p0 + k].exp_power_of_2(log_h) - shift_pow) * denom_inv;
-        const u64* hs = h_sums.data() + pd.sums_off;
-        for (u32 cc = 0; cc < pd.wc; cc++) {
-            msh::Fp s1 = msh::Fp(hs[((size_t)cc * nslots) * 2]);
-            for (u32 k = 0; k < pd.npts; k++) {
-                size_t o = ((size_t)cc * nslots + k + 1) * 2;
-                msh::Fp2 s2 = msh::Fp2(msh::Fp((msh::u64)hs[o]), msh::Fp((msh::u64)hs[o + 1]));
-                m.values[pd.p0 + k][pd.c0 + cc] = (m.points[pd.p0 + k] * s2 - s1) * scale[k];
-            }
-        }
-    }
+    op->raw_sums.resize(sums_total);
+    for (u64* pp : partials) c.free(pp);
+    // sharded: the sums of all ranks are added first (msgpu_open_sums / msgpu_open_finish_values)
+    if (!op->sharded) finish_values(op, op->raw_sums.data());
 }
 
 static void reduce_all(Ctx& c, msgpu_open* op, msh::Fp2 alpha) {
@@ -563,27 +607,38 @@ static void reduce_all(Ctx& c, msgpu_open* op, msh::Fp2 alpha) {
     DevBuf d_apow(c, apow_flat.size() * 8);
     MSG_CUDA(cudaMemcpyAsync(d_apow.p, apow_flat.data(), apow_flat.size() * 8, cudaMemcpyHostToDevice, c.stream));
     u64* ro[33] = {nullptr};
+    u64 ro_len[33] = {0};
     u64 num_reduced[33] = {0};
     ensure_max_smem(k_reduce_openings, 200 * 1024);
     for (auto& round : op->rounds)
         for (auto& m : round) {
             u32 lh = m.log_h;
-            if (!ro[lh]) {  // p3 creates the height's vector for every matrix of every round, opened or not
-                ro[lh] = (u64*)c.alloc(m.height * 16);
-                MSG_CUDA(cudaMemsetAsync(ro[lh], 0, m.height * 16, c.stream));
+            // the FRI owner keeps full-length vectors (the other ranks' shards are added into them); another rank only the
+            // rows it holds, and nothing for heights it has no rows of
+            const bool full = !op->sharded || op->fri_owner;
+            if (!ro[lh] && (full || m.rows)) {  // p3 creates the height's vector for every matrix of every round, opened or not
+                ro_len[lh] = full ? m.height : m.rows;
+                ro[lh] = (u64*)c.alloc(ro_len[lh] * 16);
+                MSG_CUDA(cudaMemsetAsync(ro[lh], 0, ro_len[lh] * 16, c.stream));
             }
             if (m.points.empty()) continue;
+            if (m.rows == 0) {  // lives elsewhere: only the alpha-power counter of its height advances
+                num_reduced[lh] += m.width * m.points.size();
+                continue;
+            }
+            MSG_REQUIRE(full || ro_len[lh] == m.rows, "open_reduce: shards of one height must cover the same rows");
             for (size_t p0 = 0; p0 < m.points.size(); p0 += kMaxPts) {
                 u32 npts = (u32)std::min<size_t>(kMaxPts, m.points.size() - p0);
                 ReduceParams rp{};
                 rp.M = m.ptr;
                 rp.apow = d_apow.u();
                 rp.ro = ro[lh];
-                rp.H = m.height;
+                rp.H = m.rows;
+                rp.ro_off = full ? m.row0 : 0;
                 rp.w = (u32)m.width;
                 rp.npts = npts;
                 for (u32 k = 0; k < npts; k++) {
-                    rp.invden[k] = find_invden(op, m.points[p0 + k], lh);
+                    rp.invden[k] = find_invden(op, m.points[p0 + k], m);
                     msh::Fp2 aoff = alpha.pow(num_reduced[lh]);
                     msh::Fp2 yred;
                     for (size_t cc = 0; cc < m.width; cc++) yred += apow[cc] * m.values[p0 + k][cc];
@@ -600,13 +655,13 @@ static void reduce_all(Ctx& c, msgpu_open* op, msh::Fp2 alpha) {
                 MSG_REQUIRE(smem <= 200 * 1024, "open: matrix too wide for the reduced-openings kernel (more than ~5000 columns)");
                 {
                     KLaunch kl(c, "k_reduce_openings");
-                    k_reduce_openings<<<(unsigned)((m.height + tr - 1) / tr), kRedThreads, smem, c.stream>>>(rp);
+                    k_reduce_openings<<<(unsigned)((m.rows + tr - 1) / tr), kRedThreads, smem, c.stream>>>(rp);
                 }
                 MSG_CUDA(cudaGetLastError());
             }
         }
     for (int lh = 32; lh >= 0; lh--)
-        if (ro[lh]) op->inputs.push_back(msgpu_open::Input{ro[lh], 1ull << lh});
+        if (ro[lh]) op->inputs.push_back(msgpu_open::Input{ro[lh], ro_len[lh]});
     c.sync();  // apow_flat (pageable) must outlive its copy
     MSG_REQUIRE(!op->inputs.empty(), "open: nothing to open");
     op->cur = op->inputs[0].ptr;
@@ -685,6 +740,52 @@ static void fri_fold_impl(msgpu_open* op, const msh::Fp2* beta, const FriChal* c
     op->cur_committed = false;
 }
 
+// shared by msgpu_open_begin / msgpu_open_begin_shard. modes[r] (sharded only): 0 = the round's matrices are here in full
+// (e.g. the quotient commitment on the rank that built it), 1 = this rank holds row shard `shard` of `n_shards` of every matrix
+// (the prover data holds the SHARDS: heights are 1 / n_shards of the matrices'), 2 = the round lives elsewhere (a placeholder
+// prover data carries the shapes).
+static void open_begin_impl(msgpu_ctx* h, uint64_t n_rounds, const msgpu_pdata* const* pds, const uint32_t* modes, uint32_t shard,
+                            uint32_t n_shards, int fri_owner, const uint64_t* n_points, const uint64_t* points, uint32_t log_blowup,
+                            msgpu_open** out, uint64_t* n_values) {
+    Ctx& c = h->c;
+    MSG_REQUIRE(pds && out && n_values, "open_begin: null argument");
+    auto op = std::unique_ptr<msgpu_open, void (*)(msgpu_open*)>(new msgpu_open(), [](msgpu_open* o) {
+        try { open_destroy(o); } catch (...) {}
+    });
+    op->ctx = &c;
+    op->log_blowup = log_blowup;
+    op->sharded = modes != nullptr;
+    op->fri_owner = fri_owner != 0;
+    size_t mi = 0, pi = 0;
+    u64 total = 0;
+    for (u64 r = 0; r < n_rounds; r++) {
+        MSG_REQUIRE(pds[r], "open_begin: null prover data");
+        const u32 mode = modes ? modes[r] : 0;
+        MSG_REQUIRE(mode <= 2, "open_begin: bad round mode");
+        std::vector<msgpu_open::Mat> round;
+        for (auto& pm : pds[r]->mats) {
+            const u64 gh = mode == 1 ? pm.height * n_shards : pm.height;
+            msgpu_open::Mat m{pm.ptr, gh, pm.width, ilog2(gh), {}, {}};
+            m.rows = mode == 2 ? 0 : pm.height;
+            m.row0 = mode == 1 ? (u64)shard * pm.height : 0;
+            MSG_REQUIRE(mode == 2 || pm.ptr || pm.width == 0, "open_begin: prover data without matrices (a placeholder needs mode 2)");
+            MSG_REQUIRE(m.log_h >= log_blowup, "open_begin: committed matrix shorter than the blowup");
+            u64 np = n_points[mi++];
+            for (u64 k = 0; k < np; k++, pi++) {
+                MSG_REQUIRE(points[2 * pi] < GLD_P && points[2 * pi + 1] < GLD_P, "open_begin: point is not canonical");
+                m.points.push_back(msh::Fp2(msh::Fp(points[2 * pi]), msh::Fp(points[2 * pi + 1])));
+            }
+            total += np * pm.width;
+            round.push_back(std::move(m));
+        }
+        op->rounds.push_back(std::move(round));
+    }
+    op->n_values = total;
+    evaluate_all(c, op.get());
+    *n_values = total;
+    *out = op.release();
+}
+
 }  // namespace msg
 
 using namespace msg;
@@ -693,36 +794,66 @@ extern "C" {
 
 int msgpu_open_begin(msgpu_ctx* h, uint64_t n_rounds, const msgpu_pdata* const* pds, const uint64_t* n_points,
                      const uint64_t* points, uint32_t log_blowup, msgpu_open** out, uint64_t* n_values) {
+    return guard([&] { open_begin_impl(h, n_rounds, pds, nullptr, 0, 1, 1, n_points, points, log_blowup, out, n_values); });
+}
+
+// ---- Pcs::open over ROW SHARDS (one proof over several GPUs) -----------------------------------------------------------------
+int msgpu_open_begin_shard(msgpu_ctx* h, uint64_t n_rounds, const msgpu_pdata* const* pds, const uint32_t* modes, uint32_t shard,
+                           uint32_t n_shards, int fri_owner, const uint64_t* n_points, const uint64_t* points, uint32_t log_blowup,
+                           msgpu_open** out, uint64_t* n_values, uint64_t* n_sums) {
+    return guard([&] {
+        MSG_REQUIRE(modes && n_sums && n_shards >= 1 && shard < n_shards && is_pow2(n_shards), "open_begin_shard: bad argument");
+        open_begin_impl(h, n_rounds, pds, modes, shard, n_shards, fri_owner, n_points, points, log_blowup, out, n_values);
+        *n_sums = (*out)->raw_sums.size();
+    });
+}
+int msgpu_open_sums(msgpu_open* op, uint64_t* out) {
+    return guard([&] {
+        MSG_REQUIRE(op && op->sharded && (out || op->raw_sums.empty()), "open_sums: not a sharded opening");
+        if (!op->raw_sums.empty()) memcpy(out, op->raw_sums.data(), op->raw_sums.size() * 8);
+    });
+}
+int msgpu_open_finish_values(msgpu_open* op, const uint64_t* total_sums) {
+    return guard([&] {
+        MSG_REQUIRE(op && op->sharded && !op->pending_sums.empty() && (total_sums || op->raw_sums.empty()), "open_finish_values: nothing pending");
+        for (size_t i = 0; i < op->raw_sums.size(); i++) MSG_REQUIRE(total_sums[i] < GLD_P, "open_finish_values: sum is not canonical");
+        finish_values(op, (const u64*)total_sums);
+    });
+}
+// prover data that carries shapes only (a round whose matrices live on other ranks)
+int msgpu_pdata_placeholder(msgpu_ctx* h, uint64_t n_mats, const uint64_t* heights, const uint64_t* widths, msgpu_pdata** out) {
+    return guard([&] {
+        MSG_REQUIRE(out && n_mats > 0 && heights && widths, "pdata_placeholder: bad argument");
+        msgpu_pdata* pd = new msgpu_pdata();
+        pd->ctx = &h->c;
+        for (u64 i = 0; i < n_mats; i++) {
+            if (!is_pow2(heights[i])) { delete pd; throw Error(-1, "pdata_placeholder: heights must be powers of two"); }
+            pd->mats.push_back(msgpu_pdata::Mat{nullptr, heights[i], widths[i], false});
+            pd->total_width += widths[i];
+            pd->max_height = std::max<u64>(pd->max_height, heights[i]);
+        }
+        memset(pd->root, 0, 32);
+        *out = pd;
+    });
+}
+// dst[i] += src[i] / v[i] += c over n extension elements (device pointers)
+int msgpu_ext_add_dev(msgpu_ctx* h, uint64_t* dst, const uint64_t* src, uint64_t n) {
     return guard([&] {
         Ctx& c = h->c;
-        MSG_REQUIRE(pds && out && n_values, "open_begin: null argument");
-        auto op = std::unique_ptr<msgpu_open, void (*)(msgpu_open*)>(new msgpu_open(), [](msgpu_open* o) {
-            try { open_destroy(o); } catch (...) {}
-        });
-        op->ctx = &c;
-        op->log_blowup = log_blowup;
-        size_t mi = 0, pi = 0;
-        u64 total = 0;
-        for (u64 r = 0; r < n_rounds; r++) {
-            MSG_REQUIRE(pds[r], "open_begin: null prover data");
-            std::vector<msgpu_open::Mat> round;
-            for (auto& pm : pds[r]->mats) {
-                msgpu_open::Mat m{pm.ptr, pm.height, pm.width, ilog2(pm.height), {}, {}};
-                MSG_REQUIRE(m.log_h >= log_blowup, "open_begin: committed matrix shorter than the blowup");
-                u64 np = n_points[mi++];
-                for (u64 k = 0; k < np; k++, pi++) {
-                    MSG_REQUIRE(points[2 * pi] < GLD_P && points[2 * pi + 1] < GLD_P, "open_begin: point is not canonical");
-                    m.points.push_back(msh::Fp2(msh::Fp(points[2 * pi]), msh::Fp(points[2 * pi + 1])));
-                }
-                total += np * pm.width;
-                round.push_back(std::move(m));
-            }
-            op->rounds.push_back(std::move(round));
-        }
-        op->n_values = total;
-        evaluate_all(c, op.get());
-        *n_values = total;
-        *out = op.release();
+        if (n == 0) return;
+        KLaunch kl(c, "k_ext_add");
+        k_ext_add<<<(unsigned)((2 * n + 255) / 256), 256, 0, c.stream>>>((u64*)dst, (const u64*)src, n);
+        MSG_CUDA(cudaGetLastError());
+    });
+}
+int msgpu_ext_add_scalar_dev(msgpu_ctx* h, uint64_t* v, uint64_t n, const uint64_t* c2) {
+    return guard([&] {
+        Ctx& c = h->c;
+        MSG_REQUIRE(c2 && c2[0] < GLD_P && c2[1] < GLD_P, "ext_add_scalar: constant is not canonical");
+        if (n == 0) return;
+        KLaunch kl(c, "k_ext_add_scalar");
+        k_ext_add_scalar<<<(unsigned)((2 * n + 255) / 256), 256, 0, c.stream>>>((u64*)v, n, gl::e2{c2[0], c2[1]});
+        MSG_CUDA(cudaGetLastError());
     });
 }
 

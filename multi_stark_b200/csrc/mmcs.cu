@@ -254,6 +254,63 @@ __global__ void __launch_bounds__(256) k_interleave_columns(const __grid_constan
     }
 }
 
+// blocks[b][r][c] = in[r][col0_b + c]: the inverse (row block -> per-destination column blocks, back to back in `out`)
+struct PackParams {
+    const u64* in;
+    u64* out;
+    u32 col0[kMaxBlocks + 1];
+    u32 n_blocks;
+    u64 rows;
+};
+__global__ void __launch_bounds__(256) k_pack_columns(const __grid_constant__ PackParams p) {
+    const u32 W = p.col0[p.n_blocks];
+    const u64 total = p.rows * W;
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (u64)gridDim.x * blockDim.x) {
+        const u64 r = e / W;
+        const u32 col = (u32)(e % W);
+        u32 b = 0;
+        while (b + 1 < p.n_blocks && p.col0[b + 1] <= col) b++;
+        const u32 wb = p.col0[b + 1] - p.col0[b];
+        p.out[p.rows * p.col0[b] + r * wb + (col - p.col0[b])] = p.in[e];
+    }
+}
+void pack_column_blocks(Ctx& c, const u64* src, u64 rows, u64 width, const std::vector<u64>& c0, const std::vector<u64>& c1, u64* dst) {
+    MSG_REQUIRE(!c0.empty() && c0.size() == c1.size() && c0.size() <= (size_t)kMaxBlocks, "pack_column_blocks: 1..16 blocks");
+    PackParams pp{};
+    pp.in = src;
+    pp.out = dst;
+    pp.n_blocks = (u32)c0.size();
+    pp.rows = rows;
+    for (size_t b = 0; b < c0.size(); b++) {
+        MSG_REQUIRE(c0[b] == (b ? c1[b - 1] : 0) && c1[b] >= c0[b], "pack_column_blocks: blocks must tile the columns in order");
+        pp.col0[b] = (u32)c0[b];
+    }
+    MSG_REQUIRE(c1.back() == width, "pack_column_blocks: blocks must cover every column");
+    pp.col0[c0.size()] = (u32)width;
+    if (rows * width == 0) return;
+    KLaunch kl(c, "k_pack_columns");
+    k_pack_columns<<<(unsigned)std::min<u64>((rows * width + 255) / 256, (u64)c.sm_count * 16), 256, 0, c.stream>>>(pp);
+    MSG_CUDA(cudaGetLastError());
+}
+void interleave_column_blocks(Ctx& c, const u64* src, u64 rows, const std::vector<u64>& widths, u64* dst) {
+    MSG_REQUIRE(!widths.empty() && widths.size() <= (size_t)kMaxBlocks, "interleave_column_blocks: 1..16 blocks");
+    InterleaveParams ip{};
+    ip.n_blocks = (u32)widths.size();
+    ip.rows = rows;
+    ip.out = dst;
+    u64 W = 0;
+    for (size_t b = 0; b < widths.size(); b++) {
+        ip.blocks[b] = src + rows * W;
+        ip.col0[b] = (u32)W;
+        W += widths[b];
+    }
+    ip.col0[widths.size()] = (u32)W;
+    if (rows * W == 0) return;
+    KLaunch kl(c, "k_interleave_columns");
+    k_interleave_columns<<<(unsigned)std::min<u64>((rows * W + 255) / 256, (u64)c.sm_count * 16), 256, 0, c.stream>>>(ip);
+    MSG_CUDA(cudaGetLastError());
+}
+
 void mmcs_from_parts(Ctx& c, msgpu_pdata* pd, const std::vector<const u64*>& blocks, const std::vector<u64>& widths, u64 height,
                      const std::vector<const uint8_t*>& part_digests) {
     const u64 n_parts = part_digests.size();

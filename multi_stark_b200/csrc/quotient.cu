@@ -197,7 +197,13 @@ struct QuotParams {
     const u64 *pre, *s1, *s2;
     const u64* apow;  // constraint_count x 2: weight of constraint j = alpha^{k-1-j}
     const u64 *sel_first, *sel_last, *inv_zh;
-    u64* out;  // nq x 2, natural order
+    u64* out;  // nq x 2, natural order (or n_local x 2 in stored order when out_stored)
+    // Row shards (one proof over several GPUs): the cur pointers address stored rows [row0, row0 + n_local) of the quotient
+    // domain, the *_n pointers the shard that holds the NEXT rows, stored rows [next_row0, ...). Unsharded: row0 = next_row0 = 0,
+    // n_local = nq and the next pointers equal the cur ones.
+    const u64 *pre_n, *s1_n, *s2_n;
+    u64 row0, n_local, next_row0;
+    u32 out_stored;
     gl::PowTable xtab;
     u64 publics[8];
     u64 delta[2];
@@ -210,18 +216,19 @@ struct QuotParams {
 template <int NSLOT>
 __global__ void __launch_bounds__(128) k_quotient_eval(QuotParams p) {
     const u64 nq = 1ull << p.log_nq;
-    const u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nq) return;
+    const u64 sl = (u64)blockIdx.x * blockDim.x + threadIdx.x;  // local row
+    if (sl >= p.n_local) return;
+    const u64 s = p.row0 + sl;
     const u64 i = gl::rev_bits((u32)s, p.log_nq);
     const u64 inext = (i + (1ull << p.log_q)) & (nq - 1);
-    const u64 sn = gl::rev_bits((u32)inext, p.log_nq);
+    const u64 sn = gl::rev_bits((u32)inext, p.log_nq) - p.next_row0;  // inside the shard the next pointers address
     RowCtx cx;
-    cx.rows[0][0] = p.pre + s * p.wpre;
-    cx.rows[0][1] = p.pre + sn * p.wpre;
-    cx.rows[1][0] = p.s1 + s * p.w1;
-    cx.rows[1][1] = p.s1 + sn * p.w1;
-    cx.rows[2][0] = p.s2 + s * p.w2;
-    cx.rows[2][1] = p.s2 + sn * p.w2;
+    cx.rows[0][0] = p.pre + sl * p.wpre;
+    cx.rows[0][1] = p.pre_n + sn * p.wpre;
+    cx.rows[1][0] = p.s1 + sl * p.w1;
+    cx.rows[1][1] = p.s1_n + sn * p.w1;
+    cx.rows[2][0] = p.s2 + sl * p.w2;
+    cx.rows[2][1] = p.s2_n + sn * p.w2;
     cx.publics = p.publics;
     cx.first = p.sel_first[s];
     cx.last = p.sel_last[s];
@@ -264,8 +271,9 @@ __global__ void __launch_bounds__(128) k_quotient_eval(QuotParams p) {
         }
     }
     const u64 iv = p.inv_zh[i & ((1ull << p.log_q) - 1)];
-    p.out[2 * i] = gl::mul(gl::acc_reduce(fa0), iv);
-    p.out[2 * i + 1] = gl::mul(gl::acc_reduce(fa1), iv);
+    const u64 o = p.out_stored ? sl : i;
+    p.out[2 * o] = gl::mul(gl::acc_reduce(fa0), iv);
+    p.out[2 * o + 1] = gl::mul(gl::acc_reduce(fa1), iv);
 }
 
 // out[r][k*d + c] = S[rev((N - (k*n + r)) mod N)][c] * weights[k]     (src/prover.rs:659-677)
@@ -865,6 +873,88 @@ void msgpu_claims_free(msgpu_claims* cl) {
     delete cl;
 }
 
+}  // extern "C"
+
+namespace msg {
+// k_quotient_eval over stored rows [row0, row0 + n_local) of the quotient domain. cur[3] / nxt[3]: pre, stage 1, stage 2 row
+// pointers of the local rows / of the shard holding the next rows (first stored row next_row0).
+static void quotient_eval(Ctx& c, const msgpu_program* prog, const u64* const cur[3], const u64* const nxt[3], u64 row0, u64 n_local,
+                          u64 next_row0, u32 log_n, u32 log_q, const uint64_t* publics8, const uint64_t* alpha2, u64* out, bool out_stored) {
+    const u32 log_nq = log_n + log_q;
+    const u64 n = 1ull << log_n;
+    for (int i = 0; i < 8; i++) MSG_REQUIRE(publics8[i] < GLD_P, "quotient: public value is not canonical");
+    QuotParams qp{};
+    qp.pre = cur[0]; qp.s1 = cur[1]; qp.s2 = cur[2];
+    qp.pre_n = nxt[0]; qp.s1_n = nxt[1]; qp.s2_n = nxt[2];
+    qp.row0 = row0; qp.n_local = n_local; qp.next_row0 = next_row0; qp.out_stored = out_stored ? 1u : 0u;
+    SelCache sel = selectors(c, log_n, log_q);
+    // alpha powers reversed (src/prover.rs:798-808): constraint j of k weighted by alpha^{k-1-j}
+    u32 k = prog->n_zeros + 2 * std::max<u32>(prog->n_lookups, 1);
+    std::vector<u64> apow(2 * (size_t)k);
+    msh::Fp2 alpha{msh::Fp(alpha2[0]), msh::Fp(alpha2[1])}, acc = msh::Fp2::one();
+    for (u32 j = 0; j < k; j++) {
+        apow[2 * (size_t)(k - 1 - j)] = acc.c[0].v;
+        apow[2 * (size_t)(k - 1 - j) + 1] = acc.c[1].v;
+        acc *= alpha;
+    }
+    DevBuf d_apow(c, apow.size() * 8);
+    MSG_CUDA(cudaMemcpyAsync(d_apow.p, apow.data(), apow.size() * 8, cudaMemcpyHostToDevice, c.stream));
+    msh::Fp inj_norm = (msh::Fp((msh::u64)n) * msh::two_adic_generator(log_n)).inverse();
+    qp.prog = prog->d_full;
+    qp.n_instr = prog->n_full;
+    qp.zero_slots = prog->d_zero_slots;
+    qp.n_zeros = prog->n_zeros;
+    qp.n_lookups = prog->n_lookups;
+    qp.lk_mult = prog->d_mult_full;
+    qp.lk_argoff = prog->d_arg_off;
+    qp.lk_args = prog->d_args_full;
+    qp.wpre = prog->pre_width;
+    qp.w1 = prog->main_width;
+    qp.w2 = prog->stage2_width;
+    qp.apow = d_apow.u();
+    qp.sel_first = sel.first;
+    qp.sel_last = sel.last;
+    qp.inv_zh = sel.inv_zh;
+    qp.out = out;
+    qp.xtab = coset_x_table(c, log_nq);
+    for (int i = 0; i < 8; i++) qp.publics[i] = publics8[i];
+    qp.delta[0] = ((msh::Fp(publics8[6]) - msh::Fp(publics8[4])) * inj_norm).v;
+    qp.delta[1] = ((msh::Fp(publics8[7]) - msh::Fp(publics8[5])) * inj_norm).v;
+    qp.g_inv = msh::two_adic_generator(log_n).inverse().v;
+    qp.log_nq = log_nq;
+    qp.log_q = log_q;
+    if (n_local) {
+        launch_by_slots(prog->slots_full, [&](auto ns) {
+            KLaunch kl(c, "k_quotient_eval");
+            k_quotient_eval<decltype(ns)::value><<<(unsigned)((n_local + 127) / 128), kInterpThreads, 0, c.stream>>>(qp);
+        });
+        MSG_CUDA(cudaGetLastError());
+    }
+    c.sync();  // apow (pageable) must outlive the copy; also surfaces kernel faults here
+}
+
+// quotient evaluations in natural order (nq x 2, device; overwritten) -> LDE of the shifted slices (src/prover.rs:631-717)
+static u64* quotient_finish(Ctx& c, u64* qv, u32 log_n, u32 log_q, u32 log_blowup) {
+    const u32 log_nq = log_n + log_q;
+    const u64 nq = 1ull << log_nq, n = 1ull << log_n, q = 1ull << log_q;
+    // shifted_quotient_slices: one DFT of the nq x 2 matrix + gather; then the LDE from coefficients
+    ntt_dft_bitrev(c, qv, qv, nq, 2, false);
+    DevBuf sl(c, n * q * 16);
+    quotient_slices(c, qv, sl.u(), log_nq, log_n, 2);
+    u64* lde = (u64*)c.alloc((n << log_blowup) * q * 16);
+    try {
+        ntt_lde_from_coeffs(c, sl.u(), lde, n, 2 * q, log_blowup);
+        c.sync();
+    } catch (...) {
+        c.free(lde);
+        throw;
+    }
+    return lde;
+}
+}  // namespace msg
+
+extern "C" {
+
 int msgpu_quotient(msgpu_ctx* h, const msgpu_program* prog, const msgpu_pdata* pd_pre, uint64_t idx_pre,
                    const msgpu_pdata* pd_s1, uint64_t idx_s1, const msgpu_pdata* pd_s2, uint64_t idx_s2, uint32_t log_n,
                    uint32_t log_q, uint32_t log_blowup, const uint64_t* publics8, const uint64_t* alpha2,
@@ -875,72 +965,55 @@ int msgpu_quotient(msgpu_ctx* h, const msgpu_program* prog, const msgpu_pdata* p
         MSG_REQUIRE(prog && pd_s1 && pd_s2 && publics8 && alpha2 && lde_out_dev, "quotient: null argument");
         MSG_REQUIRE(log_q <= log_blowup, "quotient: quotient degree exceeds the blowup");
         MSG_REQUIRE(log_n + log_blowup <= 32, "quotient: domain exceeds the two-adicity of the field");
-        const u32 log_nq = log_n + log_q;
-        const u64 nq = 1ull << log_nq, n = 1ull << log_n, q = 1ull << log_q;
-        QuotParams qp{};
-        qp.pre = nullptr;
+        const u64 nq = 1ull << (log_n + log_q);
+        const u64* cur[3] = {nullptr, nullptr, nullptr};
         if (prog->pre_width) {
             MSG_REQUIRE(pd_pre, "quotient: circuit has a preprocessed trace but no preprocessed commitment was given");
-            view_of(pd_pre, idx_pre, nq, prog->pre_width, &qp.pre);
+            view_of(pd_pre, idx_pre, nq, prog->pre_width, &cur[0]);
         }
-        view_of(pd_s1, idx_s1, nq, prog->main_width, &qp.s1);
-        view_of(pd_s2, idx_s2, nq, prog->stage2_width, &qp.s2);
-        for (int i = 0; i < 8; i++) MSG_REQUIRE(publics8[i] < GLD_P, "quotient: public value is not canonical");
-        SelCache sel = selectors(c, log_n, log_q);
-        // alpha powers reversed (src/prover.rs:798-808): constraint j of k weighted by alpha^{k-1-j}
-        u32 k = prog->n_zeros + 2 * std::max<u32>(prog->n_lookups, 1);
-        std::vector<u64> apow(2 * (size_t)k);
-        msh::Fp2 alpha{msh::Fp(alpha2[0]), msh::Fp(alpha2[1])}, acc = msh::Fp2::one();
-        for (u32 j = 0; j < k; j++) {
-            apow[2 * (size_t)(k - 1 - j)] = acc.c[0].v;
-            apow[2 * (size_t)(k - 1 - j) + 1] = acc.c[1].v;
-            acc *= alpha;
+        view_of(pd_s1, idx_s1, nq, prog->main_width, &cur[1]);
+        view_of(pd_s2, idx_s2, nq, prog->stage2_width, &cur[2]);
+        DevBuf qv(c, nq * 16);
+        quotient_eval(c, prog, cur, cur, 0, nq, 0, log_n, log_q, publics8, alpha2, qv.u(), false);
+        if (quotient_values_out) {
+            MSG_CUDA(cudaMemcpyAsync(quotient_values_out, qv.p, nq * 16, cudaMemcpyDeviceToHost, c.stream));
+            c.sync();
         }
-        DevBuf d_apow(c, apow.size() * 8), qv(c, nq * 16);
-        MSG_CUDA(cudaMemcpyAsync(d_apow.p, apow.data(), apow.size() * 8, cudaMemcpyHostToDevice, c.stream));
-        msh::Fp inj_norm = (msh::Fp((msh::u64)n) * msh::two_adic_generator(log_n)).inverse();
-        qp.prog = prog->d_full;
-        qp.n_instr = prog->n_full;
-        qp.zero_slots = prog->d_zero_slots;
-        qp.n_zeros = prog->n_zeros;
-        qp.n_lookups = prog->n_lookups;
-        qp.lk_mult = prog->d_mult_full;
-        qp.lk_argoff = prog->d_arg_off;
-        qp.lk_args = prog->d_args_full;
-        qp.wpre = prog->pre_width;
-        qp.w1 = prog->main_width;
-        qp.w2 = prog->stage2_width;
-        qp.apow = d_apow.u();
-        qp.sel_first = sel.first;
-        qp.sel_last = sel.last;
-        qp.inv_zh = sel.inv_zh;
-        qp.out = qv.u();
-        qp.xtab = coset_x_table(c, log_nq);
-        for (int i = 0; i < 8; i++) qp.publics[i] = publics8[i];
-        qp.delta[0] = ((msh::Fp(publics8[6]) - msh::Fp(publics8[4])) * inj_norm).v;
-        qp.delta[1] = ((msh::Fp(publics8[7]) - msh::Fp(publics8[5])) * inj_norm).v;
-        qp.g_inv = msh::two_adic_generator(log_n).inverse().v;
-        qp.log_nq = log_nq;
-        qp.log_q = log_q;
-        launch_by_slots(prog->slots_full, [&](auto ns) {
-            KLaunch kl(c, "k_quotient_eval");
-            k_quotient_eval<decltype(ns)::value><<<(unsigned)((nq + 127) / 128), kInterpThreads, 0, c.stream>>>(qp);
-        });
-        MSG_CUDA(cudaGetLastError());
-        if (quotient_values_out) MSG_CUDA(cudaMemcpyAsync(quotient_values_out, qv.p, nq * 16, cudaMemcpyDeviceToHost, c.stream));
-        // shifted_quotient_slices: one DFT of the nq x 2 matrix + gather; then the LDE from coefficients
-        ntt_dft_bitrev(c, qv.u(), qv.u(), nq, 2, false);
-        DevBuf sl(c, n * q * 16);
-        quotient_slices(c, qv.u(), sl.u(), log_nq, log_n, 2);
-        u64* lde = (u64*)c.alloc((n << log_blowup) * q * 16);
-        try {
-            ntt_lde_from_coeffs(c, sl.u(), lde, n, 2 * q, log_blowup);
-            c.sync();  // apow (pageable) must outlive the copy; also surfaces kernel faults here
-        } catch (...) {
-            c.free(lde);
-            throw;
-        }
-        *lde_out_dev = (uint64_t*)lde;
+        *lde_out_dev = (uint64_t*)quotient_finish(c, qv.u(), log_n, log_q, log_blowup);
+    });
+}
+
+// ---- the quotient stage over ROW SHARDS (one proof over several GPUs) -------------------------------------------------------
+// values_shard: this rank's stored rows [row0, row0 + n_local) of the quotient domain (the first n*q stored rows of the committed
+// LDEs). cur3 / next3: DEVICE pointers (pre, stage 1, stage 2; pre may be NULL) to the local rows and to the shard that holds
+// the rows one trace step further (stored rows from next_row0 on; the caller fetched it from its owner -- for the local shard
+// itself pass the cur pointers and row0). out_dev: n_local x 2 quotient evaluations in STORED order.
+int msgpu_quotient_values_shard(msgpu_ctx* h, const msgpu_program* prog, const uint64_t* const* cur3, const uint64_t* const* next3,
+                                uint64_t row0, uint64_t n_local, uint64_t next_row0, uint32_t log_n, uint32_t log_q,
+                                const uint64_t* publics8, const uint64_t* alpha2, uint64_t* out_dev) {
+    return guard([&] {
+        Ctx& c = h->c;
+        StageScope ss(c, "quotient");
+        MSG_REQUIRE(prog && cur3 && next3 && publics8 && alpha2 && (out_dev || n_local == 0), "quotient_values_shard: null argument");
+        MSG_REQUIRE(log_n + log_q <= 32 && row0 + n_local <= (1ull << (log_n + log_q)), "quotient_values_shard: rows outside the quotient domain");
+        MSG_REQUIRE((prog->pre_width == 0 || (cur3[0] && next3[0])) && cur3[1] && cur3[2] && next3[1] && next3[2], "quotient_values_shard: missing matrix");
+        const u64* cur[3] = {(const u64*)cur3[0], (const u64*)cur3[1], (const u64*)cur3[2]};
+        const u64* nxt[3] = {(const u64*)next3[0], (const u64*)next3[1], (const u64*)next3[2]};
+        quotient_eval(c, prog, cur, nxt, row0, n_local, next_row0, log_n, log_q, publics8, alpha2, (u64*)out_dev, true);
+    });
+}
+// values_stored_dev: ALL nq x 2 quotient evaluations in stored (bit-reversed) order, gathered from the shards (device, not
+// modified). Returns the quotient LDE as msgpu_quotient does.
+int msgpu_quotient_finish(msgpu_ctx* h, const uint64_t* values_stored_dev, uint32_t log_n, uint32_t log_q, uint32_t log_blowup,
+                          uint64_t** lde_out_dev) {
+    return guard([&] {
+        Ctx& c = h->c;
+        StageScope ss(c, "quotient");
+        MSG_REQUIRE(values_stored_dev && lde_out_dev && log_q <= log_blowup && log_n + log_blowup <= 32, "quotient_finish: bad argument");
+        const u64 nq = 1ull << (log_n + log_q);
+        DevBuf qv(c, nq * 16);
+        ntt_bit_reverse_rows(c, (const u64*)values_stored_dev, qv.u(), nq, 2);
+        *lde_out_dev = (uint64_t*)quotient_finish(c, qv.u(), log_n, log_q, log_blowup);
     });
 }
 

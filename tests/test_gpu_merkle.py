@@ -160,3 +160,35 @@ def test_upload_canonical_rejects_out_of_range(gpu):
         a[4321] = bad
         with pytest.raises(ms.MsgpuError):
             ctx.upload_canonical(a)
+
+
+@pytest.mark.parametrize("log_n,w,lb", [(22, 14, 1), (22, 1, 2), (23, 4, 1), (24, 1, 1), (24, 4, 1), (24, 14, 1), (18, 256, 2)])
+def test_commit_root_bit_exact_at_full_sizes(gpu, oracle, log_n, w, lb):
+    """Bit-exact Pcs::commit roots against the CPU oracle at the sizes of BASELINE configs[4] (2^22 .. 2^24 rows: the three- and
+    four-pass NTT plans 8/7/7, 8/8/7, 8/8/8 and the fused middle pass at tb = 7, 8) and of configs[2] (256 columns: two BLAKE3
+    chunks per leaf). The root binds every LDE row, so root equality is LDE equality; a sample of rows is compared as well."""
+    ms, ctx = gpu
+    rng = np.random.default_rng(log_n * 100 + w)
+    m = orc.rand_matrix(rng, 1 << log_n, w)
+    m[0, :] = P - 1
+    want_root, h = orc.pcs_commit(oracle, [m], lb)
+    pcs = ms.GpuPcs(ctx, lb)
+    root, pd = pcs.commit([m])
+    assert bytes(root) == want_root
+    rows = (1 << log_n) << lb
+    for r0 in (0, rows // 2 - 3, rows - 8):
+        got = pd.read_rows(0, r0, 8)
+        # the oracle handle keeps its LDE: compare through its opening API
+        for k in range(8):
+            opened, _ = _orc_open(oracle, h, r0 + k, w, rows)
+            assert np.array_equal(got[k], opened)
+    oracle.orc_mmcs_free(h)
+    pd.free()
+
+
+def _orc_open(L, h, index, width, rows):
+    opened = np.zeros(width, dtype=np.uint64)
+    depth = rows.bit_length() - 1
+    proof = np.zeros((max(depth, 1), 32), dtype=np.uint8)
+    L.orc_mmcs_open(h, index, opened, proof)
+    return opened, proof[:depth]
