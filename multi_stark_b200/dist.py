@@ -110,12 +110,14 @@ import ctypes as _C  # noqa: E402
 _ALLGATHER = _C.CFUNCTYPE(_C.c_int, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_uint64)
 _BCAST = _C.CFUNCTYPE(_C.c_int, _C.c_void_p, _C.c_void_p, _C.c_uint64, _C.c_int32)
 _SENDRECV = _C.CFUNCTYPE(_C.c_int, _C.c_void_p, _C.c_void_p, _C.c_uint64, _C.c_int32, _C.c_int32)
+_ALLTOALL = _C.CFUNCTYPE(_C.c_int, _C.c_void_p, _C.c_void_p, _C.POINTER(_C.c_uint64), _C.c_void_p, _C.POINTER(_C.c_uint64))
+_ALLGATHER_DEV = _C.CFUNCTYPE(_C.c_int, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_uint64)
 
 
 class MshComm(_C.Structure):
     """`msh_comm` of host/dist_backend.hpp"""
     _fields_ = [("user", _C.c_void_p), ("rank", _C.c_int32), ("world", _C.c_int32), ("allgather_host", _ALLGATHER),
-                ("bcast_host", _BCAST), ("sendrecv_dev", _SENDRECV)]
+                ("bcast_host", _BCAST), ("sendrecv_dev", _SENDRECV), ("alltoall_dev", _ALLTOALL), ("allgather_dev", _ALLGATHER_DEV)]
 
 
 class _DevView:
@@ -144,7 +146,14 @@ class TorchComm:
         self.seconds = {}    # wall time spent inside the callbacks, by kind
         self._stage = None
         self.trace = bool(os.environ.get("MSH_TRACE"))
-        self._cb = (_ALLGATHER(self._allgather), _BCAST(self._bcast), _SENDRECV(self._sendrecv))  # keep the thunks alive
+        if self.nccl:
+            # NCCL calls are ordered against torch's CURRENT stream, the library's kernels against the context's: they must be
+            # the same stream, or a send could leave before the kernel that fills the buffer has run
+            cur = torch.cuda.current_stream().cuda_stream
+            if int(ctx.stream or 0) != int(cur):
+                raise ValueError("TorchComm: create the GpuContext on torch's current stream (GpuContext(dev, stream=torch.cuda.current_stream().cuda_stream))")
+        self._cb = (_ALLGATHER(self._allgather), _BCAST(self._bcast), _SENDRECV(self._sendrecv), _ALLTOALL(self._alltoall_cb),
+                    _ALLGATHER_DEV(self._allgather_dev_cb))  # keep the thunks alive
         self.struct = MshComm(None, self.rank, self.world, *self._cb)
 
     # ---- host buffers
@@ -265,8 +274,9 @@ def _all_to_all_dev(self, send_ptr, send_counts, recv_ptr, recv_counts):
     self.bytes_dev += sum(send_counts) - send_counts[self.rank] + sum(recv_counts) - recv_counts[self.rank]
     if self.nccl:
         dev = torch.device("cuda", torch.cuda.current_device())
-        s = torch.as_tensor(_DevView(send_ptr, sum(send_counts)), device=dev)
-        r = torch.as_tensor(_DevView(recv_ptr, sum(recv_counts)), device=dev)
+        empty = torch.empty(0, dtype=torch.uint8, device=dev)
+        s = torch.as_tensor(_DevView(send_ptr, sum(send_counts)), device=dev) if sum(send_counts) else empty
+        r = torch.as_tensor(_DevView(recv_ptr, sum(recv_counts)), device=dev) if sum(recv_counts) else empty
         self.dist.all_to_all_single(r, s, output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts), group=self.group)
         torch.cuda.current_stream().synchronize()
     else:  # gloo: staged through the host, pairwise
@@ -274,21 +284,65 @@ def _all_to_all_dev(self, send_ptr, send_counts, recv_ptr, recv_counts):
         ro = [sum(recv_counts[:k]) for k in range(self.world)]
         host_s = torch.empty(max(sum(send_counts), 1), dtype=torch.uint8)
         host_r = torch.empty(max(sum(recv_counts), 1), dtype=torch.uint8)
-        check(self.ctx.L.msgpu_memcpy_d2h(self.ctx.h, _C.c_void_p(host_s.data_ptr()), _C.c_void_p(send_ptr), sum(send_counts)))
+        if sum(send_counts):
+            check(self.ctx.L.msgpu_memcpy_d2h(self.ctx.h, _C.c_void_p(host_s.data_ptr()), _C.c_void_p(send_ptr), sum(send_counts)))
         reqs = []
         for k in range(self.world):
             if k == self.rank:
                 host_r[ro[k]:ro[k] + recv_counts[k]] = host_s[so[k]:so[k] + send_counts[k]]
                 continue
-            reqs.append(self.dist.isend(host_s[so[k]:so[k] + send_counts[k]], dst=self._global(k), group=self.group))
-            reqs.append(self.dist.irecv(host_r[ro[k]:ro[k] + recv_counts[k]], src=self._global(k), group=self.group))
+            if send_counts[k]:
+                reqs.append(self.dist.isend(host_s[so[k]:so[k] + send_counts[k]], dst=self._global(k), group=self.group))
+            if recv_counts[k]:
+                reqs.append(self.dist.irecv(host_r[ro[k]:ro[k] + recv_counts[k]], src=self._global(k), group=self.group))
         for q in reqs:
             q.wait()
-        check(self.ctx.L.msgpu_memcpy_h2d(self.ctx.h, _C.c_void_p(recv_ptr), _C.c_void_p(host_r.data_ptr()), sum(recv_counts)))
+        if sum(recv_counts):
+            check(self.ctx.L.msgpu_memcpy_h2d(self.ctx.h, _C.c_void_p(recv_ptr), _C.c_void_p(host_r.data_ptr()), sum(recv_counts)))
     self.seconds["all_to_all"] = self.seconds.get("all_to_all", 0.0) + time.perf_counter() - t0
 
 
 TorchComm.all_to_all_dev = _all_to_all_dev
+
+
+def _alltoall_cb(self, user, send, send_bytes, recv, recv_bytes):
+    try:
+        self.all_to_all_dev(int(send or 0), [int(send_bytes[k]) for k in range(self.world)], int(recv or 0),
+                            [int(recv_bytes[k]) for k in range(self.world)])
+        return 0
+    except Exception as e:  # never unwind into C++
+        self.errors.append(repr(e))
+        return 1
+
+
+def _allgather_dev_cb(self, user, send, recv, nbytes):
+    """Device all-gather of equal chunks: recv = world chunks of nbytes in rank order."""
+    t0 = time.perf_counter()
+    try:
+        nbytes = int(nbytes)
+        self.bytes_dev += nbytes * (self.world - 1) * 2
+        if self.nccl:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            s = torch.as_tensor(_DevView(send, nbytes), device=dev)
+            r = torch.as_tensor(_DevView(recv, nbytes * self.world), device=dev)
+            self.dist.all_gather_into_tensor(r, s, group=self.group)
+            torch.cuda.current_stream().synchronize()
+        else:  # gloo: staged through the host
+            hs = torch.empty(nbytes, dtype=torch.uint8)
+            hr = torch.empty(nbytes * self.world, dtype=torch.uint8)
+            check(self.ctx.L.msgpu_memcpy_d2h(self.ctx.h, _C.c_void_p(hs.data_ptr()), _C.c_void_p(send), nbytes))
+            self.dist.all_gather_into_tensor(hr, hs, group=self.group)
+            check(self.ctx.L.msgpu_memcpy_h2d(self.ctx.h, _C.c_void_p(recv), _C.c_void_p(hr.data_ptr()), nbytes * self.world))
+        return 0
+    except Exception as e:
+        self.errors.append(repr(e))
+        return 1
+    finally:
+        self.seconds["allgather_dev"] = self.seconds.get("allgather_dev", 0.0) + time.perf_counter() - t0
+
+
+TorchComm._alltoall_cb = _alltoall_cb
+TorchComm._allgather_dev_cb = _allgather_dev_cb
 
 
 def assign_owners(heights, world_size):
@@ -350,6 +404,58 @@ class DistProver:
                                    for i, m in enumerate(mats)])
         hs = (_C.c_uint64 * n)(*[int(h) for h in heights])
         cl = np.ascontiguousarray(claims, dtype=np.uint64)
+        if cl.ndim != 2:
+            raise ValueError("claims: an (n, len) array is expected")
+        flat = cl.reshape(-1) if cl.size else np.zeros(1, dtype=np.uint64)
+        out, ln = _C.c_void_p(), _C.c_uint64()
+        ms = (_C.c_double * 6)()
+        rc = self.H.msh_prove(self.h, ptrs, hs, flat.ctypes.data_as(_ffi.c_u64p), None, cl.shape[1], cl.shape[0],
+                              _C.byref(out), _C.byref(ln), ms)
+        if rc != 0:
+            raise _ffi.MsgpuError(rc, (self.H.msh_last_error() or b"").decode() + " " + "; ".join(self.comm.errors))
+        data = _C.string_at(out.value, ln.value)
+        self.H.msh_bytes_free(out)
+        self.last_stage_ms = dict(zip(STAGE_NAMES, ms))
+        return data
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.H.msh_prover_free(self.h)
+            self.h = None
+
+
+class RowShardProver:
+    """`System::prove_multiple_claims` as ONE proof over the ROW SHARDS of every committed matrix (host/rowshard_backend.hpp):
+    rank d of N holds rows [d H / N, (d + 1) H / N) of every LDE, so a single tall circuit is proved by all GPUs. Every rank
+    passes ALL traces (it reads only its row block of the tall ones); the proof bytes are identical on every rank and identical
+    to the single-GPU proof."""
+
+    def __init__(self, ctx, system, group=None):
+        from . import _ffi
+        self.H = _ffi.host_lib()
+        self.ctx, self.system = ctx, system
+        self.comm = TorchComm(ctx, group)
+        self.h = self.H.msh_rowshard_prover_create(system.h, ctx.h, _C.byref(self.comm.struct))
+        if not self.h:
+            raise _ffi.MsgpuError(-3, (self.H.msh_last_error() or b"").decode() + " " + "; ".join(self.comm.errors))
+        self.last_stage_ms = None
+
+    def preprocessed_commit(self):
+        import numpy as np
+        out = np.zeros(32, dtype=np.uint8)
+        return bytes(out) if self.H.msh_prover_preprocessed_commit(self.h, out.ctypes.data_as(_C.c_void_p)) else None
+
+    def prove(self, traces, claims):
+        """traces[i]: (h x main_width) uint64 array of circuit i on EVERY rank (h = 0: inactive); claims: (n, len) uint64 array,
+        the same on every rank. Returns `Proof::to_bytes`."""
+        import numpy as np
+        from . import _ffi
+        from .system import STAGE_NAMES
+        n = self.system.num_circuits
+        mats = [np.ascontiguousarray(t, dtype=np.uint64) for t in traces]
+        ptrs = (_C.c_void_p * n)(*[m.ctypes.data if m.size else None for m in mats])
+        hs = (_C.c_uint64 * n)(*[int(m.shape[0]) for m in mats])
+        cl = np.ascontiguousarray(claims, dtype=np.uint64) if len(claims) else np.zeros((0, 1), dtype=np.uint64)
         if cl.ndim != 2:
             raise ValueError("claims: an (n, len) array is expected")
         flat = cl.reshape(-1) if cl.size else np.zeros(1, dtype=np.uint64)

@@ -5,6 +5,7 @@
 #include "system_from_graphs.hpp"
 #include "gpu_backend.hpp"
 #include "dist_backend.hpp"
+#include "rowshard_backend.hpp"
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -154,6 +155,21 @@ msh_prover* msh_dist_prover_create(msh_system* s, msgpu_ctx* ctx, const msh_comm
         p->sys = s;
         std::vector<int> own(owner, owner + s->shape.circuits.size());
         p->backend = std::make_unique<DistGpuBackend>(ctx, s->shape, *comm, own);
+        p->prover = std::make_unique<Prover>(s->shape, *p->backend);
+        return p.release();
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+// One proof over the ROW SHARDS of every matrix (rowshard_backend.hpp): every rank creates the prover with its own context and
+// calls msh_prove with ALL traces (each rank reads only its row block of the tall ones). `comm` needs the device all-to-all and
+// all-gather callbacks. All ranks get the same proof bytes, identical to the single-GPU proof.
+msh_prover* msh_rowshard_prover_create(msh_system* s, msgpu_ctx* ctx, const msh_comm* comm) {
+    try {
+        auto p = std::make_unique<msh_prover>();
+        p->sys = s;
+        p->backend = std::make_unique<RowShardBackend>(ctx, s->shape, *comm);
         p->prover = std::make_unique<Prover>(s->shape, *p->backend);
         return p.release();
     } catch (const std::exception& e) {

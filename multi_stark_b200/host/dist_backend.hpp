@@ -32,6 +32,11 @@ typedef struct msh_comm {
     int (*bcast_host)(void* user, void* buf, uint64_t bytes, int32_t root);
     // called on `src` (sends) and on `dst` (receives) only
     int (*sendrecv_dev)(void* user, void* dev, uint64_t bytes, int32_t src, int32_t dst);
+    // Device collectives of the row-sharded prover (rowshard_backend.hpp; may be NULL for the circuit-sharded one), called on
+    // every rank. all-to-all: chunk e of `send` (send_bytes[e] bytes, chunks back to back in rank order) goes to rank e, chunk e
+    // of `recv` comes from rank e. all-gather: `recv` receives world chunks of `bytes` in rank order.
+    int (*alltoall_dev)(void* user, void* send, const uint64_t* send_bytes, void* recv, const uint64_t* recv_bytes);
+    int (*allgather_dev)(void* user, void* send, void* recv, uint64_t bytes);
 } msh_comm;
 }
 

@@ -38,20 +38,32 @@ def main():
     elif kind == "mixed":
         byte, add, claims = ms.u32_add_workload(1 << log_heights[0])
         traces = [ms.fib_trace(1 << log_heights[1]), byte, add]
+    elif kind == "u32_add":
+        byte, add, claims = ms.u32_add_workload(1 << log_heights[0])
+        traces = [byte, add]
+    elif kind.startswith("wide:"):
+        traces, claims = [ms.wide_trace(1 << log_heights[0], int(kind[5:]))], np.zeros((0, 1), dtype=np.uint64)
+    elif kind == "fib":
+        traces, claims = [ms.fib_trace(1 << log_heights[0])], np.zeros((0, 1), dtype=np.uint64)
     else:
         raise SystemExit("unknown kind")
     traces = [ctx.pinned_copy(t) for t in traces]  # what a production caller hands over: page-locked host buffers
-    claims = ctx.pinned_copy(claims)
+    claims = ctx.pinned_copy(claims) if len(claims) else claims
     heights = [t.shape[0] for t in traces]
-    owner = msd.assign_owners(heights, world) if owners == "auto" else [int(x) for x in owners.split(",")]
-    prover = msd.DistProver(ctx, system, owner)
-    local = [t if owner[i] == rank else None for i, t in enumerate(traces)]
+    rowshard = owners == "rowshard"
+    if rowshard:  # every matrix split by rows over all ranks (host/rowshard_backend.hpp)
+        owner = []
+        prover = msd.RowShardProver(ctx, system)
+    else:
+        owner = msd.assign_owners(heights, world) if owners == "auto" else [int(x) for x in owners.split(",")]
+        prover = msd.DistProver(ctx, system, owner)
+    local = [t if owner[i] == rank else None for i, t in enumerate(traces)] if not rowshard else None
     times = []
     for _ in range(reps):
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        proof = prover.prove(local, heights, claims)
+        proof = prover.prove(traces, claims) if rowshard else prover.prove(local, heights, claims)
         times.append((time.perf_counter() - t0) * 1e3)
     with open("%s.rank%d.proof" % (out_prefix, rank), "wb") as f:
         f.write(proof)
