@@ -57,6 +57,16 @@ int msgpu_memcpy_h2d(msgpu_ctx* ctx, void* dst_dev, const void* src_host, size_t
 int msgpu_memcpy_d2h(msgpu_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 int msgpu_host_alloc(size_t bytes, void** hptr); /* pinned host memory */
 int msgpu_host_free(void* hptr);
+/* Page-lock host memory the caller owns (the Vec behind a p3 `RowMajorMatrix<Goldilocks>`), so that the host-pointer entry points
+ * read it directly over PCIe with no staging copy; unregister before the memory is freed. */
+int msgpu_host_register(void* hptr, size_t bytes);
+int msgpu_host_unregister(void* hptr);
+/* Context options. MSGPU_OPT_CANONICALIZE_INPUTS = 1: host matrices handed to msgpu_commit / msgpu_upload_begin /
+ * msgpu_upload_canonical may hold ANY u64 representative (p3's `Goldilocks` is `repr(transparent)` over a u64 that is not kept
+ * reduced): they are reduced mod p on the device right after the upload instead of being rejected. Together with
+ * msgpu_host_register this makes the reference's matrices uploadable with zero host-side copies. */
+#define MSGPU_OPT_CANONICALIZE_INPUTS 1
+int msgpu_ctx_set_option(msgpu_ctx* ctx, int option, uint64_t value);
 /* H2D copy of n field elements that also verifies the ABI's precondition on the device: every value must be
  * canonical (< p). Returns MSGPU_ERR_INVALID otherwise (a typed `Goldilocks` can never be out of range in the
  * reference; raw u64 buffers can). */

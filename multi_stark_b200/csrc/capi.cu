@@ -154,6 +154,7 @@ static msgpu_pdata* commit_impl(Ctx& c, const u64* const* mats, const u64* heigh
             DevBuf tmp(c, h * w * 8);
             if (host_inputs) {
                 MSG_CUDA(cudaMemcpyAsync(tmp.p, mats[i], h * w * 8, cudaMemcpyHostToDevice, c.stream));
+                if (c.canonicalize_inputs) canonicalize(c, tmp.u(), h * w);
                 ntt_coset_lde(c, tmp.u(), m.ptr, tmp.u(), h, w, log_blowup, msh::GL_GENERATOR);
             } else {
                 ntt_coset_lde(c, mats[i], m.ptr, tmp.u(), h, w, log_blowup, msh::GL_GENERATOR);
@@ -243,12 +244,37 @@ int msgpu_host_alloc(size_t bytes, void** hptr) {
 int msgpu_host_free(void* hptr) {
     return guard([&] { MSG_CUDA(cudaFreeHost(hptr)); });
 }
+// Page-lock memory the caller already owns (a `RowMajorMatrix<Goldilocks>`'s Vec): the host-pointer entry points then copy
+// straight from it at full PCIe rate, with no staging copy on either side.
+int msgpu_host_register(void* hptr, size_t bytes) {
+    return guard([&] {
+        MSG_REQUIRE(hptr && bytes, "host_register: null or empty range");
+        MSG_CUDA(cudaHostRegister(hptr, bytes, cudaHostRegisterDefault));
+    });
+}
+int msgpu_host_unregister(void* hptr) {
+    return guard([&] { MSG_CUDA(cudaHostUnregister(hptr)); });
+}
+int msgpu_ctx_set_option(msgpu_ctx* h, int option, uint64_t value) {
+    return guard([&] {
+        MSG_REQUIRE(h, "ctx_set_option: null context");
+        switch (option) {
+            case MSGPU_OPT_CANONICALIZE_INPUTS: h->c.canonicalize_inputs = value != 0; break;
+            default: throw Error(-1, "ctx_set_option: unknown option");
+        }
+    });
+}
 
 int msgpu_upload_canonical(msgpu_ctx* h, void* dst, const uint64_t* src, uint64_t n) {
     return guard([&] {
         Ctx& c = h->c;
         if (n == 0) return;
         MSG_CUDA(cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyHostToDevice, c.stream));
+        if (c.canonicalize_inputs) {
+            canonicalize(c, (u64*)dst, n);
+            c.sync();
+            return;
+        }
         DevBuf flag(c, 4);
         MSG_CUDA(cudaMemsetAsync(flag.p, 0, 4, c.stream));
         check_canonical(c, (const u64*)dst, n, (u32*)flag.p);
@@ -480,7 +506,8 @@ int msgpu_commit_upload(msgpu_upload* up, uint32_t log_blowup, int verify_canoni
                 msgpu_pdata::Mat m{(u64*)c.alloc(out_h * it.width * 8), out_h, it.width, true};
                 pd->mats.push_back(m);
                 if (it.width == 0) continue;
-                if (verify_canonical) check_canonical(c, it.dev, it.height * it.width, (u32*)flag.p);
+                if (c.canonicalize_inputs) canonicalize(c, it.dev, it.height * it.width);
+                else if (verify_canonical) check_canonical(c, it.dev, it.height * it.width, (u32*)flag.p);
                 StageScope stage_scope(c, "lde");
                 DevBuf tmp(c, it.height * it.width * 8);
                 ntt_coset_lde(c, it.dev, m.ptr, tmp.u(), it.height, it.width, log_blowup, msh::GL_GENERATOR);

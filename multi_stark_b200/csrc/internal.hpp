@@ -12,6 +12,8 @@
 #include <vector>
 #include <stdexcept>
 
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges cost nothing unless a tool (ncu --nvtx, nsys) is attached
+
 #include "gl.cuh"
 #include "../host/goldilocks.hpp"
 
@@ -48,6 +50,7 @@ struct Ctx {
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;  // lazily created: host-to-device prefetches that overlap kernels of `stream`
     unsigned long long launches = 0;  // kernels of this library launched so far
+    bool canonicalize_inputs = false;  // MSGPU_OPT_CANONICALIZE_INPUTS: host matrices are reduced mod p on the device after upload
     int sm_count = 148;
     u64* tw_full[2] = {nullptr, nullptr};  // w_1024^{i} / w_1024^{-i}, i < 1024
     std::map<std::tuple<u32, u32, u32, u64>, u64*> ntt_tables;  // per-size inter-pass twiddles / coset scales (ntt.cu)
@@ -132,11 +135,21 @@ struct KLaunch {
         if (b) cudaEventRecord(b, c.stream);
     }
 };
+// Names the stage of the launches inside it: the per-launch profile of bench.py groups by it, and it is an NVTX range named
+// after the reference's tracing spans ("stark/stage1_commit" ... are spans of src/prover.rs; the stages here are
+// the device-side pieces of those spans: lde, merkle, stage2, quotient, open, fri, transcript, exchange), so that
+// `ncu --nvtx --nvtx-include "lde/"` or an nsys timeline shows the same structure.
 struct StageScope {
     Ctx& c;
     const char* prev;
-    StageScope(Ctx& c_, const char* s) : c(c_), prev(c_.stage) { c.stage = s; }
-    ~StageScope() { c.stage = prev; }
+    StageScope(Ctx& c_, const char* s) : c(c_), prev(c_.stage) {
+        c.stage = s;
+        nvtxRangePushA(s);
+    }
+    ~StageScope() {
+        c.stage = prev;
+        nvtxRangePop();
+    }
 };
 
 // ---- NTT / LDE (ntt.cu) -------------------------------------------------------------------
@@ -168,6 +181,8 @@ void b3_merkle_subtrees(Ctx& c, const uint8_t* in, u64 len, u32 levels, uint8_t*
 void b3_hash_long(Ctx& c, const uint8_t* data_dev, u64 len, uint8_t* out_dev);
 // sets *flag_dev |= 1 if any v[i] >= p
 void check_canonical(Ctx& c, const u64* v, u64 n, u32* flag_dev);
+// v[i] <- v[i] mod p in place (device)
+void canonicalize(Ctx& c, u64* v, u64 n);
 
 inline unsigned ilog2(u64 n) {
     unsigned l = 0;

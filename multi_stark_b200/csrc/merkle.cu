@@ -395,6 +395,23 @@ __global__ void __launch_bounds__(256) k_check_canonical(const u64* v, u64 n, u3
     for (; i < n; i += (u64)gridDim.x * blockDim.x) bad |= v[i] >= GLD_P;
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
+// v[i] <- canonical representative (p3's `Goldilocks` may hold any u64 congruent to the value; the device works on canonical ones)
+__global__ void __launch_bounds__(256) k_canonicalize(u64* v, u64 n) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < n; i += (u64)gridDim.x * blockDim.x) {
+        u64 x = v[i];
+        if (x >= GLD_P) v[i] = x - GLD_P;
+    }
+}
+void canonicalize(Ctx& c, u64* v, u64 n) {
+    if (n == 0) return;
+    u64 blocks = std::min<u64>((n + 255) / 256, (u64)c.sm_count * 8);
+    {
+        KLaunch kl(c, "k_canonicalize");
+        k_canonicalize<<<(unsigned)std::max<u64>(blocks, 1), 256, 0, c.stream>>>(v, n);
+    }
+    MSG_CUDA(cudaGetLastError());
+}
 void check_canonical(Ctx& c, const u64* v, u64 n, u32* flag_dev) {
     u64 blocks = std::min<u64>((n + 255) / 256, (u64)c.sm_count * 8);
     {

@@ -995,7 +995,8 @@ int msgpu_quotient_values_shard(msgpu_ctx* h, const msgpu_program* prog, const u
         Ctx& c = h->c;
         StageScope ss(c, "quotient");
         MSG_REQUIRE(prog && cur3 && next3 && publics8 && alpha2 && (out_dev || n_local == 0), "quotient_values_shard: null argument");
-        MSG_REQUIRE(log_n + log_q <= 32 && row0 + n_local <= (1ull << (log_n + log_q)), "quotient_values_shard: rows outside the quotient domain");
+        MSG_REQUIRE(log_n + log_q <= 32 && (n_local == 0 || row0 + n_local <= (1ull << (log_n + log_q))),
+                    "quotient_values_shard: rows outside the quotient domain");
         MSG_REQUIRE((prog->pre_width == 0 || (cur3[0] && next3[0])) && cur3[1] && cur3[2] && next3[1] && next3[2], "quotient_values_shard: missing matrix");
         const u64* cur[3] = {(const u64*)cur3[0], (const u64*)cur3[1], (const u64*)cur3[2]};
         const u64* nxt[3] = {(const u64*)next3[0], (const u64*)next3[1], (const u64*)next3[2]};

@@ -43,8 +43,8 @@ def run_world(tmp_path, world, kind, log_heights, owners, params):
                 q.kill()
             raise
         outs.append(out)
-    for r, p in enumerate(procs):
-        assert p.returncode == 0, "rank %d failed:\n%s" % (r, outs[r][-3000:])
+    if any(p.returncode != 0 for p in procs):
+        raise AssertionError("\n".join("---- rank %d rc %s ----\n%s" % (r, p.returncode, outs[r][-2500:]) for r, p in enumerate(procs)))
     proofs = [open("%s.rank%d.proof" % (prefix, r), "rb").read() for r in range(world)]
     infos = [json.load(open("%s.rank%d.json" % (prefix, r))) for r in range(world)]
     single = open(prefix + ".single.proof", "rb").read()
@@ -93,8 +93,8 @@ def run_wide(tmp_path, world, log_rows, width, lb):
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_wide_worker.py"), "gloo", str(log_rows), str(width),
                                        str(lb), prefix], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=600)[0] for p in procs]
-    for r, p in enumerate(procs):
-        assert p.returncode == 0, "rank %d failed:\n%s" % (r, outs[r][-3000:])
+    if any(p.returncode != 0 for p in procs):
+        raise AssertionError("\n".join("---- rank %d rc %s ----\n%s" % (r, p.returncode, outs[r][-2500:]) for r, p in enumerate(procs)))
     infos = [json.load(open("%s.rank%d.json" % (prefix, r))) for r in range(world)]
     opens = [np.load("%s.rank%d.npz" % (prefix, r)) for r in range(world)]
     return infos, opens
@@ -128,8 +128,8 @@ def test_wide_air_proved_from_column_blocks(tmp_path, oracle, world, log_rows, w
                                        str(width), str(lb), prefix, "1", "20"], env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=600)[0] for p in procs]
-    for r, p in enumerate(procs):
-        assert p.returncode == 0, "rank %d failed:\n%s" % (r, outs[r][-3000:])
+    if any(p.returncode != 0 for p in procs):
+        raise AssertionError("\n".join("---- rank %d rc %s ----\n%s" % (r, p.returncode, outs[r][-2500:]) for r, p in enumerate(procs)))
     info = json.load(open(prefix + ".rank0.json"))
     assert info["errors"] == [] and info["identical"], "sharded proof differs from the single-GPU proof"
     proof = open(prefix + ".sharded.proof", "rb").read()

@@ -157,3 +157,52 @@ def test_valid_witness_quotient_is_low_degree(gpu, oracle):
     tot = [(int(acc[k]) + int(totals[0][k]) + int(totals[1][k])) % P for k in range(2)]
     assert tot == [0, 0]
     oracle.orc_system_free(osy)
+
+
+@pytest.mark.parametrize("k,want_slots", [(300, 1024), (1200, 4096)])
+def test_large_dag_quotient_matches_oracle(gpu, oracle, k, want_slots):
+    """The 1024- and 4096-slot instantiations of the bytecode interpreter (k_quotient_eval, k_lookup_messages) on a synthetic
+    DAG of thousands of nodes with ~k simultaneously live values (tests/_bigdag.py), handed over as a descriptor
+    (msh_system_create_from_graphs): quotient values, stage-2 trace and quotient LDE against the CPU oracle, bit for bit."""
+    from tests import _bigdag, _pyverifier as pv
+    ms, ctx = gpu
+    circ = _bigdag.big_dag_circuit(k=k)
+    g = pv.graph_dict(circ)
+    assert len(g["nodes"]) > 4 * k and circ.quotient_degree() == 2
+    lb, log_n = 1, 8
+    system = ms.System.from_graphs([g], log_blowup=lb)
+    S = orc.OracleSystem(oracle, None, graphs=[g], log_blowup=lb)
+    rng = np.random.default_rng(k)
+    n = 1 << log_n
+    main = orc.rand_matrix(rng, n, circ.main_width)
+    prog = ms.Program(ctx, system, 0)
+    # stage-2 trace (lookup prefix sweep + batch inverse + scan)
+    beta, gamma = rnd_ext(rng), rnd_ext(rng)
+    d_main = ctx.upload(main)
+    out_dev, local = prog.stage2_trace(d_main, n, beta, gamma, None)
+    got_s2 = ctx.download(out_dev, (n, circ.stage2_width))
+    want_s2 = np.zeros_like(got_s2)
+    wl = np.zeros(2, dtype=np.uint64)
+    oracle.orc_stage2_trace(S.h, 0, main, n, beta, gamma, want_s2, wl)
+    assert np.array_equal(got_s2, want_s2) and np.array_equal(local, wl)
+    ctx.free(out_dev)
+    ctx.free(d_main)
+    # quotient evaluation on the quotient domain
+    s2 = orc.rand_matrix(rng, n, circ.stage2_width)
+    pcs = ms.GpuPcs(ctx, lb)
+    _, pd1 = pcs.commit([main])
+    _, pd2 = pcs.commit([s2])
+    alpha = rnd_ext(rng)
+    publics = rng.integers(0, P, size=8, dtype=np.uint64)
+    log_q = 1
+    nq = n << log_q
+    lde, rows, cols, vals = prog.quotient(None, 0, pd1, 0, pd2, 0, log_n, log_q, lb, publics, alpha, want_values=True)
+    want = np.zeros((nq, 2), dtype=np.uint64)
+    oracle.orc_quotient_values(S.h, 0, log_n, log_q, None, pd1.read_rows(0, 0, nq), pd2.read_rows(0, 0, nq), publics, alpha, want)
+    assert np.array_equal(vals, want)
+    ctx.free(lde)
+    prog.free()
+    pd1.free()
+    pd2.free()
+    S.close()
+    system.close()

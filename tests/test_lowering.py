@@ -36,3 +36,17 @@ def test_u32_add_slot_counts(oracle):
     assert int(oracle.orc_check_lowering(S.h, 1, 4, 3, out)) == 0
     assert out[0] <= 32 and out[2] <= 32, "the U32-add circuit must fit the 32-slot kernels (shared-memory slots in k_lookup_messages)"
     S.close()
+
+
+@pytest.mark.parametrize("k,lo,hi", [(300, 257, 1024), (1200, 1025, 4096)])
+def test_large_dag_lowering(oracle, k, lo, hi):
+    """The synthetic large DAG (tests/_bigdag.py, thousands of nodes, ~k live values) lowers correctly and really needs the
+    1024- / 4096-slot instantiations of the device interpreter (tests/test_gpu_quotient.py runs them)."""
+    from tests import _bigdag, _pyverifier as pv
+    g = pv.graph_dict(_bigdag.big_dag_circuit(k=k))
+    S = orc.OracleSystem(oracle, None, graphs=[g], log_blowup=1, num_queries=4)
+    out = np.zeros(4, dtype=np.uint32)
+    assert int(oracle.orc_check_lowering(S.h, 0, 4, 99, out)) == 0
+    assert lo <= out[0] <= hi, "full program needs %d slots" % out[0]
+    assert out[2] <= 32, "the lookup prefix stays in the 32-slot kernel"
+    S.close()
