@@ -445,16 +445,39 @@ class RowShardProver:
         out = np.zeros(32, dtype=np.uint8)
         return bytes(out) if self.H.msh_prover_preprocessed_commit(self.h, out.ctypes.data_as(_C.c_void_p)) else None
 
-    def prove(self, traces, claims):
+    def shardable(self, height, width):
+        """the backend's rule (RowShardBackend::shardable): such a trace is read as natural-order row blocks"""
+        return self.comm.world > 1 and width >= self.comm.world and height >= self.comm.world * 64
+
+    def block_rows(self, height, width):
+        """(row0, rows) of the part of a height x width trace this rank reads"""
+        if not self.shardable(height, width):
+            return 0, height
+        rows = height // self.comm.world
+        return rows * self.comm.rank, rows
+
+    def prove(self, traces, claims, heights=None):
         """traces[i]: (h x main_width) uint64 array of circuit i on EVERY rank (h = 0: inactive); claims: (n, len) uint64 array,
-        the same on every rank. Returns `Proof::to_bytes`."""
+        the same on every rank. With `heights` (trace rows of every circuit) traces[i] may instead hold only the rows this rank
+        reads -- block_rows(heights[i], width) -- so that no rank needs the whole of a tall trace in host memory.
+        Returns `Proof::to_bytes`."""
         import numpy as np
         from . import _ffi
         from .system import STAGE_NAMES
         n = self.system.num_circuits
         mats = [np.ascontiguousarray(t, dtype=np.uint64) for t in traces]
-        ptrs = (_C.c_void_p * n)(*[m.ctypes.data if m.size else None for m in mats])
-        hs = (_C.c_uint64 * n)(*[int(m.shape[0]) for m in mats])
+        if heights is None:
+            ptrs = (_C.c_void_p * n)(*[m.ctypes.data if m.size else None for m in mats])
+            hs = (_C.c_uint64 * n)(*[int(m.shape[0]) for m in mats])
+        else:
+            plist = []
+            for m, h in zip(mats, heights):
+                row0, rows = self.block_rows(int(h), m.shape[1])
+                if m.shape[0] != rows:
+                    raise ValueError("a trace given as a row block must hold exactly the rows this rank reads")
+                plist.append(m.ctypes.data - row0 * m.shape[1] * 8 if m.size else None)  # the library touches [row0, row0 + rows) only
+            ptrs = (_C.c_void_p * n)(*plist)
+            hs = (_C.c_uint64 * n)(*[int(h) for h in heights])
         cl = np.ascontiguousarray(claims, dtype=np.uint64) if len(claims) else np.zeros((0, 1), dtype=np.uint64)
         if cl.ndim != 2:
             raise ValueError("claims: an (n, len) array is expected")
