@@ -394,6 +394,96 @@ def sharded_prove_leg(args, ms, msd, ctx, rank, world, steps=4):
     return out
 
 
+def rowshard_commit_leg(args, ms, msd, ctx, rs, rank, world, steps, warmup):
+    """The bench step -- both trace commitments of configs[1] -- as ONE job over all ranks: every matrix split by rows
+    (host/rowshard_backend.hpp): column-sharded NTT between two all-to-alls, leaf hashing and subtrees per rank, 32-byte subtree
+    roots all-gathered. Same work for every N (strong scaling). Returns (ms/step resident, ms/step from host, roots)."""
+    import torch
+    stages = u32_add_workload(args.log_rows, seed=0)  # the SAME matrices on every rank
+    hs = [[m.shape[0] for m in st] for st in stages]
+    ws = [[m.shape[1] for m in st] for st in stages]
+    def my_rows(m):
+        r0, n = rs.block_rows(m.shape[0], m.shape[1])
+        return np.ascontiguousarray(m[r0:r0 + n])
+    blocks = [[my_rows(m) for m in st] for st in stages]
+    pinned = [[ctx.pinned_copy(b) for b in st] for st in blocks]
+    dev = [[ctx.upload(b) for b in st] for st in blocks]
+
+    def step(host):
+        return [rs.commit(pinned[i] if host else dev[i], hs[i], ws[i], host) for i in range(len(stages))]
+
+    out = {}
+    for host in (False, True):
+        for _ in range(warmup):
+            roots = step(host)
+        msd.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            roots = step(host)
+        e1.record()
+        torch.cuda.synchronize()
+        out["host" if host else "resident"] = msd.max_over_ranks(e0.elapsed_time(e1)) / steps
+        msd.barrier()
+    for st in dev:
+        for p in st:
+            ctx.free(p)
+    return out["resident"], out["host"], roots, sum(b.nbytes for st in blocks for b in st)
+
+
+def rowshard_prove_leg(args, ms, msd, ctx, rank, world, kind, log_heights, steps=3):
+    """ONE proof over the row shards of every matrix, all ranks (kind "u32_add": one circuit of 2^log_heights[0] rows; "multi:K":
+    BASELINE configs[3] shape). Compared with the same proof on one GPU (rank 0): the bytes must be identical."""
+    import hashlib
+    import torch
+    system = ms.System(kind, **prove_params(args))
+    if kind == "u32_add":
+        byte, add, claims = u32_add_traces(log_heights[0])
+        traces = [byte, add]
+    else:
+        traces, claims = ms.multi_workload(log_heights)
+    rs = msd.RowShardProver(ctx, system)
+    heights = [t.shape[0] for t in traces]
+    mine = []
+    for t in traces:  # every rank pins only the rows it reads
+        r0, n = rs.block_rows(t.shape[0], t.shape[1])
+        mine.append(ctx.pinned_copy(t[r0:r0 + n]))
+    claims_p = ctx.pinned_copy(np.ascontiguousarray(claims))
+    times = []
+    for it in range(steps + 1):
+        msd.barrier()
+        torch.cuda.synchronize()
+        if it == steps:
+            rs.comm.seconds.clear()
+            rs.comm.bytes_dev = 0
+        t0 = time.perf_counter()
+        proof = rs.prove(mine, claims_p, heights=heights)
+        if it:
+            times.append((time.perf_counter() - t0) * 1e3)
+    out = {"kind": kind, "log_heights": log_heights, "ms": msd.max_over_ranks(float(np.median(times))), "stages_ms_rank0": rs.last_stage_ms,
+           "proof_bytes": len(proof), "digest": hashlib.sha256(proof).hexdigest(),
+           "device_bytes_exchanged_this_rank": int(rs.comm.bytes_dev),
+           "comm_ms_this_rank": {k: round(v * 1e3, 3) for k, v in rs.comm.seconds.items()},
+           "timing": "host wall clock around the call on every rank (row blocks of pinned host traces in, proof bytes out), median, max over ranks"}
+    out["all_ranks_same_proof"] = len(set(msd.gather_digests([bytes.fromhex(out["digest"])]))) == 1
+    rs.close()
+    if rank == 0:
+        single = ms.Prover(ctx, system)
+        pinned = [ctx.pinned_copy(t) for t in traces]
+        ts = []
+        for it in range(3):
+            t0 = time.perf_counter()
+            want = single.prove(pinned, claims_p)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        out["single_gpu_ms"] = float(np.min(ts[1:]))
+        out["identical_to_single_gpu_proof"] = want == proof
+        out["speedup_vs_one_gpu"] = out["single_gpu_ms"] / out["ms"]
+        single.close()
+    msd.barrier()
+    return out
+
+
 def run_reference(args):
     """The reference arm: the CPU restatement of the SAME step (both trace commitments of configs[1] at the full 2^log_rows
     rows) on every host core, plus its prove() at the same rows and at 2^big rows. Imports nothing of the product."""
@@ -575,6 +665,23 @@ def main():
     value = world * elems / (ms_step / 1e3) / 1e9
     e2e_value = world * elems / (ms_e2e / args.steps / 1e3) / 1e9
     h2d = sum(m.nbytes for st in stages for m in st)
+    replicas = None
+    if world > 1:
+        # N > 1: the headline is ONE job over all ranks (the same two commitments, every matrix split by rows: strong scaling);
+        # the independent replicas measured above (no data-path collective) are kept as an extra key
+        replicas = {"value": value, "unit": "Gelem/s", "ms_per_step": ms_step, "e2e_value": e2e_value, "scaling": "weak",
+                    "note": "every rank commits its own instance of the step: independent units, no data-path collective"}
+        rs_system = ms.System("u32_add", **prove_params(args))
+        rs = msd.RowShardProver(ctx, rs_system)
+        ms_step, ms_host, rs_roots, h2d = rowshard_commit_leg(args, ms, msd, ctx, rs, rank, world, args.steps, max(args.warmup, 3))
+        n_commits = 2 * (args.steps + max(args.warmup, 3)) * len(stages)
+        rs_bytes_per_step = rs.comm.bytes_dev // max(n_commits // len(stages), 1)
+        rs.close()
+        value = elems / (ms_step / 1e3) / 1e9
+        e2e_value = elems / (ms_host / 1e3) / 1e9
+        ms_e2e = ms_host * args.steps
+        # rank 0's replica commits the same matrices (seed 0): the sharded roots must be the single-GPU roots
+        rs_roots_ok = (rs_roots == step_resident()) if rank == 0 else None
 
     # roofline of the dominant stage: algorithmic bytes / CUDA-event time of its launches
     peak, peak_src = measured_peaks()
@@ -664,22 +771,33 @@ def main():
                 prove_big["speedup_vs_cpu_port"] = prove_big["cpu"]["ms"] / prove_big["ms"]
         if world > 1:
             prove["sharded"] = sharded_prove_leg(args, ms, msd, ctx, rank, world)
+            # every matrix split by rows over all ranks: one tall circuit (2^log_rows and 2^big rows) and the 7-circuit system
+            prove["rowshard"] = rowshard_prove_leg(args, ms, msd, ctx, rank, world, "u32_add", [args.log_rows])
+            if args.big_log_rows > args.log_rows:
+                prove_big = rowshard_prove_leg(args, ms, msd, ctx, rank, world, "u32_add", [args.big_log_rows])
+            lhs = [min(h, args.log_rows + 2) for h in (22, 21, 21, 20, 20, 19, 18)]
+            prove["rowshard_multi7"] = rowshard_prove_leg(args, ms, msd, ctx, rank, world, "multi:7", lhs)
 
     if rank == 0:
         if roofline is not None and prove is not None and prove.get("stage_roofline"):
             roofline["prove_stages"] = prove["stage_roofline"]
         print(json.dumps({
             "metric": "lde_merkle_gelem_per_s", "value": value, "unit": "Gelem/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak" if world == 1 else "strong",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": "Gelem/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
                     "ms_per_step": ms_e2e / args.steps,
-                    "call": "msgpu_upload_begin + msgpu_commit_upload on pinned host matrices, the next commitment's upload enqueued "
-                            "before this one's kernels",
+                    "call": ("msgpu_upload_begin + msgpu_commit_upload on pinned host matrices, the next commitment's upload enqueued "
+                             "before this one's kernels") if world == 1 else
+                            "msh_rowshard_commit on pinned host row blocks (each rank uploads 1 / N of every tall matrix)",
                     "serial": {"value": world * elems / (ms_e2e_serial / args.steps / 1e3) / 1e9, "ms_per_step": ms_e2e_serial / args.steps,
                                "call": "msgpu_commit (upload, then kernels, then root; no overlap between calls)"}},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "prove": prove,
-            "prove_big": prove_big,
+            "prove_big": prove_big, "replicas": replicas,
+            "sharding": None if world == 1 else {
+                "mode": "every committed matrix split by rows over the ranks (host/rowshard_backend.hpp): ONE job, the same work at every N",
+                "device_bytes_exchanged_this_rank_per_step": int(rs_bytes_per_step), "roots_equal_single_gpu_commit": rs_roots_ok},
         }))
     ctx.close()
     if world > 1:

@@ -277,8 +277,8 @@ def _all_to_all_dev(self, send_ptr, send_counts, recv_ptr, recv_counts):
         empty = torch.empty(0, dtype=torch.uint8, device=dev)
         s = torch.as_tensor(_DevView(send_ptr, sum(send_counts)), device=dev) if sum(send_counts) else empty
         r = torch.as_tensor(_DevView(recv_ptr, sum(recv_counts)), device=dev) if sum(recv_counts) else empty
+        # stream-ordered on the context's stream (checked in __init__): later kernels see the data, no host wait needed
         self.dist.all_to_all_single(r, s, output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts), group=self.group)
-        torch.cuda.current_stream().synchronize()
     else:  # gloo: staged through the host, pairwise
         so = [sum(send_counts[:k]) for k in range(self.world)]
         ro = [sum(recv_counts[:k]) for k in range(self.world)]
@@ -325,8 +325,7 @@ def _allgather_dev_cb(self, user, send, recv, nbytes):
             dev = torch.device("cuda", torch.cuda.current_device())
             s = torch.as_tensor(_DevView(send, nbytes), device=dev)
             r = torch.as_tensor(_DevView(recv, nbytes * self.world), device=dev)
-            self.dist.all_gather_into_tensor(r, s, group=self.group)
-            torch.cuda.current_stream().synchronize()
+            self.dist.all_gather_into_tensor(r, s, group=self.group)  # stream-ordered, as the all-to-all
         else:  # gloo: staged through the host
             hs = torch.empty(nbytes, dtype=torch.uint8)
             hr = torch.empty(nbytes * self.world, dtype=torch.uint8)
@@ -455,6 +454,25 @@ class RowShardProver:
             return 0, height
         rows = height // self.comm.world
         return rows * self.comm.rank, rows
+
+    def commit(self, mats, heights, widths, host):
+        """`Pcs::commit` over the row shards alone. host=False: mats[i] = DEVICE pointer of this rank's natural-order row block
+        (block_rows(heights[i], widths[i])); host=True: mats[i] = numpy array holding the rows this rank reads. Returns the root."""
+        import numpy as np
+        n = len(mats)
+        if host:
+            keep = [np.ascontiguousarray(m, dtype=np.uint64) for m in mats]
+            plist = [m.ctypes.data - self.block_rows(int(h), int(w))[0] * int(w) * 8 for m, h, w in zip(keep, heights, widths)]
+        else:
+            plist = [int(m) for m in mats]
+        ptrs = (_C.c_void_p * n)(*plist)
+        hs = (_C.c_uint64 * n)(*[int(h) for h in heights])
+        ws = (_C.c_uint64 * n)(*[int(w) for w in widths])
+        root = np.zeros(32, dtype=np.uint8)
+        if self.H.msh_rowshard_commit(self.h, ptrs, hs, ws, n, 1 if host else 0, root.ctypes.data_as(_C.c_void_p)) != 0:
+            from . import _ffi
+            raise _ffi.MsgpuError(-1, (self.H.msh_last_error() or b"").decode() + " " + "; ".join(self.comm.errors))
+        return bytes(root)
 
     def prove(self, traces, claims, heights=None):
         """traces[i]: (h x main_width) uint64 array of circuit i on EVERY rank (h = 0: inactive); claims: (n, len) uint64 array,

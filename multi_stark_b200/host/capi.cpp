@@ -177,6 +177,40 @@ msh_prover* msh_rowshard_prover_create(msh_system* s, msgpu_ctx* ctx, const msh_
         return nullptr;
     }
 }
+// Pcs::commit over the row shards alone (bench.py's strong-scaling step): mats[i] = this rank's natural-order ROW BLOCK of matrix
+// i (rows [d h / N, (d + 1) h / N) when RowShardProver.shardable(h, w), else the whole matrix), DEVICE pointers (host = 0) or
+// HOST pointers to the FULL matrices (host = 1: each rank uploads the rows it reads). Every rank gets the root.
+int msh_rowshard_commit(msh_prover* p, const uint64_t* const* mats, const uint64_t* heights, const uint64_t* widths, uint64_t n, int host,
+                        uint8_t* root32) {
+    try {
+        auto* be = dynamic_cast<RowShardBackend*>(p->backend.get());
+        if (!be) throw std::runtime_error("not a row-sharded prover");
+        std::vector<RowBlocks> blocks;
+        struct Free {
+            RowShardBackend* b; std::vector<RowBlocks>& v; bool on;
+            ~Free() { if (on) for (auto& x : v) if (x.dev) msgpu_free(b->ctx(), x.dev); }
+        } fr{be, blocks, host != 0};
+        for (uint64_t i = 0; i < n; i++) {
+            if (host) {
+                blocks.push_back(be->upload_blocks(mats[i], (size_t)heights[i], (size_t)widths[i]));
+            } else {
+                RowBlocks b;
+                b.height = (size_t)heights[i];
+                b.width = (size_t)widths[i];
+                b.whole = !be->shardable(b.height, b.width);
+                b.dev = (uint64_t*)mats[i];
+                blocks.push_back(b);
+            }
+        }
+        Digest root{};
+        auto h = be->commit_blocks(blocks, root);
+        memcpy(root32, root.data(), 32);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
 // The next msh_prove on this prover adopts `pd` (from msgpu_pdata_from_parts) as its stage-1 commitment instead of committing
 // the traces; pass NULL trace pointers with the true heights. The prover owns `pd` from here on.
 int msh_prover_inject_stage1(msh_prover* p, msgpu_pdata* pd) {
