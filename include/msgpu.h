@@ -122,6 +122,7 @@ int msgpu_commit_dev(msgpu_ctx* ctx, const uint64_t* const* mats, const uint64_t
 /* Pcs::commit_ldes (src/prover.rs:526): Merkle-only commitment to LDEs that already live on the
  * device in bit-reversed row order. The prover data BORROWS (take_ownership = 0) or adopts
  * (take_ownership = 1; buffers must come from msgpu_malloc) the matrices. */
+/* root32 == NULL: nothing is read back and nothing waits (the root is the last digest of msgpu_pdata_digests). */
 int msgpu_commit_ldes_dev(msgpu_ctx* ctx, uint64_t* const* ldes, const uint64_t* heights, const uint64_t* widths,
                           uint64_t n_mats, int take_ownership, msgpu_pdata** out, uint8_t* root32);
 /* ---- one commitment whose matrices live on several GPUs (partitioning A: circuits -> GPUs) ----
@@ -319,9 +320,13 @@ int msgpu_pack_column_blocks_dev(msgpu_ctx* ctx, const uint64_t* src, uint64_t r
                                  const uint64_t* c0, const uint64_t* c1, uint64_t* dst);
 int msgpu_interleave_column_blocks_dev(msgpu_ctx* ctx, const uint64_t* src, uint64_t rows, uint64_t n_blocks, const uint64_t* widths,
                                        uint64_t* dst);
+/* next_widths3 / next_col0_3 (optional): the next buffers may hold only columns [col0, col0 + width) of their matrices -- the
+ * ones the constraints read at the next row (msgpu_extract_columns_dev packs them for the exchange). */
 int msgpu_quotient_values_shard(msgpu_ctx* ctx, const msgpu_program* prog, const uint64_t* const* cur3, const uint64_t* const* next3,
-                                uint64_t row0, uint64_t n_local, uint64_t next_row0, uint32_t log_n, uint32_t log_quotient_degree,
-                                const uint64_t* publics8, const uint64_t* alpha2, uint64_t* out_dev);
+                                const uint32_t* next_widths3, const uint32_t* next_col0_3, uint64_t row0, uint64_t n_local,
+                                uint64_t next_row0, uint32_t log_n, uint32_t log_quotient_degree, const uint64_t* publics8,
+                                const uint64_t* alpha2, uint64_t* out_dev);
+int msgpu_extract_columns_dev(msgpu_ctx* ctx, const uint64_t* src, uint64_t rows, uint64_t width, uint64_t c0, uint64_t c1, uint64_t* dst);
 int msgpu_quotient_finish(msgpu_ctx* ctx, const uint64_t* values_stored_dev, uint32_t log_n, uint32_t log_quotient_degree,
                           uint32_t log_blowup, uint64_t** lde_out_dev);
 int msgpu_open_begin_shard(msgpu_ctx* ctx, uint64_t n_rounds, const msgpu_pdata* const* pds, const uint32_t* modes, uint32_t shard,

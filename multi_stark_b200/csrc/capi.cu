@@ -680,14 +680,17 @@ int msgpu_commit_ldes_dev(msgpu_ctx* h, uint64_t* const* ldes, const uint64_t* h
                 check_shape(heights[i], widths[i]);
                 pd->mats.push_back(msgpu_pdata::Mat{(u64*)ldes[i], heights[i], widths[i], false});
             }
-            mmcs_build(c, pd);
+            // root32 == NULL: stream-ordered, no read-back (the root is the last digest of msgpu_pdata_digests): a row shard's
+            // subtree root goes straight into a device all-gather
+            if (root32) mmcs_build(c, pd);
+            else mmcs_build_async(c, pd);
         } catch (...) {
             pdata_destroy(pd);
             throw;
         }
         if (take_ownership)
             for (auto& m : pd->mats) m.owned = true;
-        memcpy(root32, pd->root, 32);
+        if (root32) memcpy(root32, pd->root, 32);
         *out = pd;
     });
 }

@@ -202,6 +202,7 @@ struct QuotParams {
     // domain, the *_n pointers the shard that holds the NEXT rows, stored rows [next_row0, ...). Unsharded: row0 = next_row0 = 0,
     // n_local = nq and the next pointers equal the cur ones.
     const u64 *pre_n, *s1_n, *s2_n;
+    u32 wn[3], cn[3];  // the next buffers' row strides and first columns (a shard may fetch only the columns read at the next row)
     u64 row0, n_local, next_row0;
     u32 out_stored;
     gl::PowTable xtab;
@@ -224,11 +225,11 @@ __global__ void __launch_bounds__(128) k_quotient_eval(QuotParams p) {
     const u64 sn = gl::rev_bits((u32)inext, p.log_nq) - p.next_row0;  // inside the shard the next pointers address
     RowCtx cx;
     cx.rows[0][0] = p.pre + sl * p.wpre;
-    cx.rows[0][1] = p.pre_n + sn * p.wpre;
+    cx.rows[0][1] = p.pre_n + sn * p.wn[0] - p.cn[0];
     cx.rows[1][0] = p.s1 + sl * p.w1;
-    cx.rows[1][1] = p.s1_n + sn * p.w1;
+    cx.rows[1][1] = p.s1_n + sn * p.wn[1] - p.cn[1];
     cx.rows[2][0] = p.s2 + sl * p.w2;
-    cx.rows[2][1] = p.s2_n + sn * p.w2;
+    cx.rows[2][1] = p.s2_n + sn * p.wn[2] - p.cn[2];
     cx.publics = p.publics;
     cx.first = p.sel_first[s];
     cx.last = p.sel_last[s];
@@ -879,7 +880,8 @@ namespace msg {
 // k_quotient_eval over stored rows [row0, row0 + n_local) of the quotient domain. cur[3] / nxt[3]: pre, stage 1, stage 2 row
 // pointers of the local rows / of the shard holding the next rows (first stored row next_row0).
 static void quotient_eval(Ctx& c, const msgpu_program* prog, const u64* const cur[3], const u64* const nxt[3], u64 row0, u64 n_local,
-                          u64 next_row0, u32 log_n, u32 log_q, const uint64_t* publics8, const uint64_t* alpha2, u64* out, bool out_stored) {
+                          u64 next_row0, u32 log_n, u32 log_q, const uint64_t* publics8, const uint64_t* alpha2, u64* out, bool out_stored,
+                          const u32* next_widths3 = nullptr, const u32* next_col0_3 = nullptr) {
     const u32 log_nq = log_n + log_q;
     const u64 n = 1ull << log_n;
     for (int i = 0; i < 8; i++) MSG_REQUIRE(publics8[i] < GLD_P, "quotient: public value is not canonical");
@@ -887,6 +889,11 @@ static void quotient_eval(Ctx& c, const msgpu_program* prog, const u64* const cu
     qp.pre = cur[0]; qp.s1 = cur[1]; qp.s2 = cur[2];
     qp.pre_n = nxt[0]; qp.s1_n = nxt[1]; qp.s2_n = nxt[2];
     qp.row0 = row0; qp.n_local = n_local; qp.next_row0 = next_row0; qp.out_stored = out_stored ? 1u : 0u;
+    const u32 full_w[3] = {prog->pre_width, prog->main_width, prog->stage2_width};
+    for (int k = 0; k < 3; k++) {
+        qp.wn[k] = next_widths3 ? next_widths3[k] : full_w[k];
+        qp.cn[k] = next_col0_3 ? next_col0_3[k] : 0;
+    }
     SelCache sel = selectors(c, log_n, log_q);
     // alpha powers reversed (src/prover.rs:798-808): constraint j of k weighted by alpha^{k-1-j}
     u32 k = prog->n_zeros + 2 * std::max<u32>(prog->n_lookups, 1);
@@ -989,8 +996,9 @@ int msgpu_quotient(msgpu_ctx* h, const msgpu_program* prog, const msgpu_pdata* p
 // the rows one trace step further (stored rows from next_row0 on; the caller fetched it from its owner -- for the local shard
 // itself pass the cur pointers and row0). out_dev: n_local x 2 quotient evaluations in STORED order.
 int msgpu_quotient_values_shard(msgpu_ctx* h, const msgpu_program* prog, const uint64_t* const* cur3, const uint64_t* const* next3,
-                                uint64_t row0, uint64_t n_local, uint64_t next_row0, uint32_t log_n, uint32_t log_q,
-                                const uint64_t* publics8, const uint64_t* alpha2, uint64_t* out_dev) {
+                                const uint32_t* next_widths3, const uint32_t* next_col0_3, uint64_t row0, uint64_t n_local,
+                                uint64_t next_row0, uint32_t log_n, uint32_t log_q, const uint64_t* publics8, const uint64_t* alpha2,
+                                uint64_t* out_dev) {
     return guard([&] {
         Ctx& c = h->c;
         StageScope ss(c, "quotient");
@@ -1000,7 +1008,26 @@ int msgpu_quotient_values_shard(msgpu_ctx* h, const msgpu_program* prog, const u
         MSG_REQUIRE((prog->pre_width == 0 || (cur3[0] && next3[0])) && cur3[1] && cur3[2] && next3[1] && next3[2], "quotient_values_shard: missing matrix");
         const u64* cur[3] = {(const u64*)cur3[0], (const u64*)cur3[1], (const u64*)cur3[2]};
         const u64* nxt[3] = {(const u64*)next3[0], (const u64*)next3[1], (const u64*)next3[2]};
-        quotient_eval(c, prog, cur, nxt, row0, n_local, next_row0, log_n, log_q, publics8, alpha2, (u64*)out_dev, true);
+        quotient_eval(c, prog, cur, nxt, row0, n_local, next_row0, log_n, log_q, publics8, alpha2, (u64*)out_dev, true, next_widths3,
+                      next_col0_3);
+    });
+}
+// dst[r][c - c0] = src[r][c] for c in [c0, c1): the columns of a shard that another shard reads at its next rows
+__global__ void __launch_bounds__(256) k_extract_columns(const u64* src, u64 rows, u32 w, u32 c0, u32 wc, u64* dst) {
+    const u64 total = rows * wc;
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (u64)gridDim.x * blockDim.x)
+        dst[e] = src[(e / wc) * w + c0 + (u32)(e % wc)];
+}
+int msgpu_extract_columns_dev(msgpu_ctx* h, const uint64_t* src, uint64_t rows, uint64_t width, uint64_t c0, uint64_t c1, uint64_t* dst) {
+    return guard([&] {
+        Ctx& c = h->c;
+        MSG_REQUIRE(src && dst && c0 < c1 && c1 <= width, "extract_columns: bad column range");
+        if (rows == 0) return;
+        StageScope ss(c, "exchange");
+        KLaunch kl(c, "k_extract_columns");
+        k_extract_columns<<<(unsigned)std::min<u64>((rows * (c1 - c0) + 255) / 256, (u64)c.sm_count * 16), 256, 0, c.stream>>>(
+            (const u64*)src, rows, (u32)width, (u32)c0, (u32)(c1 - c0), (u64*)dst);
+        MSG_CUDA(cudaGetLastError());
     });
 }
 // values_stored_dev: ALL nq x 2 quotient evaluations in stored (bit-reversed) order, gathered from the shards (device, not

@@ -165,13 +165,18 @@ class RowShardBackend : public GpuBackend {
             hs.push_back(h->shard_rows(i));
             ws.push_back(h->shapes[i].second);
         }
-        Digest sub{};
-        gpu_check(msgpu_commit_ldes_dev(ctx_, ptrs.data(), hs.data(), ws.data(), ptrs.size(), 0, &h->local, sub.data()));
-        if (N == 1) { root = sub; return h; }
-        std::vector<u8> roots(32 * (size_t)N);
-        comm_.allgather(sub.data(), roots.data(), 32);
-        DevPtr d_roots(ctx_, roots.size());
-        gpu_check(msgpu_memcpy_h2d(ctx_, d_roots.p, roots.data(), roots.size()));
+        if (N == 1) {
+            gpu_check(msgpu_commit_ldes_dev(ctx_, ptrs.data(), hs.data(), ws.data(), ptrs.size(), 0, &h->local, root.data()));
+            return h;
+        }
+        // leaf digests + subtree, stream-ordered (no read-back); the 32-byte subtree roots are all-gathered on the device and the
+        // top levels built from them: ONE host synchronisation per commitment, for the root the transcript needs
+        gpu_check(msgpu_commit_ldes_dev(ctx_, ptrs.data(), hs.data(), ws.data(), ptrs.size(), 0, &h->local, nullptr));
+        uint8_t* dg = nullptr;
+        uint64_t nd = 0;
+        gpu_check(msgpu_pdata_digests(h->local, &dg, &nd));
+        DevPtr d_roots(ctx_, 32 * (size_t)N);
+        comm_.allgather_dev(dg + (nd - 1) * 32, d_roots.p, 32);
         uint64_t hh = (uint64_t)N;
         const uint8_t* pp = (const uint8_t*)d_roots.p;
         gpu_check(msgpu_tree_from_digests(ctx_, 1, &hh, &pp, &h->top, root.data()));
@@ -341,43 +346,58 @@ class RowShardBackend : public GpuBackend {
             const bool has_pre = j.preprocessed_idx >= 0 && hp;
             const uint64_t* cur[3] = {nullptr, nullptr, nullptr};
             const uint64_t* nxt[3] = {nullptr, nullptr, nullptr};
+            uint32_t nw[3] = {0, 0, 0}, nc0[3] = {0, 0, 0};
+            // the columns each source is read at with the NEXT-row offset: the stage-2 accumulator pair (the logUp wrap /
+            // pass-through constraint reads stage2_next[0..2], src/lookup.rs:167-208) and whatever the constraints name
+            size_t lo[3] = {SIZE_MAX, SIZE_MAX, 0}, hi[3] = {0, 0, 2};
+            for (auto& nd : shape_.circuits[j.circuit].graph.nodes)
+                if (nd.op == Op::Var && nd.col.offset == RowOffset::Next) {
+                    const int k = (int)nd.col.source;
+                    lo[k] = std::min<size_t>(lo[k], nd.col.index);
+                    hi[k] = std::max<size_t>(hi[k], (size_t)nd.col.index + 1);
+                }
             std::vector<DevPtr> halos;
             size_t next_row0 = row0;
+            const size_t dn = (size_t)d < Np ? next_of((size_t)d) : (size_t)d;
+            if ((size_t)d < Np) next_row0 = dn * Ls;
             for (int k = 0; k < 3; k++) {
                 if (k == 0 && !has_pre) continue;
                 RowShardHandle* sh = src[k].h;
                 const size_t i = src[k].idx, w = sh->shapes[i].second;
                 if (sh->shapes[i].first != H) throw RowShardError("quotient: the circuit's committed matrices differ in height");
                 cur[k] = sh->views[i];
-                if ((size_t)d < Np) {
-                    const size_t dn = next_of((size_t)d);
-                    next_row0 = dn * Ls;
-                    if (dn == (size_t)d) nxt[k] = sh->views[i];
-                    else if (sh->whole[i]) nxt[k] = sh->whole_rows_of(i, (int)dn);
-                } else {
-                    nxt[k] = sh->views[i];
-                }
-                if (Np > 1 && !sh->whole[i]) {
-                    // fetch shard next_of(d): rank e sends its quotient-domain rows to the rank whose next rows they are
+                nxt[k] = sh->views[i];  // never read when the source has no next-row reference
+                nw[k] = (uint32_t)w;
+                if (lo[k] >= hi[k] || dn == (size_t)d) continue;
+                if (sh->whole[i]) { nxt[k] = sh->whole_rows_of(i, (int)dn); continue; }
+                if (Np > 1) {
+                    // fetch columns [lo, hi) of shard dn: rank e sends those columns of its quotient-domain rows to the rank whose
+                    // next rows they are (a permutation of the ranks: one all-to-all call)
+                    const size_t wc = hi[k] - lo[k], rows = std::min(Ls, nq), bytes = rows * wc * 8;
                     std::vector<uint64_t> sb(N, 0), rb(N, 0);
-                    const size_t bytes = std::min(Ls, nq) * w * 8;
+                    DevPtr packed(ctx_, bytes);
                     bool need = false;
                     if ((size_t)d < Np) {
                         for (size_t e = 0; e < Np; e++)
                             if (next_of(e) == (size_t)d && e != (size_t)d) sb[e] = bytes;
-                        const size_t dn = next_of((size_t)d);
-                        if (dn != (size_t)d) { rb[dn] = bytes; need = true; }
+                        gpu_check(msgpu_extract_columns_dev(ctx_, sh->views[i], rows, w, lo[k], hi[k], packed.u()));
+                        rb[dn] = bytes;
+                        need = true;
                     }
                     halos.emplace_back(ctx_, need ? bytes : 8);
-                    comm_.alltoall_dev(sh->views[i], sb.data(), halos.back().p, rb.data());
-                    if (need) nxt[k] = halos.back().u();
+                    comm_.alltoall_dev(packed.p, sb.data(), halos.back().p, rb.data());
+                    if (need) {
+                        nxt[k] = halos.back().u();
+                        nw[k] = (uint32_t)wc;
+                        nc0[k] = (uint32_t)lo[k];
+                    }
                 }
             }
             // quotient evaluations of the local rows (stored order) -> all ranks -> the 2q-column quotient LDE on every rank
             DevPtr mine(ctx_, std::max<size_t>(Ls * 16, 16)), all(ctx_, (size_t)N * Ls * 16);
             uint64_t pub[8];
             for (int k = 0; k < 8; k++) pub[k] = j.publics[k].v;
-            gpu_check(msgpu_quotient_values_shard(ctx_, programs_[j.circuit], cur, nxt, row0, n_local, next_row0, j.log_degree,
+            gpu_check(msgpu_quotient_values_shard(ctx_, programs_[j.circuit], cur, nxt, nw, nc0, row0, n_local, next_row0, j.log_degree,
                                                   j.log_quotient_degree, pub, a, mine.u()));
             halos.clear();
             comm_.allgather_dev(mine.p, all.p, Ls * 16);  // the first nq rows of the result are the quotient domain
@@ -617,27 +637,39 @@ class RowShardOpenDevice : public OpenDevice {
             if (ob) memcpy(blob.data() + at, opened.data(), ob);
             if (pb) memcpy(blob.data() + at + ob, paths.data(), pb);
         }
-        if (d == fri_owner_ && n_layers) {
-            std::vector<const msgpu_pdata*> trees;
-            std::vector<uint32_t> shifts;
-            size_t open_total = 0, proof_total = 0;
-            for (size_t k = 0; k < n_layers; k++) {
-                const msgpu_pdata* pd = msgpu_fri_layer_pdata(op_, k);
-                if (!pd) throw RowShardError("open: no such commit-phase layer");
-                trees.push_back(pd);
-                shifts.push_back((uint32_t)(k + 1));
-                open_total += n * 4;
-                proof_total += n * (log_max_height_ - k - 1) * 32;
+        // every rank can compute every rank's share size (the holders follow from the indices): ONE all-gather, padded to the largest
+        std::vector<size_t> share(N, 0);
+        for (size_t r = 0; r < R; r++)
+            for (size_t q = 0; q < n; q++) share[holder[r][q]] += tw[r] * 8 + lo_depth[r] * 32;
+        if (share[d] != blob.size()) throw RowShardError("open: internal error, query share size");
+        size_t mx = 8;
+        for (size_t sz : share) mx = std::max(mx, sz);
+        std::vector<u8> sendbuf(mx, 0), recvbuf(mx * (size_t)N);
+        if (!blob.empty()) memcpy(sendbuf.data(), blob.data(), blob.size());
+        comm_.allgather(sendbuf.data(), recvbuf.data(), mx);
+        std::vector<std::vector<u8>> all(N);
+        for (int e = 0; e < N; e++) all[e].assign(recvbuf.begin() + (size_t)e * mx, recvbuf.begin() + (size_t)e * mx + share[e]);
+        // the commit-phase layers live on the FRI owner: one broadcast of their openings
+        std::vector<u8> layer_blob;
+        if (n_layers) {
+            size_t open_total = n_layers * n * 4, proof_total = 0;
+            for (size_t k = 0; k < n_layers; k++) proof_total += n * (log_max_height_ - k - 1) * 32;
+            layer_blob.resize(open_total * 8 + proof_total);
+            if (d == fri_owner_) {
+                std::vector<const msgpu_pdata*> trees;
+                std::vector<uint32_t> shifts;
+                for (size_t k = 0; k < n_layers; k++) {
+                    const msgpu_pdata* pd = msgpu_fri_layer_pdata(op_, k);
+                    if (!pd) throw RowShardError("open: no such commit-phase layer");
+                    trees.push_back(pd);
+                    shifts.push_back((uint32_t)(k + 1));
+                }
+                std::vector<uint64_t> idx(indices.begin(), indices.end());
+                gpu_check(msgpu_open_batch_multi(ctx_, trees.data(), shifts.data(), trees.size(), idx.data(), n, (uint64_t*)layer_blob.data(),
+                                                 layer_blob.data() + open_total * 8));
             }
-            std::vector<uint64_t> idx(indices.begin(), indices.end()), opened(open_total);
-            std::vector<uint8_t> proofs(std::max<size_t>(proof_total, 1));
-            gpu_check(msgpu_open_batch_multi(ctx_, trees.data(), shifts.data(), trees.size(), idx.data(), n, opened.data(), proofs.data()));
-            const size_t at = blob.size();
-            blob.resize(at + open_total * 8 + proof_total);
-            memcpy(blob.data() + at, opened.data(), open_total * 8);
-            if (proof_total) memcpy(blob.data() + at + open_total * 8, proofs.data(), proof_total);
+            comm_.bcast(layer_blob.data(), layer_blob.size(), fri_owner_);
         }
-        std::vector<std::vector<u8>> all = comm_.allgather_var(blob);
         // the top siblings of every (round, query): the top tree's leaf is the holder's subtree root
         std::vector<std::vector<uint8_t>> top_paths(R);
         for (size_t r = 0; r < R && N > 1; r++) {
@@ -675,7 +707,7 @@ class RowShardOpenDevice : public OpenDevice {
             for (int e = 0; e < N; e++) cursor[e] += cnt[e] * (tw[r] * 8 + lo_depth[r] * 32);
         }
         if (n_layers) {
-            const u8* ob = all[fri_owner_].data() + cursor[fri_owner_];
+            const u8* ob = layer_blob.data();
             const u8* pb = ob + n_layers * n * 32;
             for (size_t k = 0; k < n_layers; k++) {
                 const size_t depth = log_max_height_ - k - 1;
