@@ -55,6 +55,7 @@ int msgpu_malloc(msgpu_ctx* ctx, size_t bytes, void** dptr);
 int msgpu_free(msgpu_ctx* ctx, void* dptr);
 int msgpu_memcpy_h2d(msgpu_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int msgpu_memcpy_d2h(msgpu_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int msgpu_memcpy_d2d(msgpu_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes); /* stream-ordered, does not wait */
 int msgpu_host_alloc(size_t bytes, void** hptr); /* pinned host memory */
 int msgpu_host_free(void* hptr);
 /* Page-lock host memory the caller owns (the Vec behind a p3 `RowMajorMatrix<Goldilocks>`), so that the host-pointer entry points
@@ -125,6 +126,12 @@ int msgpu_commit_dev(msgpu_ctx* ctx, const uint64_t* const* mats, const uint64_t
 /* root32 == NULL: nothing is read back and nothing waits (the root is the last digest of msgpu_pdata_digests). */
 int msgpu_commit_ldes_dev(msgpu_ctx* ctx, uint64_t* const* ldes, const uint64_t* heights, const uint64_t* widths,
                           uint64_t n_mats, int take_ownership, msgpu_pdata** out, uint8_t* root32);
+/* The same where some LDEs still exist as COLUMN BLOCKS (block_ptrs / block_widths[i * n_blocks + b]: dense heights[i] x width_b,
+ * column order; a null first pointer = matrix i is already in ldes[i]): the leaf-hash pass reads the blocks -- which may live in
+ * other GPUs' memory, msgpu_peers_ptr -- and writes the row-major matrix to ldes[i] as it hashes (fused gather + commit). */
+int msgpu_commit_ldes_blocks_dev(msgpu_ctx* ctx, uint64_t* const* ldes, const uint64_t* heights, const uint64_t* widths, uint64_t n_mats,
+                                 uint64_t n_blocks, const uint64_t* const* block_ptrs, const uint64_t* block_widths, int take_ownership,
+                                 msgpu_pdata** out, uint8_t* root32);
 /* ---- one commitment whose matrices live on several GPUs (partitioning A: circuits -> GPUs) ----
  * The MMCS hashes, per LDE height, the rows of all matrices of that height into one leaf digest and injects the shorter
  * classes on the way up (p3-merkle-tree, src/types.rs:82-84). When every height class lives on ONE rank, a rank can hash
@@ -337,6 +344,38 @@ int msgpu_open_finish_values(msgpu_open* op, const uint64_t* total_sums);
 int msgpu_pdata_placeholder(msgpu_ctx* ctx, uint64_t n_mats, const uint64_t* heights, const uint64_t* widths, msgpu_pdata** out);
 int msgpu_ext_add_dev(msgpu_ctx* ctx, uint64_t* dst, const uint64_t* src, uint64_t n_ext);
 int msgpu_ext_add_scalar_dev(msgpu_ctx* ctx, uint64_t* v, uint64_t n_ext, const uint64_t* c2);
+
+/* ---- peer memory over NVLink (multi_stark_b200/csrc/peer.cu) -------------------------------------------------------------------
+ * The row-sharded prover's data plane without pack -> NCCL -> unpack: symmetric device windows, mapped into every rank of the node
+ * with CUDA IPC, that the exchange kernels write into / read from directly (row blocks -> column blocks before the column-local
+ * NTT, column blocks of the LDE -> row shards after it, subtree roots -> every peer). No counterpart in the reference
+ * (single-process CPU prover); the calls replace the exchange steps of host/rowshard_backend.hpp. One process per GPU, every rank
+ * makes the same calls in the same order with the same sizes (so blocks have equal (segment, offset) everywhere).
+ * Growth: msgpu_peers_alloc returns 1 when no window has room; every rank then calls msgpu_peers_segment_create with the same
+ * size, all-gathers the 64-byte handles over its host collective, and calls msgpu_peers_segment_open. */
+#define MSGPU_MAX_PEERS 16
+typedef struct msgpu_peers msgpu_peers;
+int msgpu_peers_create(msgpu_ctx* ctx, int32_t rank, int32_t world, msgpu_peers** out);
+int msgpu_peers_segment_create(msgpu_peers* p, uint64_t bytes, uint8_t* handle64);
+int msgpu_peers_segment_open(msgpu_peers* p, const uint8_t* handles);
+uint64_t msgpu_peers_num_segments(const msgpu_peers* p);
+int msgpu_peers_alloc(msgpu_peers* p, uint64_t bytes, uint32_t* segment, uint64_t* offset);
+int msgpu_peers_free_block(msgpu_peers* p, uint32_t segment, uint64_t offset);
+void* msgpu_peers_ptr(const msgpu_peers* p, uint32_t segment, uint64_t offset, int32_t peer);
+/* stream-ordered: work enqueued afterwards sees everything every peer wrote (and enqueued) before ITS call */
+int msgpu_peers_barrier(msgpu_peers* p);
+/* all-gather by remote stores: `bytes` from src_dev land at offset + rank * bytes of the block on every peer */
+int msgpu_peers_put(msgpu_peers* p, const void* src_dev, uint32_t segment, uint64_t offset, uint64_t bytes);
+/* the 32-byte subtree root of a row-sharded commitment -> slot `rank` on every peer; *gathered_dev = world x 32 bytes (local),
+ * complete after the next msgpu_peers_barrier */
+int msgpu_peers_put_root(msgpu_peers* p, const uint8_t* root_dev, uint8_t** gathered_dev);
+/* after a stream synchronisation: MSGPU_ERR_CUDA if a barrier timed out */
+int msgpu_peers_check(msgpu_peers* p);
+/* The two exchanges of a row-sharded Pcs::commit (src/prover.rs:350,419 on N GPUs): row blocks -> the owners' column blocks
+ * (remote stores) before the column-local LDE, column blocks of the LDE -> this rank's row shard (remote loads) after it. */
+int msgpu_peers_pack_push(msgpu_peers* p, const uint64_t* src_dev, uint64_t rows, uint64_t width, uint32_t segment, uint64_t offset);
+int msgpu_peers_pull_interleave(msgpu_peers* p, uint32_t segment, uint64_t offset, uint64_t rows, uint64_t width, uint64_t* dst_dev);
+void msgpu_peers_destroy(msgpu_peers* p);
 
 /* ---- transcript helper ---------------------------------------------------------------------------
  * Unkeyed BLAKE3-256 of a HOST byte string, hashed on the device (chunk chaining values in parallel, then the

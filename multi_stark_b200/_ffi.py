@@ -112,6 +112,23 @@ SIGNATURES = {
     "msgpu_host_unregister": (C.c_int, [C.c_void_p]),
     "msgpu_ctx_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64]),
     "msgpu_selectors_on_coset": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "msgpu_commit_ldes_blocks_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
+                                               C.c_int, C.c_void_p, C.c_void_p]),
+    "msgpu_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "msgpu_peers_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "msgpu_peers_segment_create": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
+    "msgpu_peers_segment_open": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "msgpu_peers_num_segments": (C.c_uint64, [C.c_void_p]),
+    "msgpu_peers_alloc": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "msgpu_peers_free_block": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64]),
+    "msgpu_peers_ptr": (C.c_void_p, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32]),
+    "msgpu_peers_barrier": (C.c_int, [C.c_void_p]),
+    "msgpu_peers_put": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64]),
+    "msgpu_peers_put_root": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "msgpu_peers_check": (C.c_int, [C.c_void_p]),
+    "msgpu_peers_pack_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64]),
+    "msgpu_peers_pull_interleave": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "msgpu_peers_destroy": (None, [C.c_void_p]),
 }
 
 
@@ -165,6 +182,8 @@ HOST_SIGNATURES = {
     "msh_u32add_workload": (None, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "msh_u32add_workload_seeded": (None, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "msh_rowshard_commit": (C.c_int, [C.c_void_p, c_vpp, c_u64p, c_u64p, C.c_uint64, C.c_int, C.c_void_p]),
+    "msh_rowshard_shardable": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
+    "msh_rowshard_peer_memory": (C.c_int, [C.c_void_p]),
     "msh_rowshard_prover_create": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "msh_dist_prover_create": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "msh_fib_trace": (None, [C.c_uint64, C.c_void_p]),

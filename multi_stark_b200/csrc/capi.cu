@@ -238,6 +238,11 @@ int msgpu_memcpy_d2h(msgpu_ctx* h, void* dst, const void* src, size_t bytes) {
         h->c.sync();
     });
 }
+int msgpu_memcpy_d2d(msgpu_ctx* h, void* dst, const void* src, size_t bytes) {
+    return guard([&] {
+        if (bytes) MSG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, h->c.stream));
+    });
+}
 int msgpu_host_alloc(size_t bytes, void** hptr) {
     return guard([&] { MSG_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 8, cudaHostAllocDefault)); });
 }
@@ -670,15 +675,30 @@ int msgpu_mmcs_commit(msgpu_ctx* h, const uint64_t* const* mats, const uint64_t*
 }
 int msgpu_commit_ldes_dev(msgpu_ctx* h, uint64_t* const* ldes, const uint64_t* heights, const uint64_t* widths,
                           uint64_t n_mats, int take_ownership, msgpu_pdata** out, uint8_t* root32) {
+    return msgpu_commit_ldes_blocks_dev(h, ldes, heights, widths, n_mats, 0, nullptr, nullptr, take_ownership, out, root32);
+}
+// The same where some matrices are still column blocks: block_ptrs[i * n_blocks + b] / block_widths[i * n_blocks + b], b <
+// n_blocks, are the dense heights[i] x width_b column blocks of matrix i in column order (all null for a matrix that is already
+// in ldes[i]). Such a matrix is WRITTEN to ldes[i] by the pass that hashes its rows (merkle.cu, AsmList): the row shard of a
+// column-sharded LDE is assembled from the peers' blocks (pointers from msgpu_peers_ptr) while it is committed.
+int msgpu_commit_ldes_blocks_dev(msgpu_ctx* h, uint64_t* const* ldes, const uint64_t* heights, const uint64_t* widths, uint64_t n_mats,
+                                 uint64_t n_blocks, const uint64_t* const* block_ptrs, const uint64_t* block_widths, int take_ownership,
+                                 msgpu_pdata** out, uint8_t* root32) {
     return guard([&] {
         Ctx& c = h->c;
         MSG_REQUIRE(n_mats > 0, "commit_ldes: no matrices given");
+        MSG_REQUIRE(n_blocks <= 16 && (n_blocks == 0 || (block_ptrs && block_widths)), "commit_ldes: bad column-block list");
         msgpu_pdata* pd = new msgpu_pdata();
         pd->ctx = &c;
         try {
             for (u64 i = 0; i < n_mats; i++) {
                 check_shape(heights[i], widths[i]);
                 pd->mats.push_back(msgpu_pdata::Mat{(u64*)ldes[i], heights[i], widths[i], false});
+                if (n_blocks == 0 || !block_ptrs[i * n_blocks]) continue;
+                for (u64 b = 0; b < n_blocks; b++) {
+                    MSG_REQUIRE(block_ptrs[i * n_blocks + b] || block_widths[i * n_blocks + b] == 0, "commit_ldes: null column block");
+                    pd->mats.back().blocks.push_back({(const u64*)block_ptrs[i * n_blocks + b], block_widths[i * n_blocks + b]});
+                }
             }
             // root32 == NULL: stream-ordered, no read-back (the root is the last digest of msgpu_pdata_digests): a row shard's
             // subtree root goes straight into a device all-gather

@@ -170,8 +170,14 @@ struct MatRef {
     u64 height;
     u64 width;
 };
+// mats[first .. first + count) are the column blocks (dense height x width_b, in column order) of ONE matrix that the leaf pass
+// also writes out, row-major over all its columns, to dst
+struct AsmTarget {
+    size_t first, count;
+    u64* dst;
+};
 // digests[i] = BLAKE3(le_bytes(row i of mats[0]) || le_bytes(row i of mats[1]) ...), all mats same height
-void b3_hash_rows(Ctx& c, const std::vector<MatRef>& mats, uint8_t* digests);
+void b3_hash_rows(Ctx& c, const std::vector<MatRef>& mats, uint8_t* digests, const std::vector<AsmTarget>& assemble = {});
 // next[i] = H(prev[2i] || prev[2i+1]), optionally followed by H(that || inject[i])
 void b3_compress_layer(Ctx& c, const uint8_t* prev, const uint8_t* inject, uint8_t* next, u64 next_len);
 

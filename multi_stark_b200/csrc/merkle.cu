@@ -23,6 +23,21 @@ struct LeafList {
     __device__ __forceinline__ LeafMat at(u32 k) const { return ext ? ext[k] : inl[k]; }
 };
 
+// Matrices that are ASSEMBLED while their rows are hashed: the leaf list names the column blocks of such a matrix (dense
+// height x width_b each, possibly in another GPU's memory, peer.cu); the staged rows -- all columns, in order -- are also
+// written to `dst` (height x width row-major). The row shard of a column-sharded LDE is materialised by the pass that hashes
+// it: the blocks are read once (whole lines over NVLink), no separate interleave pass.
+constexpr int kMaxAsm = 4;
+struct AsmRef {
+    u64* dst;
+    u32 word_off;  // first word of the matrix inside the concatenated row message
+    u32 width;     // columns
+};
+struct AsmList {
+    AsmRef a[kMaxAsm];
+    u32 n;
+};
+
 constexpr int kLeafThreads = 128;
 constexpr int kMaxStack = 24;
 
@@ -85,7 +100,7 @@ __device__ __forceinline__ void hash_words(Get get, u32 total_words, u32 out[8])
 // coalesced global reads turn into conflict-free per-thread row reads.
 __global__ void __launch_bounds__(kLeafThreads) k_hash_rows_staged(const __grid_constant__ LeafList mats, u32 nmats, u64 height,
                                                                    u32 total_words, u32 pitch, u32 rows_per_cta,
-                                                                   u32* out) {
+                                                                   u32* out, const __grid_constant__ AsmList asmb) {
     extern __shared__ u32 sm32[];
     const u64 row0 = (u64)blockIdx.x * rows_per_cta;
     const u32 nrows = (u32)min((u64)rows_per_cta, height - row0);
@@ -102,6 +117,21 @@ __global__ void __launch_bounds__(kLeafThreads) k_hash_rows_staged(const __grid_
         }
     }
     __syncthreads();
+    // assembled matrices: the staged rows go out as one contiguous run of nrows * width elements (stores are not waited for)
+    for (u32 k = 0; k < asmb.n; k++) {
+        const AsmRef ar = asmb.a[k];
+        u64* dst = ar.dst + row0 * ar.width;
+        const u32 total = nrows * ar.width;
+        u32 r = threadIdx.x / ar.width, cc = threadIdx.x % ar.width;
+        const u32 dr = blockDim.x / ar.width, dc = blockDim.x % ar.width;
+        for (u32 e = threadIdx.x; e < total; e += blockDim.x) {
+            const u32* s2 = sm32 + (size_t)r * pitch + ar.word_off + 2 * cc;
+            dst[e] = (u64)s2[0] | ((u64)s2[1] << 32);
+            r += dr;
+            cc += dc;
+            if (cc >= ar.width) { cc -= ar.width; r++; }
+        }
+    }
     if (threadIdx.x < nrows) {
         const u32* row = sm32 + (size_t)threadIdx.x * pitch;
         u32 dg[8];
@@ -120,7 +150,7 @@ __global__ void __launch_bounds__(kLeafThreads) k_hash_rows_staged(const __grid_
 // 6.7 ms instead of 5.4 ms for 2^22 rows of 256 columns; 16-word segments: no further gain).
 constexpr int kSegWords = 32;
 __global__ void __launch_bounds__(kLeafThreads) k_hash_rows_stream(const __grid_constant__ LeafList mats, u32 nmats, u64 height, u32 total_words,
-                                                                   u32* out) {
+                                                                   u32* out, const __grid_constant__ AsmList asmb) {
     __shared__ u32 tile[kLeafThreads][kSegWords + 1];
     const u64 row0 = (u64)blockIdx.x * kLeafThreads;
     const u32 nrows = (u32)min((u64)kLeafThreads, height - row0);
@@ -152,6 +182,22 @@ __global__ void __launch_bounds__(kLeafThreads) k_hash_rows_stream(const __grid_
             }
         }
         __syncthreads();
+        // assembled matrices: the columns of this segment, row by row (up to kSegWords / 2 adjacent elements per row)
+        for (u32 k = 0; k < asmb.n; k++) {
+            const AsmRef ar = asmb.a[k];
+            const u32 w0 = max(seg0, ar.word_off), w1 = min(seg1, ar.word_off + 2u * ar.width);
+            if (w0 >= w1) continue;
+            const u32 c0 = (w0 - ar.word_off) >> 1, ncols = (w1 - w0) >> 1, base = w0 - seg0;
+            u64* dst = ar.dst + row0 * ar.width + c0;
+            u32 r = threadIdx.x / ncols, cc = threadIdx.x % ncols;
+            const u32 dr = kLeafThreads / ncols, dc = kLeafThreads % ncols;
+            while (r < nrows) {
+                dst[(u64)r * ar.width + cc] = (u64)tile[r][base + 2 * cc] | ((u64)tile[r][base + 2 * cc + 1] << 32);
+                r += dr;
+                cc += dc;
+                if (cc >= ncols) { cc -= ncols; r++; }
+            }
+        }
         if (live) {
             const u32* row = tile[threadIdx.x];
 #pragma unroll 1
@@ -421,19 +467,76 @@ void check_canonical(Ctx& c, const u64* v, u64 n, u32* flag_dev) {
     MSG_CUDA(cudaGetLastError());
 }
 
-void b3_hash_rows(Ctx& c, const std::vector<MatRef>& mats, uint8_t* digests) {
+// dst[r][col0_b + c] = blocks[b][r][c] (the fallback of the assembling leaf kernels)
+struct GatherBlocks {
+    const u64* blk[16];
+    u32 col0[17];
+    u32 n;
+    u64 rows;
+    u64* dst;
+};
+__global__ void __launch_bounds__(256) k_gather_blocks(const __grid_constant__ GatherBlocks p) {
+    const u32 W = p.col0[p.n];
+    const u64 total = p.rows * W;
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (u64)gridDim.x * blockDim.x) {
+        const u64 r = e / W;
+        const u32 col = (u32)(e % W);
+        u32 b = 0;
+        while (b + 1 < p.n && p.col0[b + 1] <= col) b++;
+        p.dst[e] = p.blk[b][r * (p.col0[b + 1] - p.col0[b]) + (col - p.col0[b])];
+    }
+}
+
+void b3_hash_rows(Ctx& c, const std::vector<MatRef>& mats, uint8_t* digests, const std::vector<AsmTarget>& assemble) {
     MSG_REQUIRE(!mats.empty(), "hash_rows: no matrices");
     u64 height = mats[0].height;
     std::vector<LeafMat> lm;
+    std::vector<u32> word_off_of(mats.size(), 0);
     u64 words = 0;
-    for (auto& m : mats) {
+    for (size_t i = 0; i < mats.size(); i++) {
+        auto& m = mats[i];
         MSG_REQUIRE(m.height == height, "hash_rows: heights differ");
         MSG_REQUIRE(words + 2 * m.width < (1ull << 30), "hash_rows: row too wide");
+        word_off_of[i] = (u32)words;
         if (m.width == 0) continue;
         lm.push_back(LeafMat{m.ptr, (u32)m.width, (u32)words});
         words += 2 * m.width;
     }
     if (height == 0) return;
+    // an assembly target that the leaf kernel cannot take (more than kMaxAsm in one class, rows too wide to stage) is gathered by
+    // a pass of its own; its blocks are then hashed as they are
+    auto gather = [&](const AsmTarget& t) {
+        GatherBlocks gb{};
+        u64 w = 0;
+        for (size_t k = 0; k < t.count; k++) {
+            gb.blk[k] = mats[t.first + k].ptr;
+            gb.col0[k] = (u32)w;
+            w += mats[t.first + k].width;
+        }
+        gb.col0[t.count] = (u32)w;
+        gb.n = (u32)t.count;
+        gb.rows = height;
+        gb.dst = t.dst;
+        if (w == 0) return;
+        KLaunch kl(c, "k_gather_blocks");
+        k_gather_blocks<<<(unsigned)std::min<u64>((height * w + 255) / 256, (u64)c.sm_count * 16), 256, 0, c.stream>>>(gb);
+        MSG_CUDA(cudaGetLastError());
+    };
+    u32 total_words = (u32)words;
+    u32 pitch = total_words | 1u;
+    size_t budget = 96 * 1024;
+    u32 rows = (u32)std::min<size_t>(kLeafThreads, budget / ((size_t)pitch * 4));
+    const bool use_stream = rows < (u32)kLeafThreads && total_words * 4u > 1024u && height >= 32;
+    const bool use_staged = !use_stream && (rows >= 32 || (u64)rows >= height);
+    AsmList asmb{};
+    for (auto& t : assemble) {
+        MSG_REQUIRE(t.first < mats.size() && t.first + t.count <= mats.size() && t.count >= 1 && t.count <= 16 && t.dst, "hash_rows: bad assembly target");
+        u64 w = 0;
+        for (size_t k = 0; k < t.count; k++) w += mats[t.first + k].width;
+        if (w == 0) continue;
+        if (asmb.n < (u32)kMaxAsm && (use_stream || use_staged)) asmb.a[asmb.n++] = AsmRef{t.dst, word_off_of[t.first], (u32)w};
+        else gather(t);
+    }
     LeafList d_mats{};
     LeafMat* d_ext = nullptr;
     if (lm.size() <= (size_t)kInlineMats) {
@@ -443,22 +546,18 @@ void b3_hash_rows(Ctx& c, const std::vector<MatRef>& mats, uint8_t* digests) {
         MSG_CUDA(cudaMemcpyAsync(d_ext, lm.data(), lm.size() * sizeof(LeafMat), cudaMemcpyHostToDevice, c.stream));
         d_mats.ext = d_ext;
     }
-    u32 total_words = (u32)words;
-    u32 pitch = total_words | 1u;
-    size_t budget = 96 * 1024;
-    u32 rows = (u32)std::min<size_t>(kLeafThreads, budget / ((size_t)pitch * 4));
-    if (rows < (u32)kLeafThreads && total_words * 4u > 1024u && height >= 32) {
+    if (use_stream) {
         u64 blocks = (height + kLeafThreads - 1) / kLeafThreads;
         KLaunch kl(c, "k_hash_rows_stream");
-        k_hash_rows_stream<<<(unsigned)blocks, kLeafThreads, 0, c.stream>>>(d_mats, (u32)lm.size(), height, total_words, (u32*)digests);
-    } else if (rows >= 32 || (u64)rows >= height) {
+        k_hash_rows_stream<<<(unsigned)blocks, kLeafThreads, 0, c.stream>>>(d_mats, (u32)lm.size(), height, total_words, (u32*)digests, asmb);
+    } else if (use_staged) {
         if (rows > 32) rows = rows / 32 * 32;
         if (rows == 0) rows = 1;
         ensure_max_smem(k_hash_rows_staged, (int)budget);
         u64 blocks = (height + rows - 1) / rows;
         KLaunch kl(c, "k_hash_rows_staged");
         k_hash_rows_staged<<<(unsigned)blocks, kLeafThreads, (size_t)rows * pitch * 4, c.stream>>>(
-            d_mats, (u32)lm.size(), height, total_words, pitch, rows, (u32*)digests);
+            d_mats, (u32)lm.size(), height, total_words, pitch, rows, (u32*)digests, asmb);
     } else {
         u64 blocks = (height + kLeafThreads - 1) / kLeafThreads;
         KLaunch kl(c, "k_hash_rows_direct");

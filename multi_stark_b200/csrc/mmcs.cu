@@ -34,20 +34,32 @@ static std::vector<std::pair<u64, uint8_t*>> hash_classes(Ctx& c, msgpu_pdata* p
     while (pos < order.size()) {
         u64 h = pd->mats[order[pos]].height;
         std::vector<MatRef> group;
+        std::vector<AsmTarget> assemble;
         while (pos < order.size() && pd->mats[order[pos]].height == h) {
             auto& m = pd->mats[order[pos++]];
-            group.push_back(MatRef{m.ptr, m.height, m.width});
+            if (m.blocks.empty()) {
+                group.push_back(MatRef{m.ptr, m.height, m.width});
+                continue;
+            }
+            u64 w = 0;
+            assemble.push_back(AsmTarget{group.size(), m.blocks.size(), m.ptr});
+            for (auto& b : m.blocks) {
+                group.push_back(MatRef{b.first, m.height, b.second});
+                w += b.second;
+            }
+            MSG_REQUIRE(w == m.width, "commit: the column blocks of a matrix do not add up to its width");
         }
         uint8_t* out = (classes.empty() && first_out) ? first_out : (uint8_t*)c.alloc(h * 32);
         classes.push_back({h, out});
         try {
-            b3_hash_rows(c, group, out);
+            b3_hash_rows(c, group, out, assemble);
         } catch (...) {
             for (auto& cl : classes)
                 if (cl.second != first_out) c.free(cl.second);
             throw;
         }
     }
+    for (auto& m : pd->mats) m.blocks.clear();  // every matrix is materialised now
     return classes;
 }
 

@@ -8,6 +8,9 @@ struct msgpu_pdata {
         u64* ptr;
         u64 height, width;
         bool owned;
+        // not empty: `ptr` is still to be written -- the rows are read from these column blocks (pointer, width; dense
+        // height x width_b, in column order, possibly in a peer GPU's memory) by the leaf-hash pass, which writes ptr as it goes
+        std::vector<std::pair<const u64*, u64>> blocks;
     };
     msg::Ctx* ctx = nullptr;
     std::vector<Mat> mats;           // original (commit) order

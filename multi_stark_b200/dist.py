@@ -117,7 +117,7 @@ _ALLGATHER_DEV = _C.CFUNCTYPE(_C.c_int, _C.c_void_p, _C.c_void_p, _C.c_void_p, _
 class MshComm(_C.Structure):
     """`msh_comm` of host/dist_backend.hpp"""
     _fields_ = [("user", _C.c_void_p), ("rank", _C.c_int32), ("world", _C.c_int32), ("allgather_host", _ALLGATHER),
-                ("bcast_host", _BCAST), ("sendrecv_dev", _SENDRECV), ("alltoall_dev", _ALLTOALL), ("allgather_dev", _ALLGATHER_DEV)]
+                ("bcast_host", _BCAST), ("sendrecv_dev", _SENDRECV), ("alltoall_dev", _ALLTOALL), ("allgather_dev", _ALLGATHER_DEV), ("peer_memory", _C.c_int32)]
 
 
 class _DevView:
@@ -154,7 +154,10 @@ class TorchComm:
                 raise ValueError("TorchComm: create the GpuContext on torch's current stream (GpuContext(dev, stream=torch.cuda.current_stream().cuda_stream))")
         self._cb = (_ALLGATHER(self._allgather), _BCAST(self._bcast), _SENDRECV(self._sendrecv), _ALLTOALL(self._alltoall_cb),
                     _ALLGATHER_DEV(self._allgather_dev_cb))  # keep the thunks alive
-        self.struct = MshComm(None, self.rank, self.world, *self._cb)
+        # peer memory (csrc/peer.cu): NCCL ranks of one node, one GPU each; MSGPU_P2P=0 keeps every exchange on the collectives
+        self.peer_memory = int(self.nccl and self.world > 1 and os.environ.get("MSGPU_P2P", "1") != "0"
+                               and torch.cuda.device_count() >= self.world)
+        self.struct = MshComm(None, self.rank, self.world, *self._cb, self.peer_memory)
 
     # ---- host buffers
     def _host_tensor(self, ptr, nbytes):
@@ -446,7 +449,12 @@ class RowShardProver:
 
     def shardable(self, height, width):
         """the backend's rule (RowShardBackend::shardable): such a trace is read as natural-order row blocks"""
-        return self.comm.world > 1 and width >= self.comm.world and height >= self.comm.world * 64
+        return self.H.msh_rowshard_shardable(self.h, int(height), int(width)) == 1
+
+    @property
+    def peer_memory(self):
+        """True when the ranks exchange matrices through each other's device memory (csrc/peer.cu) rather than NCCL"""
+        return self.H.msh_rowshard_peer_memory(self.h) == 1
 
     def block_rows(self, height, width):
         """(row0, rows) of the part of a height x width trace this rank reads"""

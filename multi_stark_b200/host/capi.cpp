@@ -177,6 +177,17 @@ msh_prover* msh_rowshard_prover_create(msh_system* s, msgpu_ctx* ctx, const msh_
         return nullptr;
     }
 }
+// 1 = a height x width trace is read as natural-order row blocks by the row-sharded prover (RowShardBackend::shardable; the rule
+// depends on whether peer memory could be set up), 0 = every rank reads all of it, -1 = not a row-sharded prover
+int msh_rowshard_shardable(msh_prover* p, uint64_t height, uint64_t width) {
+    auto* be = dynamic_cast<RowShardBackend*>(p->backend.get());
+    if (!be) return -1;
+    return be->shardable((size_t)height, (size_t)width) ? 1 : 0;
+}
+int msh_rowshard_peer_memory(msh_prover* p) {
+    auto* be = dynamic_cast<RowShardBackend*>(p->backend.get());
+    return be && be->peer_memory() ? 1 : 0;
+}
 // Pcs::commit over the row shards alone (bench.py's strong-scaling step): mats[i] = this rank's natural-order ROW BLOCK of matrix
 // i (rows [d h / N, (d + 1) h / N) when RowShardProver.shardable(h, w), else the whole matrix), DEVICE pointers (host = 0) or
 // HOST pointers to the FULL matrices (host = 1: each rank uploads the rows it reads). Every rank gets the root.
@@ -188,7 +199,7 @@ int msh_rowshard_commit(msh_prover* p, const uint64_t* const* mats, const uint64
         std::vector<RowBlocks> blocks;
         struct Free {
             RowShardBackend* b; std::vector<RowBlocks>& v; bool on;
-            ~Free() { if (on) for (auto& x : v) if (x.dev) msgpu_free(b->ctx(), x.dev); }
+            ~Free() { if (on) for (auto& x : v) b->free_blocks(x); }
         } fr{be, blocks, host != 0};
         for (uint64_t i = 0; i < n; i++) {
             if (host) {

@@ -37,6 +37,10 @@ typedef struct msh_comm {
     // of `recv` comes from rank e. all-gather: `recv` receives world chunks of `bytes` in rank order.
     int (*alltoall_dev)(void* user, void* send, const uint64_t* send_bytes, void* recv, const uint64_t* recv_bytes);
     int (*allgather_dev)(void* user, void* send, void* recv, uint64_t bytes);
+    // 1 = every rank drives its own GPU of ONE node and the processes may map each other's device memory (CUDA IPC): the
+    // row-sharded prover then moves its matrices with NVLink loads / stores from inside its kernels (csrc/peer.cu) and keeps the
+    // callbacks above for the small host-side exchanges. 0 = collectives only (gloo tests, several ranks on one device).
+    int32_t peer_memory;
 } msh_comm;
 }
 

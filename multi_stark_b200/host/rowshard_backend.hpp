@@ -22,6 +22,10 @@
 //     shards (16 bytes per LDE row) added into the FRI owner's vectors; the FRI fold-and-commit rounds run on the owner with the
 //     transcript on the device and ONE broadcast of roots and final polynomial (the other ranks replay the transcript); query
 //     rows and lower sibling paths come from the rank that holds the row, the top log2 N siblings from the replicated top tree.
+// With peer memory (msh_comm::peer_memory, csrc/peer.cu) the exchanges of a commitment are kernels of this library over NVLink:
+// row blocks are written straight into the owners' column blocks (remote stores), row shards are assembled from the peers'
+// LDE column blocks (remote loads), the subtree roots are stored into every peer's window, and the only synchronisation is a
+// flag barrier in peer memory (no host round trip, no NCCL launch): three barriers per commitment.
 // Nothing of the size of a committed matrix is ever gathered on one rank. The proof is byte-identical to the single-GPU proof
 // (tests/test_gpu_rowshard.py).
 #pragma once
@@ -33,6 +37,13 @@ struct RowShardError : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 
+// A block of the symmetric peer heap: the same (segment, offset) on every rank.
+struct SymBlock {
+    uint32_t seg = 0;
+    uint64_t off = 0;
+    bool live = false;
+};
+
 // Pcs::ProverData of a row-sharded commitment.
 struct RowShardHandle : PcsHandle {
     msgpu_ctx* ctx = nullptr;
@@ -41,6 +52,9 @@ struct RowShardHandle : PcsHandle {
     std::vector<uint64_t*> views;                   // this rank's rows of matrix i: shapes[i].first / n_shards rows
     std::vector<bool> whole;                        // views[i] points into the WHOLE LDE (every rank has every row)
     std::vector<uint64_t*> owned;                   // device buffers behind the views (shard buffers or whole LDEs)
+    // (pointer, width) of the column blocks a view is still to be assembled from (peer memory: the shard is written by the
+    // pass that hashes it); empty once the commitment is built
+    std::vector<std::vector<std::pair<const uint64_t*, uint64_t>>> pending;
     msgpu_pdata* local = nullptr;                   // MMCS over the views: leaf digests + subtree of this rank's rows
     msgpu_pdata* top = nullptr;                     // the top log2(n_shards) levels over the subtree roots
     ~RowShardHandle() override {
@@ -93,8 +107,19 @@ class RowShardBackend : public GpuBackend {
         for (auto& c : shape_.circuits)  // a wrap-around next-row read inside a lookup would need a one-row halo between the blocks
             for (size_t i = 0; i < c.graph.lookup_prefix_len; i++)
                 if (c.graph.nodes[i].op == Op::Var && c.graph.nodes[i].col.offset == RowOffset::Next) lookup_next_ = true;
+        if (comm.peer_memory && n > 1) init_peers();
     }
-    ~RowShardBackend() override { RowShardBackend::end_proof(); }
+    ~RowShardBackend() override {
+        RowShardBackend::end_proof();
+        if (peers_) msgpu_peers_destroy(peers_);
+    }
+    bool peer_memory() const { return peers_ != nullptr; }
+    // matrices that take the peer-memory path: split by columns for the NTT, and tall enough for a two-pass transform
+    bool peer_path(size_t height, size_t width) const { return peers_ && shardable(height, width); }
+    void free_blocks(RowBlocks& b) {
+        if (b.dev) msgpu_free(ctx_, b.dev);
+        b.dev = nullptr;
+    }
 
     int world() const { return comm_.world(); }
     int rank() const { return comm_.rank(); }
@@ -102,7 +127,12 @@ class RowShardBackend : public GpuBackend {
     msgpu_ctx* ctx() const { return ctx_; }
 
     // wide and tall enough to be split by columns for the NTT and by rows afterwards
-    bool shardable(size_t height, size_t width) const { return (int)width >= world() && height >= (size_t)world() * 64 && world() > 1; }
+    // With peer memory any width is split (a rank may hold no column of a narrow matrix during the NTT: it still hashes its rows).
+    bool shardable(size_t height, size_t width) const {
+        if (world() <= 1) return false;
+        if (peers_) return width >= 1 && height >= 2048 && height >= (size_t)world() * 64;
+        return (int)width >= world() && height >= (size_t)world() * 64;
+    }
 
     // ---- commitments ---------------------------------------------------------------------------------------------------
     // rows of this rank's shard of the LDE of `m` (shardable: column-sharded NTT between two all-to-alls; otherwise the whole LDE
@@ -169,15 +199,41 @@ class RowShardBackend : public GpuBackend {
             gpu_check(msgpu_commit_ldes_dev(ctx_, ptrs.data(), hs.data(), ws.data(), ptrs.size(), 0, &h->local, root.data()));
             return h;
         }
+        // views that are still column blocks in the peers' windows are assembled by the leaf-hash pass itself
+        std::vector<const uint64_t*> bptr;
+        std::vector<uint64_t> bwid;
+        uint64_t n_blocks = 0;
+        h->pending.resize(h->shapes.size());
+        for (auto& pb : h->pending) n_blocks = std::max<uint64_t>(n_blocks, pb.size());
+        if (n_blocks) {
+            bptr.assign(ptrs.size() * n_blocks, nullptr);
+            bwid.assign(ptrs.size() * n_blocks, 0);
+            for (size_t i = 0; i < h->pending.size(); i++)
+                for (size_t b = 0; b < h->pending[i].size(); b++) {
+                    bptr[i * n_blocks + b] = h->pending[i][b].first;
+                    bwid[i * n_blocks + b] = h->pending[i][b].second;
+                }
+        }
         // leaf digests + subtree, stream-ordered (no read-back); the 32-byte subtree roots are all-gathered on the device and the
         // top levels built from them: ONE host synchronisation per commitment, for the root the transcript needs
-        gpu_check(msgpu_commit_ldes_dev(ctx_, ptrs.data(), hs.data(), ws.data(), ptrs.size(), 0, &h->local, nullptr));
+        gpu_check(msgpu_commit_ldes_blocks_dev(ctx_, ptrs.data(), hs.data(), ws.data(), ptrs.size(), n_blocks, n_blocks ? bptr.data() : nullptr,
+                                               n_blocks ? bwid.data() : nullptr, 0, &h->local, nullptr));
+        h->pending.clear();
         uint8_t* dg = nullptr;
         uint64_t nd = 0;
         gpu_check(msgpu_pdata_digests(h->local, &dg, &nd));
+        uint64_t hh = (uint64_t)N;
+        if (peers_) {
+            // every rank stores its root into slot `rank` of every peer's ring entry; the flag barrier publishes them
+            uint8_t* gathered = nullptr;
+            gpu_check(msgpu_peers_put_root(peers_, dg + (nd - 1) * 32, &gathered));
+            gpu_check(msgpu_peers_barrier(peers_));
+            const uint8_t* pp = gathered;
+            gpu_check(msgpu_tree_from_digests(ctx_, 1, &hh, &pp, &h->top, root.data()));
+            return h;
+        }
         DevPtr d_roots(ctx_, 32 * (size_t)N);
         comm_.allgather_dev(dg + (nd - 1) * 32, d_roots.p, 32);
-        uint64_t hh = (uint64_t)N;
         const uint8_t* pp = (const uint8_t*)d_roots.p;
         gpu_check(msgpu_tree_from_digests(ctx_, 1, &hh, &pp, &h->top, root.data()));
         return h;
@@ -189,15 +245,64 @@ class RowShardBackend : public GpuBackend {
         h->n_shards = world();
         h->shard = rank();
         const uint32_t lb = (uint32_t)shape_.log_blowup();
-        for (auto& m : mats) {
+        const size_t N = (size_t)world(), d = (size_t)rank();
+        // Peer-memory matrices. Blocks of the symmetric heap, the same (segment, offset) on every rank: col = this rank's dense
+        // column block of the evaluations (written by every rank), lde = its column block of the LDE (read by every rank).
+        std::vector<SymBlock> col(mats.size()), lde(mats.size()), held;
+        struct FreeHeld { RowShardBackend* b; std::vector<SymBlock>& v; ~FreeHeld() { for (auto& x : v) msgpu_peers_free_block(b->peers_, x.seg, x.off); } } fh{this, held};
+        bool any_peer = false;
+        for (size_t i = 0; i < mats.size(); i++) {
+            const RowBlocks& m = mats[i];
+            if (m.whole || !peer_path(m.height, m.width)) continue;
+            any_peer = true;
+            const size_t wmax = (m.width + N - 1) / N;
+            col[i] = sym_alloc(m.height * wmax * 8);
+            held.push_back(col[i]);
+            lde[i] = sym_alloc((m.height << lb) * wmax * 8);
+            held.push_back(lde[i]);
+            // my rows of every rank's column block: remote stores, contiguous per destination
+            gpu_check(msgpu_peers_pack_push(peers_, m.dev, m.height / N, m.width, col[i].seg, col[i].off));
+        }
+        if (any_peer) gpu_check(msgpu_peers_barrier(peers_));  // every rank's rows have landed in this rank's column blocks
+        for (size_t i = 0; i < mats.size(); i++) {
+            const RowBlocks& m = mats[i];
+            if (!col[i].live) continue;
+            const size_t w = m.width, base = w / N, rem = w % N, wd = base + (d < rem ? 1 : 0);
+            if (wd == 0) continue;  // a matrix narrower than the number of ranks: this rank extends no column of it
+            gpu_check(msgpu_coset_lde_batch_bitrev_dev(ctx_, sym_ptr(col[i]), m.height, wd, lb, GL_GENERATOR, sym_ptr(lde[i])));
+        }
+        if (any_peer) gpu_check(msgpu_peers_barrier(peers_));  // every rank's column block of every LDE is complete
+        for (size_t i = 0; i < mats.size(); i++) {
+            const RowBlocks& m = mats[i];
             uint64_t *owned = nullptr, *view = nullptr;
             bool whole = false;
-            lde_shard(m, &owned, &view, &whole);
-            h->owned.push_back(owned);
+            if (col[i].live) {
+                // my row shard from every rank's column block: remote loads of whole lines
+                const size_t Ls = (m.height << lb) / N;
+                void* shard = nullptr;
+                gpu_check(msgpu_malloc(ctx_, Ls * m.width * 8, &shard));
+                owned = view = (uint64_t*)shard;
+                h->owned.push_back(owned);
+                // ... inside the pass that hashes them (commit_shards): block e = rank e's columns of my rows
+                std::vector<std::pair<const uint64_t*, uint64_t>> blocks;
+                const size_t base = m.width / N, rem = m.width % N;
+                for (size_t e = 0; e < N; e++) {
+                    const size_t wde = base + (e < rem ? 1 : 0);
+                    const uint64_t* p = (const uint64_t*)msgpu_peers_ptr(peers_, lde[i].seg, lde[i].off, (int32_t)e);
+                    if (!p) throw RowShardError("peer heap: internal error, unmapped block");
+                    blocks.push_back({p + d * Ls * wde, wde});
+                }
+                h->pending.resize(i + 1);
+                h->pending[i] = std::move(blocks);
+            } else {
+                lde_shard(m, &owned, &view, &whole);
+                h->owned.push_back(owned);
+            }
             h->views.push_back(view);
             h->whole.push_back(whole);
             h->shapes.push_back({m.height << lb, m.width});
         }
+        // the root barrier inside commit_shards orders every rank's loads from the column blocks before their release
         return commit_shards(h, root);
     }
 
@@ -215,7 +320,7 @@ class RowShardBackend : public GpuBackend {
     // System::new: the preprocessed commitment (src/system.rs:180-196)
     PcsHandlePtr commit(const std::vector<const Matrix*>& evals, Digest& root) override {
         std::vector<RowBlocks> mats;
-        struct Free { msgpu_ctx* c; std::vector<RowBlocks>& v; ~Free() { for (auto& b : v) if (b.dev) msgpu_free(c, b.dev); } } fr{ctx_, mats};
+        struct Free { RowShardBackend* be; std::vector<RowBlocks>& v; ~Free() { for (auto& b : v) be->free_blocks(b); } } fr{this, mats};
         for (auto* m : evals) mats.push_back(upload_blocks((const uint64_t*)m->values.data(), m->height(), m->width));
         return commit_blocks(mats, root);
     }
@@ -262,7 +367,7 @@ class RowShardBackend : public GpuBackend {
         const int N = world(), d = rank();
         uint64_t b[2] = {beta.c[0].v, beta.c[1].v}, g[2] = {gamma.c[0].v, gamma.c[1].v};
         std::vector<RowBlocks> s2;
-        struct Free { msgpu_ctx* c; std::vector<RowBlocks>& v; ~Free() { for (auto& x : v) if (x.dev) msgpu_free(c, x.dev); } } fr{ctx_, s2};
+        struct Free { RowShardBackend* be; std::vector<RowBlocks>& v; ~Free() { for (auto& x : v) be->free_blocks(x); } } fr{this, s2};
         std::vector<uint64_t> sums(2 * active_.size(), 0);
         for (size_t p = 0; p < active_.size(); p++) {
             const Circuit& c = shape_.circuits[active_[p]];
@@ -309,13 +414,12 @@ class RowShardBackend : public GpuBackend {
             void* full = nullptr;
             gpu_check(msgpu_malloc(ctx_, s2[p].height * w * 8, &full));
             comm_.allgather_dev(s2[p].dev, full, nb * w * 8);
-            msgpu_free(ctx_, s2[p].dev);
+            free_blocks(s2[p]);
             s2[p].dev = (uint64_t*)full;
             s2[p].whole = true;
         }
         auto h = commit_blocks(s2, root);
-        for (auto& m : main_)
-            if (m.dev) msgpu_free(ctx_, m.dev);
+        for (auto& m : main_) free_blocks(m);
         main_.clear();
         return h;
     }
@@ -415,8 +519,7 @@ class RowShardBackend : public GpuBackend {
 
     void end_proof() override {
         drop_claims();
-        for (auto& m : main_)
-            if (m.dev) msgpu_free(ctx_, m.dev);
+        for (auto& m : main_) free_blocks(m);
         main_.clear();
         trace_rows_.clear();
         active_.clear();
@@ -434,7 +537,60 @@ class RowShardBackend : public GpuBackend {
         uint64_t* u() const { return (uint64_t*)p; }
     };
 
+    // ---- the symmetric peer heap -----------------------------------------------------------------------------------------
+    // Every rank makes the same calls with the same sizes, so the deterministic allocator returns the same (segment, offset)
+    // everywhere. A request that fits nowhere grows the heap by one window on all ranks at once (handles all-gathered on the host).
+    SymBlock sym_alloc(size_t bytes) {
+        SymBlock b;
+        int rc = msgpu_peers_alloc(peers_, bytes, &b.seg, &b.off);
+        if (rc == 1) {
+            sym_grow(bytes);
+            rc = msgpu_peers_alloc(peers_, bytes, &b.seg, &b.off);
+            if (rc == 1) throw RowShardError("peer heap: internal error, a fresh window cannot hold the block it was made for");
+        }
+        gpu_check(rc);
+        b.live = true;
+        return b;
+    }
+    uint64_t* sym_ptr(const SymBlock& b) const { return (uint64_t*)msgpu_peers_ptr(peers_, b.seg, b.off, comm_.rank()); }
+
   private:
+    // collective; returns false when any rank failed (the heap is then unusable on every rank)
+    bool sym_grow_try(size_t need) {
+        const int N = world();
+        size_t bytes = std::max<size_t>(need + (1u << 16), (size_t)1 << 30);
+        if (const char* e = getenv("MSGPU_PEER_WINDOW_MB")) bytes = std::max<size_t>(need + (1u << 16), (size_t)atoll(e) << 20);
+        bytes = (bytes + ((size_t)1 << 21) - 1) >> 21 << 21;
+        std::vector<uint8_t> mine(72, 0), all(72 * (size_t)N);
+        int32_t rc = msgpu_peers_segment_create(peers_, bytes, mine.data());
+        memcpy(mine.data() + 64, &rc, 4);
+        comm_.allgather(mine.data(), all.data(), 72);
+        std::vector<uint8_t> handles(64 * (size_t)N);
+        bool ok = true;
+        for (int e = 0; e < N; e++) {
+            int32_t r;
+            memcpy(&r, all.data() + 72 * (size_t)e + 64, 4);
+            ok = ok && r == 0;
+            memcpy(handles.data() + 64 * (size_t)e, all.data() + 72 * (size_t)e, 64);
+        }
+        int32_t rc2 = ok ? msgpu_peers_segment_open(peers_, handles.data()) : -1;
+        std::vector<int32_t> rcs(N);
+        comm_.allgather(&rc2, rcs.data(), 4);
+        for (int32_t r : rcs) ok = ok && r == 0;
+        return ok;
+    }
+    void sym_grow(size_t need) {
+        if (!sym_grow_try(need)) throw RowShardError(std::string("peer heap: a window could not be created or mapped on every rank: ") + msgpu_last_error());
+    }
+    void init_peers() {
+        gpu_check(msgpu_peers_create(ctx_, comm_.rank(), comm_.world(), &peers_));
+        if (!sym_grow_try(0)) {  // no CUDA IPC between these processes: every rank falls back to the collectives
+            msgpu_peers_destroy(peers_);
+            peers_ = nullptr;
+            if (getenv("MSH_TRACE")) fprintf(stderr, "[rowshard] rank %d: peer memory unavailable (%s), using collectives\n", comm_.rank(), msgpu_last_error());
+        }
+    }
+    msgpu_peers* peers_ = nullptr;
     RowShardComm comm_;
     std::vector<RowBlocks> main_;  // the natural-order traces (row blocks or whole), kept for the stage-2 construction
     int claims_rank_ = 0;
