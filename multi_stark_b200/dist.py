@@ -146,6 +146,7 @@ class TorchComm:
         self.seconds = {}    # wall time spent inside the callbacks, by kind
         self._stage = None
         self.trace = bool(os.environ.get("MSH_TRACE"))
+        self.trace2 = int(os.environ.get("MSH_TRACE") or 0) >= 2
         if self.nccl:
             # NCCL calls are ordered against torch's CURRENT stream, the library's kernels against the context's: they must be
             # the same stream, or a send could leave before the kernel that fills the buffer has run
@@ -163,7 +164,25 @@ class TorchComm:
     def _host_tensor(self, ptr, nbytes):
         return torch.frombuffer((_C.c_uint8 * nbytes).from_address(ptr), dtype=torch.uint8)
 
+    def _t2(self, what, n=0):
+        if self.trace2:
+            print("[comm %d] %s %d" % (self.rank, what, n), file=sys.stderr, flush=True)
+
+    def _same_call(self, kind):
+        """gloo only: the staged device exchanges below move data pairwise, so a rank that SKIPPED one (a rank-dependent branch
+        around a collective -- a hang under NCCL) would go unnoticed by the single-GPU tests. Every rank announces (sequence
+        number, kind) first; a mismatch fails the call on every rank."""
+        if self.nccl:
+            return
+        self._seq = getattr(self, "_seq", 0) + 1
+        mine = torch.tensor([self._seq, kind], dtype=torch.int64)
+        allv = torch.empty(2 * self.world, dtype=torch.int64)
+        self.dist.all_gather_into_tensor(allv, mine, group=self.group)
+        if any(allv[2 * r] != self._seq or allv[2 * r + 1] != kind for r in range(self.world)):
+            raise RuntimeError("ranks disagree on the sequence of device collectives: %s" % allv.tolist())
+
     def _allgather(self, user, send, recv, nbytes):
+        self._t2("allgather_host", nbytes)
         t0 = time.perf_counter()
         try:
             return self._allgather_impl(send, recv, nbytes)
@@ -210,6 +229,7 @@ class TorchComm:
             return 1
 
     def _bcast(self, user, buf, nbytes, root):
+        self._t2("bcast_host", nbytes)
         t0 = time.perf_counter()
         try:
             nbytes = int(nbytes)
@@ -273,6 +293,8 @@ class TorchComm:
 
 def _all_to_all_dev(self, send_ptr, send_counts, recv_ptr, recv_counts):
     """Device all-to-all with per-peer byte counts (chunks in rank order in both buffers)."""
+    self._t2("alltoall_dev", sum(send_counts))
+    self._same_call(1)
     t0 = time.perf_counter()
     self.bytes_dev += sum(send_counts) - send_counts[self.rank] + sum(recv_counts) - recv_counts[self.rank]
     if self.nccl:
@@ -320,8 +342,10 @@ def _alltoall_cb(self, user, send, send_bytes, recv, recv_bytes):
 
 def _allgather_dev_cb(self, user, send, recv, nbytes):
     """Device all-gather of equal chunks: recv = world chunks of nbytes in rank order."""
+    self._t2("allgather_dev", nbytes)
     t0 = time.perf_counter()
     try:
+        self._same_call(2)
         nbytes = int(nbytes)
         self.bytes_dev += nbytes * (self.world - 1) * 2
         if self.nccl:

@@ -82,6 +82,15 @@ struct RowShardComm : CommView {
     }
 };
 
+// MSH_TRACE=2: one line per protocol step and rank on stderr (a rank that stops printing is where a multi-GPU run hangs)
+inline void rs_trace(int rank, const char* what, size_t a = 0, size_t b = 0) {
+    static const bool on = getenv("MSH_TRACE") && atoi(getenv("MSH_TRACE")) >= 2;
+    if (on) {
+        fprintf(stderr, "[rs %d] %s %zu %zu\n", rank, what, a, b);
+        fflush(stderr);
+    }
+}
+
 inline unsigned rs_rev_bits(unsigned x, unsigned bits) {
     unsigned r = 0;
     for (unsigned i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
@@ -230,6 +239,7 @@ class RowShardBackend : public GpuBackend {
             gpu_check(msgpu_peers_barrier(peers_));
             const uint8_t* pp = gathered;
             gpu_check(msgpu_tree_from_digests(ctx_, 1, &hh, &pp, &h->top, root.data()));
+            rs_trace(rank(), "root");
             return h;
         }
         DevPtr d_roots(ctx_, 32 * (size_t)N);
@@ -251,6 +261,7 @@ class RowShardBackend : public GpuBackend {
         std::vector<SymBlock> col(mats.size()), lde(mats.size()), held;
         struct FreeHeld { RowShardBackend* b; std::vector<SymBlock>& v; ~FreeHeld() { for (auto& x : v) msgpu_peers_free_block(b->peers_, x.seg, x.off); } } fh{this, held};
         bool any_peer = false;
+        rs_trace(rank(), "commit_blocks", mats.size());
         for (size_t i = 0; i < mats.size(); i++) {
             const RowBlocks& m = mats[i];
             if (m.whole || !peer_path(m.height, m.width)) continue;
@@ -263,6 +274,7 @@ class RowShardBackend : public GpuBackend {
             // my rows of every rank's column block: remote stores, contiguous per destination
             gpu_check(msgpu_peers_pack_push(peers_, m.dev, m.height / N, m.width, col[i].seg, col[i].off));
         }
+        rs_trace(rank(), "pushed");
         if (any_peer) gpu_check(msgpu_peers_barrier(peers_));  // every rank's rows have landed in this rank's column blocks
         for (size_t i = 0; i < mats.size(); i++) {
             const RowBlocks& m = mats[i];
@@ -302,6 +314,7 @@ class RowShardBackend : public GpuBackend {
             h->whole.push_back(whole);
             h->shapes.push_back({m.height << lb, m.width});
         }
+        rs_trace(rank(), "ldes done");
         // the root barrier inside commit_shards orders every rank's loads from the column blocks before their release
         return commit_shards(h, root);
     }
@@ -386,6 +399,7 @@ class RowShardBackend : public GpuBackend {
         }
         // the ranks' totals: offsets of the row blocks' running sums, and the circuits' totals for the accumulator chain
         std::vector<uint64_t> all(sums.size() * (size_t)N);
+        rs_trace(d, "stage2 sums allgather");
         comm_.allgather(sums.data(), all.data(), sums.size() * 8);
         intermediate.clear();
         for (size_t p = 0; p < active_.size(); p++) {
@@ -438,6 +452,7 @@ class RowShardBackend : public GpuBackend {
         h->n_shards = N;
         h->shard = d;
         for (auto& j : jobs) {
+            rs_trace(rank(), "quotient job", j.circuit, j.log_degree);
             const size_t H = (size_t)1 << (j.log_degree + lb), Ls = H / (size_t)N, nq = (size_t)1 << (j.log_degree + j.log_quotient_degree);
             const size_t q = (size_t)1 << j.log_quotient_degree;
             // shards spanning the quotient domain, the rows of it held here, and the shard that holds their next rows
@@ -472,16 +487,21 @@ class RowShardBackend : public GpuBackend {
                 cur[k] = sh->views[i];
                 nxt[k] = sh->views[i];  // never read when the source has no next-row reference
                 nw[k] = (uint32_t)w;
-                if (lo[k] >= hi[k] || dn == (size_t)d) continue;
-                if (sh->whole[i]) { nxt[k] = sh->whole_rows_of(i, (int)dn); continue; }
-                if (Np > 1) {
+                // every condition that skips the exchange must hold on ALL ranks alike (a collective under NCCL): no next-row
+                // reference, the whole matrix here, or a trace step that stays inside the shard (q = 0 mod Np)
+                if (lo[k] >= hi[k]) continue;
+                if (sh->whole[i]) {
+                    if (dn != (size_t)d) nxt[k] = sh->whole_rows_of(i, (int)dn);
+                    continue;
+                }
+                if (Np > 1 && (q & (Np - 1)) != 0) {
                     // fetch columns [lo, hi) of shard dn: rank e sends those columns of its quotient-domain rows to the rank whose
                     // next rows they are (a permutation of the ranks: one all-to-all call)
                     const size_t wc = hi[k] - lo[k], rows = std::min(Ls, nq), bytes = rows * wc * 8;
                     std::vector<uint64_t> sb(N, 0), rb(N, 0);
                     DevPtr packed(ctx_, bytes);
                     bool need = false;
-                    if ((size_t)d < Np) {
+                    if ((size_t)d < Np && dn != (size_t)d) {
                         for (size_t e = 0; e < Np; e++)
                             if (next_of(e) == (size_t)d && e != (size_t)d) sb[e] = bytes;
                         gpu_check(msgpu_extract_columns_dev(ctx_, sh->views[i], rows, w, lo[k], hi[k], packed.u()));
@@ -489,6 +509,7 @@ class RowShardBackend : public GpuBackend {
                         need = true;
                     }
                     halos.emplace_back(ctx_, need ? bytes : 8);
+                    rs_trace(rank(), "halo a2a", (size_t)k, bytes);
                     comm_.alltoall_dev(packed.p, sb.data(), halos.back().p, rb.data());
                     if (need) {
                         nxt[k] = halos.back().u();
@@ -504,6 +525,7 @@ class RowShardBackend : public GpuBackend {
             gpu_check(msgpu_quotient_values_shard(ctx_, programs_[j.circuit], cur, nxt, nw, nc0, row0, n_local, next_row0, j.log_degree,
                                                   j.log_quotient_degree, pub, a, mine.u()));
             halos.clear();
+            rs_trace(rank(), "quotient values allgather", Ls * 16);
             comm_.allgather_dev(mine.p, all.p, Ls * 16);  // the first nq rows of the result are the quotient domain
             uint64_t* lde = nullptr;
             gpu_check(msgpu_quotient_finish(ctx_, all.u(), j.log_degree, j.log_quotient_degree, lb, &lde));
@@ -625,6 +647,7 @@ class RowShardOpenDevice : public OpenDevice {
         uint64_t n_sums = 0;
         gpu_check(msgpu_open_begin_shard(ctx_, pds.size(), pds.data(), modes.data(), (uint32_t)d, (uint32_t)N, d == fri_owner_ ? 1 : 0, npts.data(),
                                          pts.data(), log_blowup, &op_, &n_values_, &n_sums));
+        rs_trace(d, "open_begin done", n_sums);
         // barycentric sums of all ranks, added in the field
         std::vector<uint64_t> mine(std::max<uint64_t>(n_sums, 1)), all((size_t)N * std::max<uint64_t>(n_sums, 1));
         gpu_check(msgpu_open_sums(op_, mine.data()));
@@ -662,6 +685,7 @@ class RowShardOpenDevice : public OpenDevice {
         const int N = comm_.world(), d = comm_.rank();
         uint64_t a[2] = {alpha.c[0].v, alpha.c[1].v}, n_in = 0;
         uint32_t lm = 0;
+        rs_trace(d, "reduce");
         gpu_check(msgpu_open_reduce(op_, a, &n_in, &lm));
         // every rank holds rows of every height: the shards (16 bytes per LDE row) are added into the owner's full-length vectors
         for (uint64_t k = 0; k < n_in && N > 1; k++) {
@@ -697,6 +721,7 @@ class RowShardOpenDevice : public OpenDevice {
         for (size_t l = cur_len_; l > stop_len; l >>= 1) rounds++;
         const size_t final_len = cur_len_ >> rounds;
         std::vector<u8> blob(rounds * 40 + final_len * 16);
+        rs_trace(comm_.rank(), "fri commit phase", rounds);
         if (comm_.rank() == fri_owner_) {
             const std::vector<u8>& buf = ch.input_buffer();
             if (pow_bits == 0 && !buf.empty() && buf.size() <= 960 && rounds <= 64) {
@@ -764,6 +789,7 @@ class RowShardOpenDevice : public OpenDevice {
                       std::vector<std::vector<BatchOpening>>& rounds_out, std::vector<std::vector<BatchOpening>>& layers_out) override {
         const int N = comm_.world(), d = comm_.rank();
         const size_t n = indices.size(), R = handles_.size();
+        rs_trace(d, "open_queries", n, R);
         const unsigned log_n_shards = log2_strict((size_t)N);
         // per round: the round's index of every query, its holder and the index inside the holder's shard
         std::vector<std::vector<size_t>> ridx(R, std::vector<size_t>(n)), holder(R, std::vector<size_t>(n));
