@@ -456,14 +456,14 @@ def rowshard_prove_leg(args, ms, msd, ctx, rank, world, kind, log_heights, steps
         torch.cuda.synchronize()
         if it == steps:
             rs.comm.seconds.clear()
-            rs.comm.bytes_dev = 0
+            bytes0 = rs.bytes_dev
         t0 = time.perf_counter()
         proof = rs.prove(mine, claims_p, heights=heights)
         if it:
             times.append((time.perf_counter() - t0) * 1e3)
     out = {"kind": kind, "log_heights": log_heights, "ms": msd.max_over_ranks(float(np.median(times))), "stages_ms_rank0": rs.last_stage_ms,
            "proof_bytes": len(proof), "digest": hashlib.sha256(proof).hexdigest(),
-           "device_bytes_exchanged_this_rank": int(rs.comm.bytes_dev),
+           "device_bytes_exchanged_this_rank": int(rs.bytes_dev - bytes0), "peer_memory": rs.peer_memory,
            "comm_ms_this_rank": {k: round(v * 1e3, 3) for k, v in rs.comm.seconds.items()},
            "timing": "host wall clock around the call on every rank (row blocks of pinned host traces in, proof bytes out), median, max over ranks"}
     out["all_ranks_same_proof"] = len(set(msd.gather_digests([bytes.fromhex(out["digest"])]))) == 1
@@ -675,7 +675,8 @@ def main():
         rs = msd.RowShardProver(ctx, rs_system)
         ms_step, ms_host, rs_roots, h2d = rowshard_commit_leg(args, ms, msd, ctx, rs, rank, world, args.steps, max(args.warmup, 3))
         n_commits = 2 * (args.steps + max(args.warmup, 3)) * len(stages)
-        rs_bytes_per_step = rs.comm.bytes_dev // max(n_commits // len(stages), 1)
+        rs_bytes_per_step = rs.bytes_dev // max(n_commits // len(stages), 1)
+        rs_peer = rs.peer_memory
         rs.close()
         value = elems / (ms_step / 1e3) / 1e9
         e2e_value = elems / (ms_host / 1e3) / 1e9
@@ -797,6 +798,8 @@ def main():
             "prove_big": prove_big, "replicas": replicas,
             "sharding": None if world == 1 else {
                 "mode": "every committed matrix split by rows over the ranks (host/rowshard_backend.hpp): ONE job, the same work at every N",
+                "exchange": ("peer memory: NVLink stores / loads issued by this library's kernels into CUDA-IPC windows (csrc/peer.cu), "
+                             "flag barriers in peer memory; no NCCL call on the data path") if rs_peer else "NCCL all-to-all / all-gather",
                 "device_bytes_exchanged_this_rank_per_step": int(rs_bytes_per_step), "roots_equal_single_gpu_commit": rs_roots_ok},
         }))
     ctx.close()

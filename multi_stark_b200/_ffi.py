@@ -184,6 +184,7 @@ HOST_SIGNATURES = {
     "msh_rowshard_commit": (C.c_int, [C.c_void_p, c_vpp, c_u64p, c_u64p, C.c_uint64, C.c_int, C.c_void_p]),
     "msh_rowshard_shardable": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
     "msh_rowshard_peer_memory": (C.c_int, [C.c_void_p]),
+    "msh_rowshard_peer_bytes": (C.c_uint64, [C.c_void_p]),
     "msh_rowshard_prover_create": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "msh_dist_prover_create": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "msh_fib_trace": (None, [C.c_uint64, C.c_void_p]),

@@ -476,6 +476,11 @@ class RowShardProver:
         return self.H.msh_rowshard_shardable(self.h, int(height), int(width)) == 1
 
     @property
+    def bytes_dev(self):
+        """device bytes this rank exchanged so far: NCCL collectives + NVLink loads / stores of the peer-memory kernels"""
+        return int(self.comm.bytes_dev) + int(self.H.msh_rowshard_peer_bytes(self.h))
+
+    @property
     def peer_memory(self):
         """True when the ranks exchange matrices through each other's device memory (csrc/peer.cu) rather than NCCL"""
         return self.H.msh_rowshard_peer_memory(self.h) == 1

@@ -188,6 +188,10 @@ int msh_rowshard_peer_memory(msh_prover* p) {
     auto* be = dynamic_cast<RowShardBackend*>(p->backend.get());
     return be && be->peer_memory() ? 1 : 0;
 }
+uint64_t msh_rowshard_peer_bytes(msh_prover* p) {
+    auto* be = dynamic_cast<RowShardBackend*>(p->backend.get());
+    return be ? be->peer_bytes() : 0;
+}
 // Pcs::commit over the row shards alone (bench.py's strong-scaling step): mats[i] = this rank's natural-order ROW BLOCK of matrix
 // i (rows [d h / N, (d + 1) h / N) when RowShardProver.shardable(h, w), else the whole matrix), DEVICE pointers (host = 0) or
 // HOST pointers to the FULL matrices (host = 1: each rank uploads the rows it reads). Every rank gets the root.

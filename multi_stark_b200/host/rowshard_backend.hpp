@@ -123,6 +123,8 @@ class RowShardBackend : public GpuBackend {
         if (peers_) msgpu_peers_destroy(peers_);
     }
     bool peer_memory() const { return peers_ != nullptr; }
+    // bytes this rank wrote into / read from the other ranks' windows so far (matrix data; roots and flags not counted)
+    uint64_t peer_bytes() const { return peer_bytes_; }
     // matrices that take the peer-memory path: split by columns for the NTT, and tall enough for a two-pass transform
     bool peer_path(size_t height, size_t width) const { return peers_ && shardable(height, width); }
     void free_blocks(RowBlocks& b) {
@@ -273,6 +275,10 @@ class RowShardBackend : public GpuBackend {
             held.push_back(lde[i]);
             // my rows of every rank's column block: remote stores, contiguous per destination
             gpu_check(msgpu_peers_pack_push(peers_, m.dev, m.height / N, m.width, col[i].seg, col[i].off));
+            {   // NVLink bytes of this matrix: rows pushed to the other ranks' column blocks + shard rows pulled from theirs
+                const size_t w = m.width, base = w / N, rem = w % N, wd = base + (d < rem ? 1 : 0);
+                peer_bytes_ += (m.height / N) * (w - wd) * 8 + ((m.height << lb) / N) * (w - wd) * 8;
+            }
         }
         rs_trace(rank(), "pushed");
         if (any_peer) gpu_check(msgpu_peers_barrier(peers_));  // every rank's rows have landed in this rank's column blocks
@@ -613,6 +619,7 @@ class RowShardBackend : public GpuBackend {
         }
     }
     msgpu_peers* peers_ = nullptr;
+    uint64_t peer_bytes_ = 0;
     RowShardComm comm_;
     std::vector<RowBlocks> main_;  // the natural-order traces (row blocks or whole), kept for the stage-2 construction
     int claims_rank_ = 0;
