@@ -325,6 +325,28 @@ class GpuPcs:
                                            root.ctypes.data_as(C.c_void_p)))
         return root, ProverData(self.ctx, h, root)
 
+    def commit_ldes_blocks(self, mats):
+        """`commit_ldes` where some LDEs still exist as COLUMN BLOCKS (msgpu_commit_ldes_blocks_dev): mats = list of
+        (dst_device_ptr, rows, cols, blocks) with blocks = None (the matrix is already at dst) or a list of
+        (block_device_ptr, block_cols) -- dense rows x block_cols matrices in column order, possibly in another GPU's memory.
+        Such a matrix is written to dst by the pass that hashes its rows. Returns (root, ProverData)."""
+        n = len(mats)
+        nb = max([len(b) for _, _, _, b in mats if b] or [0])
+        ptrs = (C.c_void_p * n)(*[p for p, _, _, _ in mats])
+        hs = (C.c_uint64 * n)(*[r for _, r, _, _ in mats])
+        ws = (C.c_uint64 * n)(*[c for _, _, c, _ in mats])
+        bp = (C.c_void_p * max(n * nb, 1))()
+        bw = (C.c_uint64 * max(n * nb, 1))()
+        for i, (_, _, _, blocks) in enumerate(mats):
+            for b, (ptr, cols) in enumerate(blocks or []):
+                bp[i * nb + b] = ptr
+                bw[i * nb + b] = cols
+        h = C.c_void_p()
+        root = np.zeros(32, dtype=np.uint8)
+        check(self.L.msgpu_commit_ldes_blocks_dev(self.ctx.h, ptrs, hs, ws, n, nb, bp if nb else None, bw if nb else None, 0, C.byref(h),
+                                                  root.ctypes.data_as(C.c_void_p)))
+        return root, ProverData(self.ctx, h, root)
+
     def get_evaluations_on_domain(self, pdata, idx, log_quotient_size):
         """View of the committed LDE on the coset GENERATOR * H_{2^log_quotient_size}: the first
         2^log_quotient_size stored rows, bit-reversed (src/prover.rs:454-468).

@@ -25,13 +25,14 @@ def free_port():
     return p
 
 
-def run_world(tmp_path, world, kind, log_heights, owners, params):
+def run_world(tmp_path, world, kind, log_heights, owners, params, backend="gloo", extra_env=None):
     port = free_port()
     prefix = str(tmp_path / "dist")
     procs = []
     for r in range(world):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_dist_worker.py"), "gloo", kind,
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   **(extra_env or {}))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_dist_worker.py"), backend, kind,
                                        ",".join(map(str, log_heights)), owners, prefix, json.dumps(params)], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = []

@@ -12,6 +12,7 @@ from tests import _oracle as orc
 from tests.test_oracle_hash import KAT_MSG, KAT_OUT, KAT_STATE, leaf, b3
 
 pytestmark = pytest.mark.gpu
+P = orc.P
 
 
 @pytest.fixture(scope="module")
@@ -118,6 +119,71 @@ def test_pcs_commit_matches_oracle(gpu, oracle, shapes, lb):
     for p, _, _ in dptrs:
         ctx.free(p)
     pd3.free(); pd2.free(); pd.free()
+
+
+def _split_columns(m, widths):
+    out, c = [], 0
+    for w in widths:
+        out.append(np.ascontiguousarray(m[:, c:c + w]))
+        c += w
+    assert c == m.shape[1]
+    return out
+
+
+@pytest.mark.parametrize("shapes", [
+    # (rows, block widths or None): matrices of one commitment, commit order
+    [(4096, [7, 7])],                                         # one matrix from two blocks: staged leaf kernel
+    [(256, None), (4096, [2, 2, 2, 2, 2, 2, 1, 1])],          # BASELINE cfg1 stage-1 shapes split over 8 ranks + a whole byte table
+    [(2048, [4, 4, 3, 3, 3, 3, 3, 3]), (2048, [1, 1, 0, 0])],  # two assembled matrices in one class, zero-width blocks
+    [(1024, [32, 32, 32, 32, 32, 32, 32, 32])],               # 256 columns: the streamed leaf kernel
+    [(512, [100, 100, 56]), (512, None), (1024, [3, 2])],     # streamed, mixed with a plain matrix and a taller class
+    [(64, [1, 1]), (64, [1, 1]), (64, [2, 1]), (64, [1, 2]), (64, [3, 3])],  # five assembled matrices: one falls back to its own gather
+    [(8, [6000, 3000])],                                      # rows too wide to stage: gather pass + direct kernel
+])
+def test_commit_from_column_blocks(gpu, shapes):
+    """msgpu_commit_ldes_blocks_dev: matrices that still exist as column blocks (the row shard of a column-sharded LDE, read from
+    the peers' windows in the multi-GPU prover) are assembled by the leaf-hash pass. Same root, same digest layers and the same
+    row-major matrices as committing the assembled matrices."""
+    ms, ctx = gpu
+    rng = np.random.default_rng(5)
+    pcs = ms.GpuPcs(ctx, 1)
+    whole, args, frees, dsts = [], [], [], []
+    for rows, widths in shapes:
+        w = sum(widths) if widths else 5
+        m = orc.rand_matrix(rng, rows, w)
+        whole.append(m)
+        if widths is None:
+            p = ctx.upload(m)
+            frees.append(p)
+            args.append((p, rows, w, None))
+            dsts.append(None)
+            continue
+        blocks = []
+        for b in _split_columns(m, widths):
+            bp = ctx.upload(b) if b.shape[1] else ctx.malloc(8)
+            frees.append(bp)
+            blocks.append((bp, b.shape[1]))
+        dst = ctx.malloc(rows * w * 8)
+        frees.append(dst)
+        dsts.append(dst)
+        args.append((dst, rows, w, blocks))
+    root, pd = pcs.commit_ldes_blocks(args)
+    ref_ptrs = [(ctx.upload(m), m.shape[0], m.shape[1]) for m in whole]
+    root_ref, pd_ref = pcs.commit_ldes(ref_ptrs)
+    assert bytes(root) == bytes(root_ref)
+    for i, m in enumerate(whole):
+        assert np.array_equal(pd.read_rows(i), m), "matrix %d was not assembled correctly" % i
+    for a, b in zip(pd.layers(), pd_ref.layers()):
+        assert np.array_equal(a, b)
+    max_h = max(m.shape[0] for m in whole)
+    idx = [0, max_h - 1, 3 % max_h]
+    got, want = pd.open_batch(idx), pd_ref.open_batch(idx)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    pd.free(); pd_ref.free()
+    for p, _, _ in ref_ptrs:
+        ctx.free(p)
+    for p in frees:
+        ctx.free(p)
 
 
 def test_commit_full_size_root_of_roots(gpu):

@@ -28,7 +28,7 @@ for r in rows[1:]:
         d["us"] += v
     else:
         d["dram_bytes"] += v
-stage_of = {"k_ntt_strided": "lde", "k_ntt_block": "lde", "k_hash_rows_staged": "merkle", "k_hash_rows_direct": "merkle",
+stage_of = {"k_ntt_strided": "lde", "k_ntt_block": "lde", "k_lde_mid": "lde", "k_hash_rows_staged": "merkle", "k_hash_rows_direct": "merkle",
             "k_merkle_subtree": "merkle"}
 out = {"steps_captured": steps, "kernels": {}, "stages": {}}
 for k, d in agg.items():
