@@ -716,6 +716,19 @@ def main():
                 st["dram_traffic_bytes_per_step"] = c["dram_bytes_per_step"]
         traffic = dom.get("dram_traffic_bytes_per_step")
         top = max((k for k in kernels if k["stage"] == dom["stage"]), key=lambda k: k["ms_per_step"])
+        # the dominant kernel on its own: k_lde_mid reads every evaluation once and writes every LDE element once, i.e. it
+        # moves the whole stage's algorithmic bytes by itself (the strided passes around it are in-place re-reads)
+        dom_kernel = {"name": top["kernel"], "launches_per_step": top["launches_per_step"], "ms_per_step": top["ms_per_step"]}
+        if top["kernel"] in ("k_lde_mid", "k_hash_rows_staged", "k_hash_rows_stream"):
+            kb = dom["algorithmic_bytes"] if top["kernel"] == "k_lde_mid" else sum(
+                8 * (m.shape[0] << B) * m.shape[1] + 32 * (m.shape[0] << B) for st in stages for m in st)
+            dom_kernel.update({"algorithmic_bytes_per_launch": kb / top["launches_per_step"],
+                               "achieved_gbs": kb / (top["ms_per_step"] / 1e3) / 1e9,
+                               "frac": kb / (top["ms_per_step"] / 1e3) / 1e9 / peak})
+            kc = (counters or {}).get("kernels", {}).get(top["kernel"]) if default_shape else None
+            if kc:
+                dom_kernel["dram_traffic_bytes_per_launch"] = kc["dram_bytes_per_step"] / kc["launches_per_step"]
+                dom_kernel["int_pipe_frac_of_mixed_peak"] = kc["thread_inst_per_step"] / (top["ms_per_step"] / 1e3) / 1e9 / ipk["mixed"]
         roofline = {"bound": "hbm", "stage": "%s (%d launches/step)" % (dom["stage"], dom["launches_per_step"]),
                     "kernel": "%s (%d launches/step, %.3f ms/step)" % (top["kernel"], top["launches_per_step"], top["ms_per_step"]),
                     "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
@@ -723,7 +736,7 @@ def main():
                     "traffic_note": "dram read+write bytes per launch (ncu, %s); achieved/frac use ALGORITHMIC bytes per launch" % counters_file,
                     "peak_source": peak_src, "algorithmic_bytes_per_step": dom["algorithmic_bytes"],
                     "algorithmic_bytes_per_launch": dom["algorithmic_bytes"] / dom["launches_per_step"],
-                    "share_of_step": dom["ms_per_step"] / ms_step,
+                    "share_of_step": dom["ms_per_step"] / ms_step, "dominant_kernel": dom_kernel,
                     "binding_resource": "INT32 pipes (ALU + FMA-heavy): see int_pipe; HBM is not the bound for this stage",
                     "int_pipe": {"unit": "G thread-inst/s", "peak_alu_only": ipk["alu"], "peak_imad_only": ipk["imad"],
                                  "peak_mixed": ipk["mixed"], "peak_source": "msgpu_measure_int_peak, live, CUDA events",
