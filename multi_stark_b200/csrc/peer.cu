@@ -11,6 +11,7 @@
 // window is deterministic (first fit, lowest offset): every rank performs the same sequence of calls with the same sizes, so a
 // block has the same (segment, offset) on every rank and no addresses are ever exchanged.
 #include "capi_common.hpp"
+#include "peer_heap.hpp"
 
 #include <cstring>
 #include <map>
@@ -20,7 +21,6 @@ using namespace msg;
 namespace {
 constexpr int kMaxPeers = MSGPU_MAX_PEERS;
 constexpr size_t kFlagPage = 4096;      // start of segment 0: barrier flags, error word, root ring
-constexpr size_t kAlign = 512;
 constexpr size_t kErrOff = 512;         // u32 error word
 constexpr size_t kRingOff = 1024;       // 2 slots x kMaxPeers x 32 bytes
 
@@ -111,8 +111,7 @@ struct msgpu_peers {
         size_t bytes = 0;
         char* base[kMaxPeers] = {};
         bool opened = false;
-        std::map<size_t, size_t> free_list;   // offset -> size
-        std::map<size_t, size_t> used;        // offset -> size
+        FirstFitHeap heap;
     };
     std::vector<Seg> segs;
     unsigned long long epoch = 0, ring = 0;
@@ -157,7 +156,7 @@ int msgpu_peers_segment_create(msgpu_peers* p, uint64_t bytes, uint8_t* handle64
             first = kFlagPage;
         }
         MSG_CUDA(cudaDeviceSynchronize());
-        s.free_list[first] = s.bytes - first;
+        s.heap = FirstFitHeap(first, s.bytes);
         cudaIpcMemHandle_t hd;
         cudaError_t e = cudaIpcGetMemHandle(&hd, base);
         if (e != cudaSuccess) {
@@ -198,21 +197,15 @@ int msgpu_peers_alloc(msgpu_peers* p, uint64_t bytes, uint32_t* seg, uint64_t* o
     int rc = 1;
     int g = guard([&] {
         MSG_REQUIRE(p && seg && off, "peers: null argument");
-        const size_t need = std::max<size_t>((bytes + kAlign - 1) / kAlign * kAlign, kAlign);
         for (size_t s = 0; s < p->segs.size(); s++) {
             auto& sg = p->segs[s];
             if (!sg.opened) continue;
-            for (auto it = sg.free_list.begin(); it != sg.free_list.end(); ++it) {
-                if (it->second < need) continue;
-                const size_t o = it->first, sz = it->second;
-                sg.free_list.erase(it);
-                if (sz > need) sg.free_list[o + need] = sz - need;
-                sg.used[o] = need;
-                *seg = (uint32_t)s;
-                *off = o;
-                rc = 0;
-                return;
-            }
+            const size_t o = sg.heap.alloc((size_t)bytes);
+            if (o == FirstFitHeap::npos) continue;
+            *seg = (uint32_t)s;
+            *off = o;
+            rc = 0;
+            return;
         }
     });
     return g != MSGPU_OK ? g : rc;
@@ -221,24 +214,7 @@ int msgpu_peers_alloc(msgpu_peers* p, uint64_t bytes, uint32_t* seg, uint64_t* o
 int msgpu_peers_free_block(msgpu_peers* p, uint32_t seg, uint64_t off) {
     return guard([&] {
         MSG_REQUIRE(p && seg < p->segs.size(), "peers: no such segment");
-        auto& sg = p->segs[seg];
-        auto it = sg.used.find((size_t)off);
-        MSG_REQUIRE(it != sg.used.end(), "peers: not a live block");
-        size_t o = it->first, sz = it->second;
-        sg.used.erase(it);
-        auto nx = sg.free_list.lower_bound(o);
-        if (nx != sg.free_list.end() && o + sz == nx->first) {
-            sz += nx->second;
-            nx = sg.free_list.erase(nx);
-        }
-        if (nx != sg.free_list.begin()) {
-            auto pv = std::prev(nx);
-            if (pv->first + pv->second == o) {
-                pv->second += sz;
-                return;
-            }
-        }
-        sg.free_list[o] = sz;
+        MSG_REQUIRE(p->segs[seg].heap.free((size_t)off), "peers: not a live block");
     });
 }
 

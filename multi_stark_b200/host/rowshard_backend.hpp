@@ -241,6 +241,7 @@ class RowShardBackend : public GpuBackend {
             gpu_check(msgpu_peers_barrier(peers_));
             const uint8_t* pp = gathered;
             gpu_check(msgpu_tree_from_digests(ctx_, 1, &hh, &pp, &h->top, root.data()));
+            gpu_check(msgpu_peers_check(peers_));  // a barrier of this commitment timed out: fail here, not with a wrong root
             rs_trace(rank(), "root");
             return h;
         }
