@@ -89,7 +89,17 @@ COMM_WORKER = textwrap.dedent("""
     # broadcast from rank 1
     buf = np.full(5, 7 + r, dtype=np.uint64)
     assert st.bcast_host(None, buf.ctypes.data, 40, 1) == 0
-    print(json.dumps({"rank": r, "recv": recv.tolist(), "buf": buf.tolist(), "errors": comm.errors}))
+    # the staged device exchanges announce (sequence number, kind) first: ranks that make different sequences of device
+    # collectives (a rank-dependent branch around one: a hang under NCCL) are told apart on every rank
+    comm._same_call(1)
+    comm._same_call(2)
+    try:
+        comm._same_call(1 if r == 0 else 2)
+        mismatch = False
+    except RuntimeError:
+        mismatch = True
+    print(json.dumps({"rank": r, "recv": recv.tolist(), "buf": buf.tolist(), "errors": comm.errors, "peer_memory": comm.peer_memory,
+                      "mismatch_detected": mismatch}))
     dist.destroy_process_group()
 """)
 
@@ -113,6 +123,8 @@ def test_comm_callbacks_over_gloo(tmp_path):
         assert d["errors"] == []
         assert d["recv"] == [0, 1, 2, 100, 101, 102]
         assert d["buf"] == [8] * 5
+        assert d["peer_memory"] == 0          # gloo ranks never map each other's device memory
+        assert d["mismatch_detected"] is True
 
 
 def test_assign_owners_keeps_height_classes_together():
