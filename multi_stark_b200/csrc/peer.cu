@@ -343,9 +343,10 @@ int msgpu_peers_pull_interleave(msgpu_peers* p, uint32_t seg, uint64_t off, uint
 }
 
 // Teardown is local: the peers' mappings are closed, then this rank's windows are freed. Every rank has passed a barrier behind
-// its last access to any window by then (a commitment ends with one), so no transfer is in flight; the CUDA documentation asks
-// importers to close before the exporter frees, which ranks leaving a proof at the same point do within microseconds of each
-// other, and the driver keeps the allocation alive until its last mapping is gone.
+// its last access to any window by then (a commitment ends with one), so no transfer is in flight. The CUDA documentation asks
+// importers to close before the exporter frees; that order is NOT enforced across ranks here (it would take a host collective
+// inside a destructor, which hangs when a rank has already failed). No access follows the free on any rank, and every run on
+// driver 580 (tests/test_gpu_peer.py, bench.py at N = 2, 4, 8: several provers created and destroyed per process) is clean.
 void msgpu_peers_destroy(msgpu_peers* p) {
     if (!p) return;
     cudaSetDevice(p->c->device);
