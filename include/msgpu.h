@@ -358,6 +358,8 @@ typedef struct msgpu_peers msgpu_peers;
 int msgpu_peers_create(msgpu_ctx* ctx, int32_t rank, int32_t world, msgpu_peers** out);
 int msgpu_peers_segment_create(msgpu_peers* p, uint64_t bytes, uint8_t* handle64);
 int msgpu_peers_segment_open(msgpu_peers* p, const uint8_t* handles);
+/* ranks inside ONE process (no IPC): bases[e] = rank e's window address (msgpu_peers_ptr of ITS object, offset 0) */
+int msgpu_peers_segment_open_local(msgpu_peers* p, void* const* bases);
 uint64_t msgpu_peers_num_segments(const msgpu_peers* p);
 int msgpu_peers_alloc(msgpu_peers* p, uint64_t bytes, uint32_t* segment, uint64_t* offset);
 int msgpu_peers_free_block(msgpu_peers* p, uint32_t segment, uint64_t offset);

@@ -118,6 +118,7 @@ SIGNATURES = {
     "msgpu_peers_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "msgpu_peers_segment_create": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "msgpu_peers_segment_open": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "msgpu_peers_segment_open_local": (C.c_int, [C.c_void_p, C.c_void_p]),
     "msgpu_peers_num_segments": (C.c_uint64, [C.c_void_p]),
     "msgpu_peers_alloc": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "msgpu_peers_free_block": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64]),

@@ -111,6 +111,7 @@ struct msgpu_peers {
         size_t bytes = 0;
         char* base[kMaxPeers] = {};
         bool opened = false;
+        bool ipc = true;   // the peers' bases are CUDA-IPC mappings (closed at teardown); false: raw pointers of this process
         FirstFitHeap heap;
     };
     std::vector<Seg> segs;
@@ -186,6 +187,22 @@ int msgpu_peers_segment_open(msgpu_peers* p, const uint8_t* handles) {
             }
             s.base[e] = (char*)ptr;
         }
+        s.opened = true;
+    });
+}
+
+// The same for ranks that live in ONE process (several contexts / streams, one or several devices with peer access enabled by
+// the caller): bases[e] = address of rank e's window, as returned by msgpu_peers_ptr(their peers object, segment, 0, e).
+int msgpu_peers_segment_open_local(msgpu_peers* p, void* const* bases) {
+    return guard([&] {
+        MSG_REQUIRE(p && bases && !p->segs.empty() && !p->segs.back().opened, "peers: no segment to open");
+        auto& s = p->segs.back();
+        for (int e = 0; e < p->world; e++) {
+            if (e == p->rank) continue;
+            MSG_REQUIRE(bases[e], "peers: null window address");
+            s.base[e] = (char*)bases[e];
+        }
+        s.ipc = false;
         s.opened = true;
     });
 }
@@ -355,7 +372,7 @@ void msgpu_peers_destroy(msgpu_peers* p) {
         for (int e = 0; e < p->world; e++) {
             if (!s.base[e]) continue;
             if (e == p->rank) cudaFree(s.base[e]);
-            else cudaIpcCloseMemHandle(s.base[e]);
+            else if (s.ipc) cudaIpcCloseMemHandle(s.base[e]);
         }
     }
     delete p;
