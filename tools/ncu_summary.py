@@ -11,6 +11,7 @@ WANT = [
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
     ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu%"),
     ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma%"),
+    ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "fmaheavy_busy%"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"),
     ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
