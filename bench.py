@@ -208,6 +208,22 @@ def step_counters():
         return None, None
 
 
+def ncu_pipe_busy():
+    """Per-kernel ALU / FMA-heavy pipe busy percentages from the committed `ncu --set full` capture of the same kernels
+    (tools/ncu_pipe_busy.py): static annotation of the bench line, labelled with its source file."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "pipe_busy_*.json")))
+    if not files:
+        return None
+    try:
+        with open(files[-1]) as f:
+            d = json.load(f)
+        return {"file": os.path.basename(files[-1]), "what": d.get("what"),
+                "kernels": {k: v for k, v in d.get("kernels", {}).items() if not k.startswith("k_fill")}}
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -742,7 +758,7 @@ def main():
                                  "peak_mixed": ipk["mixed"], "peak_source": "msgpu_measure_int_peak, live, CUDA events",
                                  "achieved": dom.get("int_pipe", {}).get("achieved_ginst_s"),
                                  "frac": dom.get("int_pipe", {}).get("frac_of_mixed_peak")},
-                    "stages": stages_out, "kernels": kernels}
+                    "stages": stages_out, "kernels": kernels, "ncu_pipe_busy": ncu_pipe_busy()}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
