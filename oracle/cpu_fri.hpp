@@ -18,6 +18,7 @@
 #include "cpu_eval.hpp"
 #include "cpu_mmcs.hpp"
 #include <list>
+#include <omp.h>
 
 namespace orc {
 using namespace msh;
@@ -73,17 +74,34 @@ class CpuOpenDevice : public OpenDevice {
                     size_t h = lde.height() >> log_blowup_, w = lde.width;
                     unsigned lh = log2_strict(h);
                     Matrix nat(h, w);
-                    for (size_t i = 0; i < h; i++) std::copy(lde.row(reverse_bits_len(i, lh)), lde.row(reverse_bits_len(i, lh)) + w, nat.row(i));
-                    Matrix coeffs = coset_idft_batch(std::move(nat), Fp(GL_GENERATOR));
-                    for (const Fp2& z : r.points[m]) {
-                        std::vector<Fp2> ys(w, Fp2::zero());
-                        long long ww = (long long)w;
+                    {
+                        const long long hh = (long long)h;
 #pragma omp parallel for schedule(static)
-                        for (long long c = 0; c < ww; c++) {
-                            Fp2 acc = Fp2::zero();
-                            for (size_t j = h; j-- > 0;) acc = acc * z + coeffs.row(j)[c];
-                            ys[c] = acc;
+                        for (long long i = 0; i < hh; i++) {
+                            const Fp* src = lde.row(reverse_bits_len((size_t)i, lh));
+                            std::copy(src, src + w, nat.row((size_t)i));
                         }
+                    }
+                    Matrix coeffs = coset_idft_batch(std::move(nat), Fp(GL_GENERATOR));
+                    // Horner in row blocks: block b evaluates sum_j c[j0 + j] z^j for every column at once (row-major reads),
+                    // the blocks are combined with z^{j0}. Exact field arithmetic: the same values as one long Horner chain.
+                    const size_t n_blocks = std::min<size_t>(h, (size_t)omp_get_max_threads() * 8);
+                    const size_t bl = (h + n_blocks - 1) / n_blocks;
+                    for (const Fp2& z : r.points[m]) {
+                        std::vector<Fp2> part(n_blocks * w, Fp2::zero());
+#pragma omp parallel for schedule(static)
+                        for (long long b = 0; b < (long long)n_blocks; b++) {
+                            const size_t j0 = (size_t)b * bl, j1 = std::min(h, j0 + bl);
+                            Fp2* acc = part.data() + (size_t)b * w;
+                            for (size_t j = j1; j-- > j0;) {
+                                const Fp* row = coeffs.row(j);
+                                for (size_t c = 0; c < w; c++) acc[c] = acc[c] * z + row[c];
+                            }
+                        }
+                        std::vector<Fp2> ys(w, Fp2::zero());
+                        const Fp2 zb = z.pow(bl);
+                        for (size_t b = n_blocks; b-- > 0;)  // Horner over the blocks with z^bl
+                            for (size_t c = 0; c < w; c++) ys[c] = ys[c] * zb + part[b * w + c];
                         per_point.push_back(std::move(ys));
                     }
                 }
